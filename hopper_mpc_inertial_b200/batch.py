@@ -1,0 +1,183 @@
+"""Batched hopper MPC on one B200: torch CUDA tensors as the batch container over the C ABI.
+
+All tensors are float64, structure-of-arrays with the hopper index LAST (contiguous), exactly the
+layout include/hmpc.h documents: x_in (12, B), x_ref (N, 12, B), pf (N, 3, B), U (N, 6, B) ...
+``soa()`` / ``aos()`` convert from / to the batch-first layout.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def soa(t: torch.Tensor) -> torch.Tensor:
+    """(B, ...) -> (..., B) contiguous."""
+    return t.movedim(0, -1).contiguous()
+
+
+def aos(t: torch.Tensor) -> torch.Tensor:
+    """(..., B) -> (B, ...) contiguous."""
+    return t.movedim(-1, 0).contiguous()
+
+
+def cbits_from_C(Cmat) -> np.ndarray:
+    """Contact schedule matrix (B, N) of 0/1 floats (gait_map, robotrunner.py:172-180) -> uint64 masks."""
+    Cm = np.asarray(Cmat) != 0
+    N = Cm.shape[-1]
+    w = (np.uint64(1) << np.arange(N, dtype=np.uint64))
+    return (Cm.astype(np.uint64) * w).sum(axis=-1).astype(np.uint64)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+class BatchMpc:
+    """B independent hoppers' MPC state + solver workspace on one GPU (one hmpc handle)."""
+
+    def __init__(self, batch, dyn="3f", N=10, device=0, **overrides):
+        if not torch.cuda.is_available():
+            raise RuntimeError("hopper_mpc_inertial_b200 needs a CUDA device (no CPU fallback)")
+        self.lib = _lib.load()
+        cfg = _lib.default_config()
+        cfg.batch, cfg.N, cfg.dyn, cfg.device = int(batch), int(N), _lib.DYN[dyn], int(device)
+        for k, v in overrides.items():
+            cur = getattr(cfg, k)
+            if hasattr(cur, "__len__"):
+                arr = np.asarray(v, dtype=float).reshape(-1)
+                for i in range(len(cur)):
+                    cur[i] = float(arr[i])
+            else:
+                setattr(cfg, k, v)
+        if "J" in overrides and "Jinv" not in overrides:
+            Ji = np.linalg.inv(np.asarray(overrides["J"], float).reshape(3, 3)).reshape(-1)
+            for i in range(9):
+                cfg.Jinv[i] = float(Ji[i])
+        self.cfg = cfg
+        self.B, self.N, self.dyn = int(batch), int(N), dyn
+        self.device = torch.device("cuda", int(device))
+        h = C.c_void_p()
+        _lib.check(self.lib.hmpc_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.hmpc_set_stream(self._h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.hmpc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers -------------------------------------------------------------------------------
+    def _chk(self, t, shape, dtype=torch.float64):
+        if t.device != self.device or t.dtype != dtype or not t.is_contiguous() or tuple(t.shape) != tuple(shape):
+            raise ValueError(f"expected contiguous {dtype} tensor of shape {tuple(shape)} on {self.device}, "
+                             f"got {t.dtype} {tuple(t.shape)} on {t.device}")
+        return t
+
+    def empty(self, *shape, dtype=torch.float64):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def use_current_stream(self):
+        _lib.check(self.lib.hmpc_set_stream(self._h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+
+    # -- ABI calls -----------------------------------------------------------------------------
+    def set_gains(self, Qdiag=None, Rdiag=None):
+        if Qdiag is not None:
+            self._chk(Qdiag, (12, self.B))
+        if Rdiag is not None:
+            self._chk(Rdiag, (6, self.B))
+        _lib.check(self.lib.hmpc_set_gains(self._h, _ptr(Qdiag), _ptr(Rdiag)))
+
+    def convert(self, X):
+        self._chk(X, (13, self.B))
+        x = self.empty(12, self.B)
+        _lib.check(self.lib.hmpc_convert(self._h, _ptr(X), _ptr(x)))
+        return x
+
+    def rk4(self, X, U, pf, nsteps=1, log_steps=False):
+        """In-place on X.  Returns the per-step states (nsteps, 13, B) when log_steps."""
+        self._chk(X, (13, self.B)); self._chk(U, (6, self.B)); self._chk(pf, (3, self.B))
+        Xs = self.empty(nsteps, 13, self.B) if log_steps else None
+        _lib.check(self.lib.hmpc_rk4(self._h, _ptr(X), _ptr(U), _ptr(pf), int(nsteps), _ptr(Xs)))
+        return Xs
+
+    def linearize(self, x_guess, pf):
+        N, B = self.N, self.B
+        self._chk(x_guess, (N + 1, 12, B)); self._chk(pf, (N, 3, B))
+        Ad, Bd = self.empty(N, 12, 12, B), self.empty(N, 12, 6, B)
+        _lib.check(self.lib.hmpc_linearize(self._h, _ptr(x_guess), _ptr(pf), _ptr(Ad), _ptr(Bd)))
+        return Ad, Bd
+
+    def condense(self, x_in, x_guess, x_ref, pf, Cbits):
+        N, B = self.N, self.B
+        n, m = 6 * N, 11 * N
+        self._chk(x_in, (12, B)); self._chk(x_guess, (N + 1, 12, B)); self._chk(x_ref, (N, 12, B))
+        self._chk(pf, (N, 3, B)); self._chk(Cbits, (B,), torch.int64)
+        H, g = self.empty(n, n, B), self.empty(n, B)
+        lo, hi = self.empty(m, B), self.empty(m, B)
+        _lib.check(self.lib.hmpc_condense(self._h, _ptr(x_in), _ptr(x_guess), _ptr(x_ref), _ptr(pf),
+                                          _ptr(Cbits), _ptr(H), _ptr(g), _ptr(lo), _ptr(hi)))
+        return H, g, lo, hi
+
+    def solve(self, x_in, x_ref, pf, Cbits, init, out=None):
+        """mpcontrol for the batch.  Returns (U (N,6,B), Xsol (N+1,12,B), status (B,), iters (B,))."""
+        N, B = self.N, self.B
+        self._chk(x_in, (12, B)); self._chk(x_ref, (N, 12, B)); self._chk(pf, (N, 3, B))
+        self._chk(Cbits, (B,), torch.int64)
+        if out is None:
+            out = (self.empty(N, 6, B), self.empty(N + 1, 12, B),
+                   self.empty(B, dtype=torch.int32), self.empty(B, dtype=torch.int32))
+        U, Xs, st, it = out
+        _lib.check(self.lib.hmpc_solve(self._h, _ptr(x_in), _ptr(x_ref), _ptr(pf), _ptr(Cbits),
+                                       1 if init else 0, _ptr(U), _ptr(Xs), _ptr(st), _ptr(it)))
+        return U, Xs, st, it
+
+    def rollout(self, X, xref_tab, pf_tab, C_tab, pf_switch=None, tick0=0, n_ticks=1, init=True,
+                log=False, out=None):
+        """Closed loop for n_ticks ticks, in place on X.  Returns dict(status, iters[, X_log, U_log])."""
+        B, N = self.B, self.N
+        self._chk(X, (13, B))
+        T = C_tab.shape[0]
+        self._chk(C_tab, (T, B), torch.int64)
+        if xref_tab.shape[0] < tick0 + n_ticks - 1 + N or pf_tab.shape[0] < tick0 + n_ticks + max(N - 1, 1):
+            raise ValueError("reference tables too short for the requested ticks")
+        self._chk(xref_tab, (xref_tab.shape[0], 12, B)); self._chk(pf_tab, (pf_tab.shape[0], 3, B))
+        if tick0 + n_ticks > T:
+            raise ValueError("contact table too short")
+        if pf_switch is not None:
+            self._chk(pf_switch, (T, B), torch.uint8)
+        if out is None:
+            out = dict(status=self.empty(B, dtype=torch.int32), iters=self.empty(B, dtype=torch.int32))
+            if log:
+                out["X_log"] = self.empty(n_ticks + 1, 13, B)
+                out["U_log"] = self.empty(n_ticks, 6, B)
+        _lib.check(self.lib.hmpc_rollout(self._h, _ptr(X), _ptr(xref_tab), _ptr(pf_tab), _ptr(C_tab),
+                                         _ptr(pf_switch), int(tick0), int(n_ticks), 1 if init else 0,
+                                         _ptr(out.get("X_log")), _ptr(out.get("U_log")),
+                                         _ptr(out["status"]), _ptr(out["iters"])))
+        return out
+
+    def launch_count(self):
+        n = C.c_int64()
+        _lib.check(self.lib.hmpc_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def measure_fp64_peak(self):
+        v = C.c_double()
+        _lib.check(self.lib.hmpc_measure_fp64_peak(self._h, C.byref(v)))
+        return v.value
+
+    def synchronize(self):
+        _lib.check(self.lib.hmpc_synchronize(self._h))

@@ -1,0 +1,640 @@
+// hmpc_api.cu -- kernels and the C ABI of libhmpc_b200.so (declared in include/hmpc.h).
+//
+// Kernels
+//   sim_kernel        K3: mpc_factor x RK4 (ZOH control) + convert, one thread per hopper, SoA I/O
+//   mpc_kernel        K1+K2: time shift, linearise, condense, ADMM + verified polish, solution rollout;
+//                     one CTA per hopper (persistent grid-stride loop)
+//   convert_kernel / linearize_kernel / condense_kernel   parity-test entry points
+//   dfma_peak_kernel  FP64 FMA roofline microbenchmark
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+
+#include "../../include/hmpc.h"
+#include "hmpc_sim.cuh"
+#include "hmpc_qp.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define HMPC_CUDA(call)                                                                       \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(HMPC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));   \
+    } while (0)
+
+}  // namespace
+
+struct hmpc_handle {
+    hmpc_config cfg;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    // per-hopper persistent state
+    double* Qd = nullptr;     // [12][B]
+    double* Rd = nullptr;     // [6][B]
+    double* Xsol = nullptr;   // [N+1][12][B] previous QP state trajectory (x.value)
+    double* Usol = nullptr;   // [N][6][B]    previous QP inputs (u.value)
+    double* xin = nullptr;    // [12][B]
+    double* U0 = nullptr;     // [6][B]
+    int32_t* st_tmp = nullptr;
+    int32_t* it_tmp = nullptr;
+    // solver launch geometry
+    int mpc_threads = 128;
+    int mpc_grid = 0;
+    size_t mpc_smem = 0;
+    bool mats_in_smem = false;
+    double* ws = nullptr;     // per-CTA matrix workspace (3 n^2 doubles each) when not in smem
+    int64_t launches = 0;
+};
+
+namespace hmpc {
+
+// ------------------------------------------------------------------------------------------------
+// K3: simulator.  X [13][B] in/out; U [6][B]; pfa/pfb [3][B] footstep before/after the switch step.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+sim_kernel(SimConst c, int B, double* __restrict__ X, const double* __restrict__ U,
+           const double* __restrict__ pfa, const double* __restrict__ pfb,
+           const uint8_t* __restrict__ sw, int nsteps, double* __restrict__ xin_out,
+           double* __restrict__ Xlog, double* __restrict__ Ulog, double* __restrict__ Xsteps) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double Xl[13], Ul[6], pa[3], pb[3];
+#pragma unroll
+    for (int i = 0; i < 13; ++i) Xl[i] = X[(size_t)i * B + b];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) Ul[i] = U[(size_t)i * B + b];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { pa[i] = pfa[(size_t)i * B + b]; pb[i] = pfb ? pfb[(size_t)i * B + b] : pa[i]; }
+    const int s = sw ? (int)sw[b] : nsteps;
+    for (int k = 0; k < nsteps; ++k) {
+        rk4_step(c, Xl, Ul, (k < s) ? pa : pb);
+        if (Xsteps) {
+#pragma unroll
+            for (int i = 0; i < 13; ++i) Xsteps[((size_t)k * 13 + i) * B + b] = Xl[i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 13; ++i) X[(size_t)i * B + b] = Xl[i];
+    if (Xlog) {
+#pragma unroll
+        for (int i = 0; i < 13; ++i) Xlog[(size_t)i * B + b] = Xl[i];
+    }
+    if (Ulog) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) Ulog[(size_t)i * B + b] = Ul[i];
+    }
+    if (xin_out) {
+        double x[12];
+        convert_state(Xl, x);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) xin_out[(size_t)i * B + b] = x[i];
+    }
+}
+
+__global__ void convert_kernel(int B, const double* __restrict__ X, double* __restrict__ x) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double Xl[13], xl[12];
+#pragma unroll
+    for (int i = 0; i < 13; ++i) Xl[i] = X[(size_t)i * B + b];
+    convert_state(Xl, xl);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) x[(size_t)i * B + b] = xl[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared set-up of one hopper's Work: carve shared memory, point the matrices
+// ------------------------------------------------------------------------------------------------
+__device__ inline void setup_work(Work& w, const QpConst& c, double* smem, double* ws, bool mats_in_smem) {
+    carve(w, smem, c.N);
+    const size_t n = 6 * (size_t)c.N;
+    double* mat = mats_in_smem ? smem + ((work_vec_doubles(c.N) + 1) & ~(size_t)1) : ws + (size_t)blockIdx.x * 3 * n * n;
+    w.H = mat; w.LC = mat + n * n; w.LR = mat + 2 * n * n;
+}
+
+__device__ inline void load_hopper(const QpConst& c, Work& w, int b, int B, const double* x_in,
+                                   const double* pf, const uint64_t* Cbits, const double* Qd,
+                                   const double* Rd) {
+    const int N = c.N, tid = threadIdx.x, T = blockDim.x;
+    for (int i = tid; i < 12; i += T) { w.xin[i] = x_in[(size_t)i * B + b]; w.Qd[i] = Qd[(size_t)i * B + b]; }
+    for (int i = tid; i < 6; i += T) w.Rd[i] = Rd[(size_t)i * B + b];
+    for (int i = tid; i < 3 * N; i += T) w.pfw[i] = pf[(size_t)i * B + b];
+    const uint64_t bits = Cbits[b];
+    for (int k = tid; k < N; k += T) w.stance[k] = (int)((bits >> k) & 1ull);
+}
+
+// linear rollout of the solution (mpc_cvx_euler_3f.py:133,140 dynamics rows): xs [(N+1)][12] in shared
+__device__ inline void rollout_solution(const QpConst& c, Work& w, const double* u, double* xs) {
+    const int N = c.N, tid = threadIdx.x;
+    const double dt = c.dt, gdt = -c.g * dt;
+    if (tid < 12) xs[tid] = w.xin[tid];
+    __syncthreads();
+    if (tid < 6) {
+        double acc = w.xin[6 + tid];
+        for (int k = 0; k < N; ++k) {
+            const double* uk = u + 6 * k;
+            if (tid < 3) {
+                const double* Bv = w.Bv + 9 * k + 3 * tid;
+                acc += Bv[0] * uk[0] + Bv[1] * uk[1] + Bv[2] * uk[2];
+                if (tid == 2) acc += gdt;
+            } else {
+                const double* Bw = w.Bw + 18 * k + 6 * (tid - 3);
+                acc += Bw[0] * uk[0] + Bw[1] * uk[1] + Bw[2] * uk[2] + Bw[3] * uk[3] + Bw[4] * uk[4] + Bw[5] * uk[5];
+            }
+            xs[12 * (k + 1) + 6 + tid] = acc;
+        }
+    }
+    __syncthreads();
+    if (tid < 6) {
+        double acc = w.xin[tid];
+        for (int k = 0; k < N; ++k) {
+            const double* xk = xs + 12 * k;
+            if (tid < 3) acc += dt * xk[6 + tid];
+            else {
+                const double cs = w.cz[k], sn = w.sz[k];
+                const double wx = xk[9], wy = xk[10], wz = xk[11];
+                const double r = (tid == 3) ? (cs * wx + sn * wy) : (tid == 4) ? (-sn * wx + cs * wy) : wz;
+                acc += dt * r;
+            }
+            xs[12 * (k + 1) + tid] = acc;
+        }
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1+K2: mpcontrol for a batch (mpc_cvx_euler_3f.py:41-69)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mpc_kernel(QpConst c, int B, int init, int mats_in_smem, double* __restrict__ ws,
+           const double* __restrict__ x_in, const double* __restrict__ x_ref,
+           const double* __restrict__ pf, const uint64_t* __restrict__ Cbits,
+           const double* __restrict__ Qd, const double* __restrict__ Rd,
+           double* __restrict__ Xsol /* handle state, in/out */, double* __restrict__ Usol,
+           double* __restrict__ U_out, double* __restrict__ X_out, double* __restrict__ U0_out,
+           int32_t* __restrict__ status, int32_t* __restrict__ iters, int accumulate) {
+    extern __shared__ double smem[];
+    Work w;
+    setup_work(w, c, smem, ws, mats_in_smem != 0);
+    const int N = c.N, n = 6 * N, m = 11 * N, tid = threadIdx.x, T = blockDim.x;
+    AOp A{N, n, c.dyn == 3 ? 1 : 0, c.mu, c.dt * c.dt / c.m, w.stance};
+    CholSys sys{n, w.LC, w.LR, w.dinv, w.H};
+    double* xs = w.err;   // reused after condense: solution trajectory [(N+1)][12]
+
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        load_hopper(c, w, b, B, x_in, pf, Cbits, Qd, Rd);
+        __syncthreads();
+        int st = 0, its = 0;
+        const int passes = init ? 2 : 1;
+        for (int pass = 0; pass < passes; ++pass) {
+            // linearisation point (mpc_cvx_euler_3f.py:50-62); only p and yaw of rows 0..N-1 matter
+            for (int k = tid; k < N; k += T) {
+                double* gp = w.gp + 4 * k;
+                if (k == 0) { gp[0] = w.xin[0]; gp[1] = w.xin[1]; gp[2] = w.xin[2]; gp[3] = w.xin[5]; }
+                else if (init && pass == 0) {
+                    const size_t o = (size_t)(k - 1) * 12;
+                    gp[0] = x_ref[(o + 0) * B + b]; gp[1] = x_ref[(o + 1) * B + b];
+                    gp[2] = x_ref[(o + 2) * B + b]; gp[3] = x_ref[(o + 5) * B + b];
+                } else if (init) {   // second pass of the first call: x_guess = x.value of pass 0
+                    gp[0] = xs[12 * k]; gp[1] = xs[12 * k + 1]; gp[2] = xs[12 * k + 2]; gp[3] = xs[12 * k + 5];
+                } else {             // time shift: x_guess[k] = x.value[k+1]
+                    const size_t o = (size_t)(k + 1) * 12;
+                    gp[0] = Xsol[(o + 0) * B + b]; gp[1] = Xsol[(o + 1) * B + b];
+                    gp[2] = Xsol[(o + 2) * B + b]; gp[3] = Xsol[(o + 5) * B + b];
+                }
+            }
+            __syncthreads();
+            const int infeasible = condense(c, w, x_ref + b, (size_t)B);
+            for (int i = tid; i < n; i += T) w.x[i] = 0.0;
+            for (int r = tid; r < m; r += T) w.y[r] = 0.0;
+            __syncthreads();
+            if (infeasible) {
+                st = 2;
+            } else {
+                SolveInfo info = admm_solve(c, w, sys, A);
+                its += info.iters;
+                if (info.status != 0 && st == 0) st = info.status;
+            }
+            rollout_solution(c, w, w.x, xs);
+        }
+        // outputs
+        for (int i = tid; i < (N + 1) * 12; i += T) {
+            Xsol[(size_t)i * B + b] = xs[i];
+            if (X_out) X_out[(size_t)i * B + b] = xs[i];
+        }
+        for (int i = tid; i < n; i += T) {
+            if (Usol) Usol[(size_t)i * B + b] = w.x[i];
+            if (U_out) U_out[(size_t)i * B + b] = w.x[i];
+        }
+        if (U0_out) for (int i = tid; i < 6; i += T) U0_out[(size_t)i * B + b] = w.x[i];
+        if (tid == 0) {
+            if (accumulate) {
+                if (status[b] == 0) status[b] = st;
+                iters[b] += its;
+            } else {
+                status[b] = st;
+                iters[b] = its;
+            }
+        }
+    }
+}
+
+// parity-test kernels ---------------------------------------------------------------------------
+__global__ void linearize_kernel(QpConst c, int B, const double* __restrict__ x_guess,
+                                 const double* __restrict__ pf, double* __restrict__ Ad,
+                                 double* __restrict__ Bd) {
+    extern __shared__ double smem[];
+    Work w;
+    carve(w, smem, c.N);
+    const int N = c.N, tid = threadIdx.x, T = blockDim.x, b = blockIdx.x;
+    for (int i = tid; i < 3 * N; i += T) w.pfw[i] = pf[(size_t)i * B + b];
+    for (int k = tid; k < N; k += T) {
+        const size_t o = (size_t)k * 12;
+        w.gp[4 * k] = x_guess[(o + 0) * B + b]; w.gp[4 * k + 1] = x_guess[(o + 1) * B + b];
+        w.gp[4 * k + 2] = x_guess[(o + 2) * B + b]; w.gp[4 * k + 3] = x_guess[(o + 5) * B + b];
+    }
+    __syncthreads();
+    for (int k = tid; k < N; k += T) linearize_stage(c, k, w);
+    __syncthreads();
+    for (int e = tid; e < N * 144; e += T) {
+        const int k = e / 144, r = (e % 144) / 12, cc = e % 12;
+        double v = (r == cc) ? 1.0 : 0.0;
+        if (r < 3 && cc == r + 6) v += c.dt;
+        if (r >= 3 && r < 6 && cc >= 9) {
+            const double cs = w.cz[k], sn = w.sz[k];
+            const double Rz[9] = {cs, sn, 0, -sn, cs, 0, 0, 0, 1};
+            v += Rz[3 * (r - 3) + (cc - 9)] * c.dt;
+        }
+        Ad[(size_t)e * B + b] = v;
+    }
+    for (int e = tid; e < N * 72; e += T) {
+        const int k = e / 72, r = (e % 72) / 6, cc = e % 6;
+        double v = 0.0;
+        if (r >= 6 && r < 9 && cc < 3) v = w.Bv[9 * k + 3 * (r - 6) + cc];
+        if (r >= 9) v = w.Bw[18 * k + 6 * (r - 9) + cc];
+        Bd[(size_t)e * B + b] = v;
+    }
+}
+
+__global__ void condense_kernel(QpConst c, int B, int mats_in_smem, double* __restrict__ ws,
+                                const double* __restrict__ x_in, const double* __restrict__ x_guess,
+                                const double* __restrict__ x_ref, const double* __restrict__ pf,
+                                const uint64_t* __restrict__ Cbits, const double* __restrict__ Qd,
+                                const double* __restrict__ Rd, double* __restrict__ H,
+                                double* __restrict__ g, double* __restrict__ lo, double* __restrict__ hi) {
+    extern __shared__ double smem[];
+    Work w;
+    setup_work(w, c, smem, ws, mats_in_smem != 0);
+    const int N = c.N, n = 6 * N, m = 11 * N, tid = threadIdx.x, T = blockDim.x;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        load_hopper(c, w, b, B, x_in, pf, Cbits, Qd, Rd);
+        for (int k = tid; k < N; k += T) {
+            const size_t o = (size_t)k * 12;
+            w.gp[4 * k] = x_guess[(o + 0) * B + b]; w.gp[4 * k + 1] = x_guess[(o + 1) * B + b];
+            w.gp[4 * k + 2] = x_guess[(o + 2) * B + b]; w.gp[4 * k + 3] = x_guess[(o + 5) * B + b];
+        }
+        __syncthreads();
+        condense(c, w, x_ref + b, (size_t)B);
+        for (int e = tid; e < n * n; e += T) H[(size_t)e * B + b] = w.H[e];
+        for (int i = tid; i < n; i += T) g[(size_t)i * B + b] = w.g[i];
+        for (int r = tid; r < m; r += T) { lo[(size_t)r * B + b] = w.lo[r]; hi[(size_t)r * B + b] = w.hi[r]; }
+    }
+}
+
+// FP64 FMA peak: 8 independent accumulator chains per thread, no memory traffic in the loop.
+__global__ void dfma_peak_kernel(double* out, int iters, double a, double bseed) {
+    double acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = bseed + (double)(threadIdx.x + i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fma(acc[i], a, bseed);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += acc[i];
+    if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace hmpc
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+namespace {
+
+hmpc::QpConst make_qp_const(const hmpc_config& cfg) {
+    hmpc::QpConst c;
+    c.N = cfg.N; c.dyn = cfg.dyn; c.uref_mode = cfg.uref_mode; c.mode = cfg.mode;
+    c.max_iter = cfg.max_iter; c.check = cfg.check_interval; c.polish = cfg.polish;
+    c.adaptive_rho = cfg.adaptive_rho;
+    c.dt = cfg.mpc_dt; c.m = cfg.m; c.g = cfg.g; c.mu = cfg.mu;
+    for (int i = 0; i < 9; ++i) c.Jinv[i] = cfg.Jinv[i];
+    for (int i = 0; i < 3; ++i) { c.rh[i] = cfg.rh[i]; c.tau_max[i] = cfg.tau_max[i]; }
+    c.fz_max = cfg.fz_max; c.z_min = cfg.z_min; c.kf = cfg.kf;
+    c.eps_abs = cfg.eps_abs; c.eps_rel = cfg.eps_rel; c.rho0 = cfg.rho0; c.sigma = cfg.sigma;
+    c.alpha = cfg.alpha; c.delta = cfg.polish_delta; c.polish_tol = cfg.polish_tol;
+    return c;
+}
+
+hmpc::SimConst make_sim_const(const hmpc_config& cfg) {
+    hmpc::SimConst s;
+    s.m = cfg.m; s.g = cfg.g; s.h = cfg.sim_dt;
+    for (int i = 0; i < 9; ++i) { s.J[i] = cfg.J[i]; s.Jinv[i] = cfg.Jinv[i]; }
+    for (int i = 0; i < 3; ++i) s.rh[i] = cfg.rh[i];
+    return s;
+}
+
+int check_handle(hmpc_handle* h) {
+    if (!h) return fail(HMPC_ERR_BAD_ARG, "null handle");
+    cudaError_t e = cudaSetDevice(h->cfg.device);
+    if (e != cudaSuccess) return fail(HMPC_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    return HMPC_OK;
+}
+
+void inv3(const double* J, double* Ji) {
+    const double a = J[0], b = J[1], c = J[2], d = J[3], e = J[4], f = J[5], g = J[6], h = J[7], i = J[8];
+    const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+    Ji[0] = (e * i - f * h) / det; Ji[1] = (c * h - b * i) / det; Ji[2] = (b * f - c * e) / det;
+    Ji[3] = (f * g - d * i) / det; Ji[4] = (a * i - c * g) / det; Ji[5] = (c * d - a * f) / det;
+    Ji[6] = (d * h - e * g) / det; Ji[7] = (b * g - a * h) / det; Ji[8] = (a * e - b * d) / det;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hmpc_abi_version(void) { return HMPC_ABI_VERSION; }
+
+const char* hmpc_last_error(void) { return g_err.c_str(); }
+
+int hmpc_default_config(hmpc_config* cfg) {
+    if (!cfg) return fail(HMPC_ERR_BAD_ARG, "null config");
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->abi_version = HMPC_ABI_VERSION;
+    cfg->device = 0; cfg->batch = 1; cfg->dyn = HMPC_DYN_3F; cfg->N = 60; cfg->mpc_factor = 20;
+    cfg->precision = HMPC_FP64; cfg->uref_mode = HMPC_UREF_ALIASED; cfg->mode = HMPC_MODE_EARLY_EXIT;
+    cfg->max_iter = 10000; cfg->check_interval = 25; cfg->polish = 1; cfg->adaptive_rho = 1;
+    cfg->warm_start = 0; cfg->linsys = 0;
+    cfg->mpc_dt = 0.02; cfg->sim_dt = 1e-3; cfg->m = 7.5; cfg->g = 9.807; cfg->mu = 1.0;
+    const double J[9] = {76148072.89e-9, 70089.52e-9, 2067970.36e-9, 70089.52e-9, 45477183.53e-9,
+                         -87045.58e-9, 2067970.36e-9, -87045.58e-9, 76287220.47e-9};
+    memcpy(cfg->J, J, sizeof(J));
+    inv3(cfg->J, cfg->Jinv);
+    cfg->rh[0] = -0.02663114 / 1000; cfg->rh[1] = -0.04435752 / 1000; cfg->rh[2] = -6.61082088 / 1000;
+    cfg->tau_max[0] = 7.78; cfg->tau_max[1] = 7.78; cfg->tau_max[2] = 4.0;
+    cfg->fz_max = 206.0; cfg->z_min = 0.1; cfg->kf = 100.0;
+    cfg->eps_abs = 1e-5; cfg->eps_rel = 1e-5; cfg->rho0 = 0.1; cfg->sigma = 1e-6; cfg->alpha = 1.6;
+    cfg->polish_delta = 1e-5; cfg->polish_tol = 1e-9;
+    return HMPC_OK;
+}
+
+int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
+    if (!cfg || !out) return fail(HMPC_ERR_BAD_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != HMPC_ABI_VERSION) return fail(HMPC_ERR_BAD_ARG, "abi_version mismatch");
+    if (cfg->batch < 1) return fail(HMPC_ERR_BAD_ARG, "batch must be >= 1");
+    if (cfg->N < 2 || cfg->N > HMPC_MAX_N) return fail(HMPC_ERR_BAD_ARG, "N must be in [2, 64]");
+    if (cfg->dyn != HMPC_DYN_2F && cfg->dyn != HMPC_DYN_3F) return fail(HMPC_ERR_BAD_ARG, "dyn must be 2 or 3");
+    if (cfg->precision != HMPC_FP64) return fail(HMPC_ERR_UNSUPPORTED, "only FP64 precision is implemented");
+    if (cfg->mpc_factor < 1 || cfg->mpc_factor > 255) return fail(HMPC_ERR_BAD_ARG, "mpc_factor must be in [1,255]");
+    if (cfg->max_iter < 1 || cfg->check_interval < 1) return fail(HMPC_ERR_BAD_ARG, "max_iter/check_interval must be >= 1");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(HMPC_ERR_NO_DEVICE, "no CUDA device available (there is no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(HMPC_ERR_BAD_ARG, "device ordinal out of range");
+    HMPC_CUDA(cudaSetDevice(cfg->device));
+    hmpc_handle* h = new (std::nothrow) hmpc_handle();
+    if (!h) return fail(HMPC_ERR_ALLOC, "host allocation failed");
+    h->cfg = *cfg;
+    cudaDeviceProp prop;
+    HMPC_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    h->sm_count = prop.multiProcessorCount;
+    const size_t B = (size_t)cfg->batch, N = (size_t)cfg->N, n = 6 * N;
+    auto dalloc = [&](void** p, size_t bytes) { return cudaMalloc(p, bytes); };
+    cudaError_t e = cudaSuccess;
+    if ((e = dalloc((void**)&h->Qd, 12 * B * 8)) != cudaSuccess || (e = dalloc((void**)&h->Rd, 6 * B * 8)) != cudaSuccess ||
+        (e = dalloc((void**)&h->Xsol, (N + 1) * 12 * B * 8)) != cudaSuccess ||
+        (e = dalloc((void**)&h->Usol, N * 6 * B * 8)) != cudaSuccess ||
+        (e = dalloc((void**)&h->xin, 12 * B * 8)) != cudaSuccess || (e = dalloc((void**)&h->U0, 6 * B * 8)) != cudaSuccess ||
+        (e = dalloc((void**)&h->st_tmp, B * 4)) != cudaSuccess || (e = dalloc((void**)&h->it_tmp, B * 4)) != cudaSuccess) {
+        hmpc_destroy(h);
+        return fail(HMPC_ERR_ALLOC, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    }
+    cudaMemset(h->Xsol, 0, (N + 1) * 12 * B * 8);
+    cudaMemset(h->Usol, 0, N * 6 * B * 8);
+    // default gains = the reference's (mpc_cvx_euler_3f.py:35,37)
+    {
+        const double Qref[12] = {50., 50., 2., 1., 1., 50., 1., 1., 1., 10., 10., 10.};
+        double* tmp = new (std::nothrow) double[18 * B];
+        if (!tmp) { hmpc_destroy(h); return fail(HMPC_ERR_ALLOC, "host allocation failed"); }
+        for (size_t i = 0; i < 12; ++i) for (size_t b = 0; b < B; ++b) tmp[i * B + b] = Qref[i];
+        for (size_t i = 0; i < 6; ++i) for (size_t b = 0; b < B; ++b) tmp[(12 + i) * B + b] = 0.001;
+        cudaMemcpy(h->Qd, tmp, 12 * B * 8, cudaMemcpyHostToDevice);
+        cudaMemcpy(h->Rd, tmp + 12 * B, 6 * B * 8, cudaMemcpyHostToDevice);
+        delete[] tmp;
+    }
+    // solver geometry
+    const size_t vec_bytes = ((hmpc::work_vec_doubles((int)N) + 1) & ~(size_t)1) * 8;
+    const size_t mat_bytes = 3 * n * n * 8;
+    const size_t smem_cap = (size_t)prop.sharedMemPerBlockOptin;
+    h->mats_in_smem = (vec_bytes + mat_bytes + 1024 <= smem_cap) && cfg->linsys != 3;
+    h->mpc_smem = vec_bytes + (h->mats_in_smem ? mat_bytes : 0);
+    if (h->mpc_smem > smem_cap) { hmpc_destroy(h); return fail(HMPC_ERR_UNSUPPORTED, "horizon too large for shared memory"); }
+    h->mpc_threads = (n <= 128) ? 128 : 256;
+    int per_sm = 1;
+    if (h->mats_in_smem) per_sm = std::max<int>(1, (int)((size_t)prop.sharedMemPerMultiprocessor / (h->mpc_smem + 1024)));
+    else per_sm = std::max<int>(1, std::min<int>(8, (int)((size_t)prop.sharedMemPerMultiprocessor / (h->mpc_smem + 1024))));
+    h->mpc_grid = (int)std::min<size_t>(B, (size_t)h->sm_count * per_sm);
+    if (!h->mats_in_smem) {
+        if ((e = cudaMalloc((void**)&h->ws, (size_t)h->mpc_grid * mat_bytes)) != cudaSuccess) {
+            hmpc_destroy(h);
+            return fail(HMPC_ERR_ALLOC, std::string("cudaMalloc workspace: ") + cudaGetErrorString(e));
+        }
+    }
+    if ((e = cudaFuncSetAttribute(hmpc::mpc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mpc_smem)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(hmpc::condense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mpc_smem)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(hmpc::linearize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vec_bytes)) != cudaSuccess) {
+        hmpc_destroy(h);
+        return fail(HMPC_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    }
+    if ((e = cudaDeviceSynchronize()) != cudaSuccess) {
+        hmpc_destroy(h);
+        return fail(HMPC_ERR_CUDA, std::string("create: ") + cudaGetErrorString(e));
+    }
+    *out = h;
+    return HMPC_OK;
+}
+
+int hmpc_destroy(hmpc_handle* h) {
+    if (!h) return HMPC_OK;
+    cudaSetDevice(h->cfg.device);
+    cudaFree(h->Qd); cudaFree(h->Rd); cudaFree(h->Xsol); cudaFree(h->Usol); cudaFree(h->xin);
+    cudaFree(h->U0); cudaFree(h->st_tmp); cudaFree(h->it_tmp); cudaFree(h->ws);
+    delete h;
+    return HMPC_OK;
+}
+
+int hmpc_set_stream(hmpc_handle* h, void* s) {
+    if (int rc = check_handle(h)) return rc;
+    h->stream = (cudaStream_t)s;
+    return HMPC_OK;
+}
+
+int hmpc_synchronize(hmpc_handle* h) {
+    if (int rc = check_handle(h)) return rc;
+    HMPC_CUDA(cudaStreamSynchronize(h->stream));
+    return HMPC_OK;
+}
+
+int hmpc_set_gains(hmpc_handle* h, const double* Qdiag, const double* Rdiag) {
+    if (int rc = check_handle(h)) return rc;
+    const size_t B = (size_t)h->cfg.batch;
+    if (Qdiag) HMPC_CUDA(cudaMemcpyAsync(h->Qd, Qdiag, 12 * B * 8, cudaMemcpyDeviceToDevice, h->stream));
+    if (Rdiag) HMPC_CUDA(cudaMemcpyAsync(h->Rd, Rdiag, 6 * B * 8, cudaMemcpyDeviceToDevice, h->stream));
+    return HMPC_OK;
+}
+
+int hmpc_convert(hmpc_handle* h, const double* X, double* x) {
+    if (int rc = check_handle(h)) return rc;
+    if (!X || !x) return fail(HMPC_ERR_BAD_ARG, "null array");
+    const int B = h->cfg.batch;
+    hmpc::convert_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(B, X, x);
+    ++h->launches;
+    HMPC_CUDA(cudaGetLastError());
+    return HMPC_OK;
+}
+
+int hmpc_rk4(hmpc_handle* h, double* X, const double* U, const double* pf, int nsteps, double* X_steps) {
+    if (int rc = check_handle(h)) return rc;
+    if (!X || !U || !pf || nsteps < 0) return fail(HMPC_ERR_BAD_ARG, "bad argument");
+    const int B = h->cfg.batch;
+    hmpc::sim_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(make_sim_const(h->cfg), B, X, U, pf, nullptr,
+                                                              nullptr, nsteps, nullptr, nullptr, nullptr, X_steps);
+    ++h->launches;
+    HMPC_CUDA(cudaGetLastError());
+    return HMPC_OK;
+}
+
+int hmpc_linearize(hmpc_handle* h, const double* x_guess, const double* pf, double* Ad, double* Bd) {
+    if (int rc = check_handle(h)) return rc;
+    if (!x_guess || !pf || !Ad || !Bd) return fail(HMPC_ERR_BAD_ARG, "null array");
+    const size_t vec_bytes = ((hmpc::work_vec_doubles(h->cfg.N) + 1) & ~(size_t)1) * 8;
+    hmpc::linearize_kernel<<<h->cfg.batch, 128, vec_bytes, h->stream>>>(make_qp_const(h->cfg), h->cfg.batch,
+                                                                        x_guess, pf, Ad, Bd);
+    ++h->launches;
+    HMPC_CUDA(cudaGetLastError());
+    return HMPC_OK;
+}
+
+int hmpc_condense(hmpc_handle* h, const double* x_in, const double* x_guess, const double* x_ref,
+                  const double* pf, const uint64_t* Cbits, double* H, double* g, double* lo, double* hi) {
+    if (int rc = check_handle(h)) return rc;
+    if (!x_in || !x_guess || !x_ref || !pf || !Cbits || !H || !g || !lo || !hi)
+        return fail(HMPC_ERR_BAD_ARG, "null array");
+    hmpc::condense_kernel<<<h->mpc_grid, h->mpc_threads, h->mpc_smem, h->stream>>>(
+        make_qp_const(h->cfg), h->cfg.batch, h->mats_in_smem ? 1 : 0, h->ws, x_in, x_guess, x_ref, pf, Cbits,
+        h->Qd, h->Rd, H, g, lo, hi);
+    ++h->launches;
+    HMPC_CUDA(cudaGetLastError());
+    return HMPC_OK;
+}
+
+int hmpc_solve(hmpc_handle* h, const double* x_in, const double* x_ref, const double* pf,
+               const uint64_t* Cbits, int init, double* U, double* Xsol, int32_t* status, int32_t* iters) {
+    if (int rc = check_handle(h)) return rc;
+    if (!x_in || !x_ref || !pf || !Cbits) return fail(HMPC_ERR_BAD_ARG, "null input array");
+    hmpc::mpc_kernel<<<h->mpc_grid, h->mpc_threads, h->mpc_smem, h->stream>>>(
+        make_qp_const(h->cfg), h->cfg.batch, init ? 1 : 0, h->mats_in_smem ? 1 : 0, h->ws, x_in, x_ref, pf, Cbits,
+        h->Qd, h->Rd, h->Xsol, h->Usol, U, Xsol, nullptr, status ? status : h->st_tmp, iters ? iters : h->it_tmp, 0);
+    ++h->launches;
+    HMPC_CUDA(cudaGetLastError());
+    return HMPC_OK;
+}
+
+int hmpc_rollout(hmpc_handle* h, double* X, const double* xref_tab, const double* pf_tab,
+                 const uint64_t* C_tab, const uint8_t* pf_switch, int tick0, int n_ticks, int init,
+                 double* X_log, double* U_log, int32_t* status, int32_t* iters) {
+    if (int rc = check_handle(h)) return rc;
+    if (!X || !xref_tab || !pf_tab || !C_tab || tick0 < 0 || n_ticks < 0)
+        return fail(HMPC_ERR_BAD_ARG, "bad argument");
+    const size_t B = (size_t)h->cfg.batch;
+    const int Bi = h->cfg.batch;
+    int32_t* st = status ? status : h->st_tmp;
+    int32_t* it = iters ? iters : h->it_tmp;
+    HMPC_CUDA(cudaMemsetAsync(st, 0, B * 4, h->stream));
+    HMPC_CUDA(cudaMemsetAsync(it, 0, B * 4, h->stream));
+    const hmpc::QpConst qc = make_qp_const(h->cfg);
+    const hmpc::SimConst sc = make_sim_const(h->cfg);
+    const int sim_grid = (Bi + 127) / 128;
+    // x_in for the first tick; afterwards sim_kernel emits it fused with the integration
+    hmpc::convert_kernel<<<sim_grid, 128, 0, h->stream>>>(Bi, X, h->xin);
+    ++h->launches;
+    if (X_log) HMPC_CUDA(cudaMemcpyAsync(X_log, X, 13 * B * 8, cudaMemcpyDeviceToDevice, h->stream));
+    for (int t = 0; t < n_ticks; ++t) {
+        const size_t row = (size_t)(tick0 + t);
+        hmpc::mpc_kernel<<<h->mpc_grid, h->mpc_threads, h->mpc_smem, h->stream>>>(
+            qc, Bi, (init && t == 0) ? 1 : 0, h->mats_in_smem ? 1 : 0, h->ws, h->xin, xref_tab + row * 12 * B,
+            pf_tab + row * 3 * B, C_tab + row * B, h->Qd, h->Rd, h->Xsol, h->Usol, nullptr, nullptr, h->U0, st, it, 1);
+        hmpc::sim_kernel<<<sim_grid, 128, 0, h->stream>>>(
+            sc, Bi, X, h->U0, pf_tab + row * 3 * B, pf_tab + (row + 1) * 3 * B,
+            pf_switch ? pf_switch + row * B : nullptr, h->cfg.mpc_factor, h->xin,
+            X_log ? X_log + (size_t)(t + 1) * 13 * B : nullptr, U_log ? U_log + (size_t)t * 6 * B : nullptr,
+            nullptr);
+        h->launches += 2;
+    }
+    HMPC_CUDA(cudaGetLastError());
+    return HMPC_OK;
+}
+
+int hmpc_launch_count(hmpc_handle* h, int64_t* n) {
+    if (!h || !n) return fail(HMPC_ERR_BAD_ARG, "null argument");
+    *n = h->launches;
+    return HMPC_OK;
+}
+
+int hmpc_measure_fp64_peak(hmpc_handle* h, double* tflops) {
+    if (int rc = check_handle(h)) return rc;
+    if (!tflops) return fail(HMPC_ERR_BAD_ARG, "null argument");
+    double* out = nullptr;
+    const int blocks = h->sm_count * 8, threads = 256, iters = 4096;
+    HMPC_CUDA(cudaMalloc((void**)&out, (size_t)blocks * threads * 8));
+    cudaEvent_t e0, e1;
+    HMPC_CUDA(cudaEventCreate(&e0));
+    HMPC_CUDA(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        HMPC_CUDA(cudaEventRecord(e0, h->stream));
+        hmpc::dfma_peak_kernel<<<blocks, threads, 0, h->stream>>>(out, iters, 0.999999, 1e-3);
+        HMPC_CUDA(cudaEventRecord(e1, h->stream));
+        HMPC_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        HMPC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+        ++h->launches;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    *tflops = best;
+    return HMPC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,217 @@
+"""Host-side planning for the MPC hot path: reference trajectories, footsteps and contact schedules.
+
+This is the caller side of the hot path: a one-off precompute per run, done in
+numpy/scipy on the host exactly as the reference does, then shipped to the GPU as MPC-rate tables.
+
+Reference behaviour (file:line into the reference's src/):
+  gait_scheduler / gait_map   robotrunner.py:166-180  (accumulated float sums)
+  path_plan_init              robotrunner.py:182-226  (incl. the --curve column quirk, App. D4)
+  path_plan_grab              robotrunner.py:228-230
+  run-loop time stepping      robotrunner.py:83-113   (t += dt before use; MPC at k = 0, 20, 40 ...)
+"""
+from __future__ import annotations
+
+import numpy as np
+
+T_P = 0.8           # gait period (robotrunner.py:43)
+PHI_SWITCH = 0.5    # stance fraction (robotrunner.py:44)
+STEP_ADJUSTMENT = -115  # robotrunner.py:79
+
+
+def gait_scheduler(t, t0=0.0, t_p=T_P, phi_switch=PHI_SWITCH):
+    """1 = scheduled stance, 0 = swing (robotrunner.py:166-171).  Works on scalars and arrays."""
+    phi = np.mod((t - t0) / t_p, 1)
+    return np.where(phi > phi_switch, 0, 1)
+
+
+def gait_map(N, dt, ts, t0=0.0, t_p=T_P, phi_switch=PHI_SWITCH):
+    """Contact flags over a horizon with the reference's running sum ts += dt (robotrunner.py:172-180).
+
+    ``ts`` may be an array (one start time per hopper); returns shape (N,) or (B, N) float64."""
+    ts = np.array(ts, dtype=float)
+    out = np.zeros(ts.shape + (N,))
+    for k in range(N):
+        out[..., k] = gait_scheduler(ts, t0, t_p, phi_switch)
+        ts = ts + dt
+    return out
+
+
+def path_plan_init(x_in, xf, N_run, N, mpc_factor, dt, curve, t_start, t_p=T_P, phi_switch=PHI_SWITCH,
+                   step_adjustment=STEP_ADJUSTMENT):
+    """Full-rate reference for one hopper: x_ref (N_run + N*mpc_factor, 12), pf_ref (.., 3)."""
+    from scipy.interpolate import CubicSpline
+    from scipy.signal import find_peaks
+    N_k = N * mpc_factor
+    t_ref = N_run + N_k
+    x_ref = np.linspace(start=x_in, stop=xf, num=N_run)
+    if curve:
+        knots = np.array([0, N_run * 0.5, N_run])
+        k_all = np.arange(N_run)
+        x_ref[:, 0] = CubicSpline(knots, np.array([x_in[1], xf[1] * 0.9, xf[1]]))(k_all)
+        s45 = np.sin(45 * np.pi / 180)
+        x_ref[:, 5] = CubicSpline(knots, np.array([0, -s45 * 0.4, -s45]))(k_all)
+        x_ref[:-1, 11] = (x_ref[1:, 11] - x_ref[:-1, 11]) / dt
+    x_ref = np.vstack((x_ref, np.tile(xf, (N_k, 1))))
+    amp = t_p / 4
+    phase = np.pi * 3 / 2
+    x_ref[:, 2] = [x_in[2] + amp + amp * np.sin(2 * np.pi / t_p * (i * dt) + phase) for i in range(t_ref)]
+    x_ref[:-1, 6:9] = (x_ref[1:, 0:3] - x_ref[:-1, 0:3]) / dt
+    Cmap = gait_map(t_ref, dt, t_start, 0.0, t_p, phi_switch)
+    idx_pf = find_peaks(-x_ref[:, 2])[0] + step_adjustment
+    idx_pf = np.hstack((0, idx_pf, t_ref - 1))
+    edges = np.zeros(t_ref, dtype=np.int64)
+    edges[1:] = (Cmap[:-1] == 1) & (Cmap[1:] == 0)
+    kf = np.minimum(np.cumsum(edges), idx_pf.shape[0] - 1)
+    pf_ref = np.zeros((t_ref, 3))
+    pf_ref[1:, 0:2] = x_ref[idx_pf[kf[1:]], 0:2]
+    return x_ref, pf_ref
+
+
+def path_plan_grab(x_ref, k, N, mpc_factor):
+    return x_ref[k:(k + N * mpc_factor):mpc_factor, :]
+
+
+def run_clock(n_steps, dt, t_start):
+    """Times the run loop sees: t_k = t_start + dt + ... + dt (k+1 additions), robotrunner.py:83,97."""
+    t = np.empty(n_steps)
+    acc = t_start
+    for k in range(n_steps):
+        acc = acc + dt
+        t[k] = acc
+    return t
+
+
+def mpc_tables(x_ref, pf_ref, n_ticks, N, mpc_factor, dt, mpc_dt, t_start):
+    """MPC-rate tables of one hopper for ``hmpc_rollout``.
+
+    Returns xref_tab (n_ticks+N, 12), pf_tab (n_ticks+N+1, 3), C (n_ticks, N) and pf_switch (n_ticks,)
+    such that pf_ref[20 j + i] == (pf_tab[j] if i < pf_switch[j] else pf_tab[j+1])."""
+    rows = np.arange(n_ticks + N + 1) * mpc_factor
+    rows = np.minimum(rows, x_ref.shape[0] - 1)
+    xref_tab = x_ref[rows[:-1]]
+    pf_tab = pf_ref[rows]
+    t = run_clock(n_ticks * mpc_factor, dt, t_start)
+    C = gait_map(N, mpc_dt, t[::mpc_factor], 0.0)
+    sw = np.full(n_ticks, mpc_factor, dtype=np.uint8)
+    for j in range(n_ticks):
+        seg = pf_ref[j * mpc_factor:(j + 1) * mpc_factor]
+        diff = np.any(seg != pf_tab[j], axis=1)
+        if diff.any():
+            s = int(np.argmax(diff))
+            if not np.all(seg[s:] == pf_tab[j + 1]):
+                raise ValueError("footstep changes more than once inside an MPC tick")
+            sw[j] = s
+    return xref_tab, pf_tab, C, sw
+
+
+# ------------------------------------------------------------------------------------------------
+# vectorised planner for synthetic batches (same formulas, all hoppers at once, MPC-rate rows only)
+# ------------------------------------------------------------------------------------------------
+def _parabola(y0, y1, y2, T, k):
+    """Value at k of the parabola through (0,y0), (T/2,y1), (T,y2): what a 3-point not-a-knot
+    CubicSpline reduces to (robotrunner.py:192-196)."""
+    s = k / T
+    return y0 * (1 - s) * (1 - 2 * s) + y1 * 4 * s * (1 - s) + y2 * s * (2 * s - 1)
+
+
+def batch_tables(x0, xf, curve, t_start, N_run, n_ticks, N, mpc_factor=20, dt=1e-3, mpc_dt=0.02,
+                 t_p=T_P, phi_switch=PHI_SWITCH, step_adjustment=STEP_ADJUSTMENT):
+    """Planner + gait for B hoppers at once.
+
+    x0, xf (B,12) start / goal MPC states, curve (B,) bool, t_start (B,) gait phase offsets.
+    Returns dict of numpy arrays in the SoA layout of include/hmpc.h:
+      xref_tab (n_ticks+N, 12, B), pf_tab (n_ticks+N+1, 3, B), C_tab (n_ticks, B) uint64,
+      pf_switch (n_ticks, B) uint8, C (n_ticks, B, N) float."""
+    x0 = np.asarray(x0, float); xf = np.asarray(xf, float)
+    B = x0.shape[0]
+    curve = np.asarray(curve, bool); t_start = np.asarray(t_start, float)
+    N_k = N * mpc_factor
+    t_ref = N_run + N_k
+    n_sim = n_ticks * mpc_factor
+    amp = t_p / 4
+
+    def ref_rows(i):
+        """x_ref rows (len(i), B, 12) without the velocity columns, i = array of sim indices."""
+        i = np.asarray(i)
+        ii = np.minimum(i, t_ref - 1)[:, None, None].astype(float)
+        step = (xf - x0) / (N_run - 1)
+        lin = ii * step[None] + x0[None]
+        last = (ii == N_run - 1)
+        lin = np.where(last, xf[None], lin)
+        out = lin.copy()
+        T = float(N_run)
+        k = ii[..., 0]
+        s45 = np.sin(45 * np.pi / 180)
+        cx = _parabola(x0[None, :, 1], 0.9 * xf[None, :, 1], xf[None, :, 1], T, k)
+        cpsi = _parabola(0.0, -0.4 * s45, -s45, T, k)
+        out[..., 0] = np.where(curve[None], cx, lin[..., 0])
+        out[..., 5] = np.where(curve[None], cpsi, lin[..., 5])
+        d11 = np.where(k < N_run - 1, (((ii[..., 0] + 1) * step[None, :, 11] + x0[None, :, 11])
+                                        - lin[..., 11]) / dt, lin[..., 11])
+        # the row N_run-2 difference uses the exact endpoint xf
+        d11 = np.where(k == N_run - 2, (xf[None, :, 11] - lin[..., 11]) / dt, d11)
+        out[..., 11] = np.where(curve[None], d11, lin[..., 11])
+        goal = (ii[..., 0] >= N_run)
+        out = np.where(goal[..., None], xf[None], out)
+        out[..., 2] = x0[None, :, 2] + amp + amp * np.sin(2 * np.pi / t_p * (ii[..., 0] * dt) + np.pi * 3 / 2)
+        return out
+
+    rows = np.minimum(np.arange(n_ticks + N + 1) * mpc_factor, t_ref - 1)
+    r0 = ref_rows(rows)
+    r1 = ref_rows(rows + 1)
+    vel = (r1[..., 0:3] - r0[..., 0:3]) / dt
+    # the very last reference row keeps the goal's own velocity (x_ref[:-1, 6:9] assignment)
+    is_last = (rows == t_ref - 1)[:, None, None]
+    r0[..., 6:9] = np.where(is_last, xf[None, :, 6:9], vel)
+    xref_tab = r0[:-1]
+
+    # footsteps: contact map at 1 kHz from t_start with running sums, stance->swing edge counter
+    n_need = int(rows[-1]) + 1
+    ts = t_start.copy()
+    prev = gait_scheduler(ts, 0.0, t_p, phi_switch)
+    kf = np.zeros(B, dtype=np.int64)
+    # footstep sample indices: minima of z at i = 800 k (k >= 1), shifted; first 0, last t_ref-1
+    period = int(round(t_p / dt))
+    minima = np.arange(period, t_ref - 1, period)
+    # find_peaks needs a strict interior maximum of -z; i = multiples of the period qualify
+    idx_pf = np.hstack((0, minima + step_adjustment, t_ref - 1))
+    kf_rows = np.zeros((n_need, B), dtype=np.int64)
+    for k in range(1, n_need):
+        ts = ts + dt
+        cur = gait_scheduler(ts, 0.0, t_p, phi_switch)
+        kf = kf + ((prev == 1) & (cur == 0))
+        prev = cur
+        kf_rows[k] = kf
+    kf_rows = np.minimum(kf_rows, idx_pf.shape[0] - 1)
+    pf_idx = idx_pf[kf_rows]                       # (n_need, B) sim index whose xy is the footstep
+    uniq = np.unique(pf_idx)
+    xy_at = {int(u): ref_rows(np.array([u]))[0][:, 0:2] for u in uniq}   # (B,2) each
+    pf_tab = np.zeros((len(rows), B, 3))
+    for j, r in enumerate(rows):
+        sel = pf_idx[r]
+        for u in np.unique(sel):
+            msk = sel == u
+            pf_tab[j, msk, 0:2] = xy_at[int(u)][msk]
+    # switch step inside each tick (pf_ref[k] for k = 20 j + i); row 0 follows the same rule as the
+    # others, which equals the reference's all-zero pf_ref[0] whenever the start xy is the origin
+    sw = np.full((n_ticks, B), mpc_factor, dtype=np.uint8)
+    for j in range(n_ticks):
+        base = j * mpc_factor
+        seg = pf_idx[base:base + mpc_factor]            # (20, B)
+        diff = seg != pf_idx[base][None]
+        anyd = diff.any(axis=0)
+        sw[j, anyd] = np.argmax(diff, axis=0)[anyd].astype(np.uint8)
+        sw[j, np.all(pf_tab[j] == pf_tab[j + 1], axis=-1)] = mpc_factor   # same footstep either side
+
+    # MPC contact windows from the run clock
+    t = t_start.copy()
+    C = np.zeros((n_ticks, B, N))
+    for k in range(n_sim):
+        t = t + dt
+        if k % mpc_factor == 0:
+            C[k // mpc_factor] = gait_map(N, mpc_dt, t, 0.0, t_p, phi_switch)
+    w = (np.uint64(1) << np.arange(N, dtype=np.uint64))
+    C_tab = ((C != 0).astype(np.uint64) * w).sum(axis=-1).astype(np.uint64)
+    return dict(xref_tab=np.ascontiguousarray(xref_tab.transpose(0, 2, 1)),
+                pf_tab=np.ascontiguousarray(pf_tab.transpose(0, 2, 1)),
+                C_tab=C_tab, pf_switch=sw, C=C)

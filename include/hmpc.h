@@ -1,0 +1,172 @@
+/* hmpc.h -- C ABI of libhmpc_b200.so: batched hopper MPC hot path on NVIDIA B200 (sm_100a).
+ *
+ * The reference (bbokser/hopper-mpc-inertial) is pure Python and has no FFI; this header is the
+ * boundary a maintainer would bind with ctypes.  Each entry point names the
+ * reference interface it replaces (file:line into the reference's src/).
+ *
+ * Conventions
+ *  - Every function returns 0 on success or a negative hmpc_error; hmpc_last_error() gives text.
+ *    Nothing throws or aborts across the boundary.
+ *  - All array arguments are DEVICE pointers (e.g. torch tensor.data_ptr()) unless the name ends
+ *    in _host.  Layout is structure-of-arrays with the hopper (batch) index FASTEST:
+ *    an array documented as [R][C][B] stores element (r,c,b) at ((r*C)+c)*B + b.
+ *  - Element type is double (FP64) for every floating-point array at the boundary, whatever the
+ *    internal solver precision (hmpc_config.precision).
+ *  - A handle is bound to one device and one stream; calls are stream-asynchronous; a handle is
+ *    not thread-safe.  The library allocates only its own opaque workspace.
+ *  - There is no CPU fallback: creating a handle without a usable CUDA device fails.
+ */
+#ifndef HMPC_H
+#define HMPC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HMPC_ABI_VERSION 1
+#define HMPC_INF 1e30          /* "no bound" marker (same convention as OSQP's OSQP_INFTY) */
+#define HMPC_NX 12             /* Euler MPC state  [p, rpy, pdot_w, omega_w]  (mpc_cvx_euler_3f.py:21) */
+#define HMPC_NU 6              /* control [f(3), tau_body(3)]                 (mpc_cvx_euler_3f.py:22) */
+#define HMPC_NXSIM 13          /* simulator state [p, q(wxyz), v_b, omega_b]  (robotrunner.py:50)      */
+#define HMPC_MAX_N 64          /* contact schedule is shipped as one 64-bit mask per hopper            */
+
+typedef enum hmpc_error {
+    HMPC_OK = 0,
+    HMPC_ERR_BAD_ARG = -1,
+    HMPC_ERR_CUDA = -2,
+    HMPC_ERR_UNSUPPORTED = -3,
+    HMPC_ERR_NO_DEVICE = -4,
+    HMPC_ERR_ALLOC = -5
+} hmpc_error;
+
+/* per-hopper solve status (device int32 arrays) */
+typedef enum hmpc_status {
+    HMPC_SOLVED = 0,           /* KKT-verified optimum (polish accepted)                               */
+    HMPC_SOLVED_INEXACT = 4,   /* ADMM residual test met (eps_abs/eps_rel) but polish not verified     */
+    HMPC_MAX_ITER = 1,
+    HMPC_PRIMAL_INFEASIBLE = 2,/* x[0,2] or x[1,2] below z_min: u-independent rows;
+                                  the reference raises "QP FAILED" (mpc_cvx_euler_3f.py:158-159)       */
+    HMPC_NON_FINITE = 3
+} hmpc_status;
+
+enum { HMPC_DYN_2F = 2, HMPC_DYN_3F = 3 };                 /* mpc_cvx_euler_2f / mpc_cvx_euler_3f      */
+enum { HMPC_FP64 = 0, HMPC_FP32 = 1 };
+enum { HMPC_UREF_ALIASED = 0, HMPC_UREF_PER_STAGE = 1 };   /* SURVEY App. D1                           */
+enum { HMPC_MODE_EARLY_EXIT = 0, HMPC_MODE_FIXED_ITER = 1 };
+
+/* Constants of Mpc.__init__ (mpc_cvx_euler_3f.py:12-39), Runner.__init__ (robotrunner.py:37-79) and
+ * the literals inside build_qp (mpc_cvx_euler_3f.py:113-146), plus solver settings. */
+typedef struct hmpc_config {
+    int32_t abi_version;   /* = HMPC_ABI_VERSION */
+    int32_t device;        /* CUDA device ordinal */
+    int32_t batch;         /* B: hoppers handled by this handle */
+    int32_t dyn;           /* HMPC_DYN_2F | HMPC_DYN_3F */
+    int32_t N;             /* horizon (robotrunner.py:46 uses 60; benches 10/20/40) */
+    int32_t mpc_factor;    /* sim steps per MPC tick (robotrunner.py:48) = 20 */
+    int32_t precision;     /* HMPC_FP64 | HMPC_FP32 (FP32 not implemented yet -> HMPC_ERR_UNSUPPORTED) */
+    int32_t uref_mode;     /* HMPC_UREF_ALIASED (reference-faithful) | HMPC_UREF_PER_STAGE */
+    int32_t mode;          /* HMPC_MODE_EARLY_EXIT | HMPC_MODE_FIXED_ITER */
+    int32_t max_iter;      /* ADMM iteration cap (cvxpy passes 10000) */
+    int32_t check_interval;/* residual / polish / rho-adaptation cadence (OSQP: 25) */
+    int32_t polish;        /* 1: verified active-set polish (exact optimum); 0: plain ADMM */
+    int32_t adaptive_rho;  /* 1: OSQP residual-balancing rho update at check time */
+    int32_t warm_start;    /* 1: rollout warm-starts ADMM from the time-shifted previous (u,y) */
+    int32_t linsys;        /* 0 auto; 1 generic (Cholesky in smem/L2); 2 register-resident inverse */
+    int32_t reserved0;
+    double mpc_dt;         /* robotrunner.py:47  0.02  */
+    double sim_dt;         /* run.py:24          1e-3  */
+    double m, g, mu;       /* robotrunner.py:37,42,68 */
+    double J[9];           /* row-major inertia (robotrunner.py:38-40) */
+    double Jinv[9];        /* robotrunner.py:41 */
+    double rh[3];          /* robotrunner.py:42 */
+    double tau_max[3];     /* mpc_cvx_euler_3f.py:123-128  7.78, 7.78, 4 */
+    double fz_max;         /* mpc_cvx_euler_3f.py:20,146   206 */
+    double z_min;          /* mpc_cvx_euler_3f.py:129      0.1 */
+    double kf;             /* terminal state-cost factor, mpc_cvx_euler_3f.py:113 (100); input factor kuf=0 */
+    double eps_abs, eps_rel;   /* ADMM residual test (cvxpy: 1e-5 each) */
+    double rho0, sigma, alpha; /* OSQP defaults 0.1, 1e-6, 1.6 */
+    double polish_delta;       /* OSQP default 1e-6 */
+    double polish_tol;         /* KKT acceptance tolerance of the polish (relative), default 1e-9 */
+} hmpc_config;
+
+typedef struct hmpc_handle hmpc_handle;
+
+/* Fill a config with the reference's constants and OSQP/cvxpy solver defaults. */
+int hmpc_default_config(hmpc_config* cfg);
+
+/* Replaces Mpc.__init__ (mpc_cvx_euler_3f.py:12-39 / mpc_cvx_euler_2f.py:12-38) for a batch. */
+int hmpc_create(const hmpc_config* cfg, hmpc_handle** out);
+int hmpc_destroy(hmpc_handle* h);
+int hmpc_set_stream(hmpc_handle* h, void* cuda_stream);
+int hmpc_synchronize(hmpc_handle* h);
+
+/* Per-hopper gains: the public Mpc.Q / Mpc.R attributes (mpc_cvx_euler_3f.py:34-37), diagonals only.
+ * Qdiag [12][B], Rdiag [6][B].  Defaults are the reference's values for every hopper. */
+int hmpc_set_gains(hmpc_handle* h, const double* Qdiag, const double* Rdiag);
+
+/* convert (robotrunner.py:19-28): X [13][B] -> x [12][B]. */
+int hmpc_convert(hmpc_handle* h, const double* X, double* x);
+
+/* rk4_normalized repeated nsteps times with a zero-order-hold control (robotrunner.py:154-164,
+ * dynamics_ct :126-152).  X [13][B] in/out, U [6][B], pf [3][B]; X_steps [nsteps][13][B] optional
+ * (may be NULL): the state after every step (X_traj rows, robotrunner.py:113). */
+int hmpc_rk4(hmpc_handle* h, double* X, const double* U, const double* pf, int nsteps, double* X_steps);
+
+/* gen_dt_dynamics (mpc_cvx_euler_3f.py:71-94 / 2f:70-94): x_guess [N+1][12][B], pf [N][3][B] ->
+ * Ad [N][12][12][B], Bd [N][12][6][B].  Exposed for parity tests; the solver never materialises these. */
+int hmpc_linearize(hmpc_handle* h, const double* x_guess, const double* pf, double* Ad, double* Bd);
+
+/* Condensed QP data for parity tests: given the linearisation point, emit
+ * H [n][n][B], g [n][B], lo/hi [m][B] in the slot layout  rows = [6N box | 4N friction | N height]
+ * (n = 6N, m = 11N).  Built from build_qp (mpc_cvx_euler_3f.py:96-153). */
+int hmpc_condense(hmpc_handle* h, const double* x_in, const double* x_guess, const double* x_ref,
+                  const double* pf, const uint64_t* Cbits, double* H, double* g, double* lo, double* hi);
+
+/* Mpc.mpcontrol (mpc_cvx_euler_3f.py:41-69): linearise, build and solve the QP for every hopper.
+ *   x_in  [12][B]        convert()ed current state
+ *   x_ref [N][12][B]     reference window (path_plan_grab, robotrunner.py:228-230)
+ *   pf    [N][3][B]      footstep window
+ *   Cbits [B]            contact schedule, bit k = C[k] != 0 (gait_map, robotrunner.py:172-180)
+ *   init                 1: first call (two solves, x_guess[1:] = x_ref);  0: time-shift the handle's
+ *                        previous solution (mpc_cvx_euler_3f.py:50-62)
+ *   U     [N][6][B]      out: u.value
+ *   Xsol  [N+1][12][B]   out: x.value (also kept inside the handle for the next time shift)
+ *   status, iters [B]    out: hmpc_status and ADMM iterations (int32)
+ */
+int hmpc_solve(hmpc_handle* h, const double* x_in, const double* x_ref, const double* pf,
+               const uint64_t* Cbits, int init, double* U, double* Xsol, int32_t* status,
+               int32_t* iters);
+
+/* Closed loop of Runner.run (robotrunner.py:96-113) for n_ticks MPC ticks, state resident in HBM:
+ * per tick: convert -> mpcontrol -> mpc_factor x rk4 with ZOH U[0].
+ *   X        [13][B]               in/out simulator state
+ *   xref_tab [T+N][12][B]          MPC-rate reference rows (row j = x_ref[j*mpc_factor])
+ *   pf_tab   [T+N][3][B]           MPC-rate footstep rows
+ *   C_tab    [T][B]                contact masks per tick
+ *   pf_switch[T][B] (uint8)        sim step within the tick at which pf_ref changes from row t to t+1
+ *                                  (mpc_factor = never)  -- reproduces pf_ref[k] at 1 kHz
+ *   tick0                          index of the first tick in the tables; init = 1 on the run's first tick
+ *   X_log    [n_ticks+1][13][B]    optional (may be NULL): state at every tick boundary
+ *   U_log    [n_ticks][6][B]       optional: applied control per tick (f_hist, robotrunner.py:111)
+ *   status   [B], iters [B]        worst status / accumulated iterations over the ticks
+ */
+int hmpc_rollout(hmpc_handle* h, double* X, const double* xref_tab, const double* pf_tab,
+                 const uint64_t* C_tab, const uint8_t* pf_switch, int tick0, int n_ticks, int init,
+                 double* X_log, double* U_log, int32_t* status, int32_t* iters);
+
+/* Counters since handle creation: kernels launched by this library (for bench gpu_launches). */
+int hmpc_launch_count(hmpc_handle* h, int64_t* n_launches);
+
+/* FP64 FMA peak microbenchmark (roofline denominator): returns TFLOP/s measured with a
+ * dependent-chain-free DFMA kernel on the handle's device. */
+int hmpc_measure_fp64_peak(hmpc_handle* h, double* tflops);
+
+const char* hmpc_last_error(void);
+int hmpc_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HMPC_H */
