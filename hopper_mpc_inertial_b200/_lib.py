@@ -15,28 +15,34 @@ HMPC_ABI_VERSION = 1
 HMPC_INF = 1e30
 DYN = {"2f": 2, "3f": 3}
 STATUS_SOLVED, STATUS_MAX_ITER, STATUS_INFEASIBLE, STATUS_NON_FINITE, STATUS_INEXACT = 0, 1, 2, 3, 4
+PATH_NONE, PATH_WARM, PATH_IPM_POLISH, PATH_IPM, PATH_ADMM = 0, 1, 2, 3, 4
+SOLVER = {"exact": 0, "admm": 1}
+MODE = {"early_exit": 0, "fixed_iter": 1}
+ON_INFEASIBLE = {"hold": 0, "respawn": 1}
 
 # every symbol include/hmpc.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = [
     "hmpc_default_config", "hmpc_create", "hmpc_destroy", "hmpc_set_stream", "hmpc_synchronize",
     "hmpc_set_gains", "hmpc_convert", "hmpc_rk4", "hmpc_linearize", "hmpc_condense", "hmpc_solve",
-    "hmpc_rollout", "hmpc_launch_count", "hmpc_measure_fp64_peak", "hmpc_last_error",
+    "hmpc_rollout", "hmpc_solve_stats", "hmpc_launch_count", "hmpc_measure_fp64_peak", "hmpc_last_error",
     "hmpc_abi_version",
 ]
 
 
 class HmpcConfig(C.Structure):
+    """Mirror of ``hmpc_config`` (include/hmpc.h) -- field order and types must match exactly."""
     _fields_ = [
         ("abi_version", C.c_int32), ("device", C.c_int32), ("batch", C.c_int32), ("dyn", C.c_int32),
         ("N", C.c_int32), ("mpc_factor", C.c_int32), ("precision", C.c_int32), ("uref_mode", C.c_int32),
-        ("mode", C.c_int32), ("max_iter", C.c_int32), ("check_interval", C.c_int32),
-        ("polish", C.c_int32), ("adaptive_rho", C.c_int32), ("warm_start", C.c_int32),
-        ("linsys", C.c_int32), ("reserved0", C.c_int32),
+        ("solver", C.c_int32), ("mode", C.c_int32), ("max_iter", C.c_int32), ("check_interval", C.c_int32),
+        ("first_check", C.c_int32), ("polish", C.c_int32), ("adaptive_rho", C.c_int32),
+        ("warm_start", C.c_int32), ("polish_retries", C.c_int32), ("ipm_max_iter", C.c_int32),
+        ("on_infeasible", C.c_int32), ("reserved0", C.c_int32),
         ("mpc_dt", C.c_double), ("sim_dt", C.c_double), ("m", C.c_double), ("g", C.c_double),
         ("mu", C.c_double), ("J", C.c_double * 9), ("Jinv", C.c_double * 9), ("rh", C.c_double * 3),
         ("tau_max", C.c_double * 3), ("fz_max", C.c_double), ("z_min", C.c_double), ("kf", C.c_double),
         ("eps_abs", C.c_double), ("eps_rel", C.c_double), ("rho0", C.c_double), ("sigma", C.c_double),
-        ("alpha", C.c_double), ("polish_delta", C.c_double), ("polish_tol", C.c_double),
+        ("alpha", C.c_double), ("kkt_eps", C.c_double), ("polish_tol", C.c_double), ("ipm_tol", C.c_double),
     ]
 
 
@@ -69,9 +75,10 @@ def load():
     lib.hmpc_convert.argtypes = [vp, vp, vp]
     lib.hmpc_rk4.argtypes = [vp, vp, vp, vp, i32, vp]
     lib.hmpc_linearize.argtypes = [vp, vp, vp, vp, vp]
-    lib.hmpc_condense.argtypes = [vp] + [vp] * 9
+    lib.hmpc_condense.argtypes = [vp] + [vp] * 10
     lib.hmpc_solve.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]
     lib.hmpc_rollout.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]
+    lib.hmpc_solve_stats.argtypes = [vp, vp, vp, vp]
     lib.hmpc_launch_count.argtypes = [vp, i64p]
     lib.hmpc_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
     for name in SYMBOLS:

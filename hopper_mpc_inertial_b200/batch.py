@@ -48,6 +48,12 @@ class BatchMpc:
         cfg = _lib.default_config()
         cfg.batch, cfg.N, cfg.dyn, cfg.device = int(batch), int(N), _lib.DYN[dyn], int(device)
         for k, v in overrides.items():
+            if k == "solver" and isinstance(v, str):
+                v = _lib.SOLVER[v]
+            if k == "mode" and isinstance(v, str):
+                v = _lib.MODE[v]
+            if k == "on_infeasible" and isinstance(v, str):
+                v = _lib.ON_INFEASIBLE[v]
             cur = getattr(cfg, k)
             if hasattr(cur, "__len__"):
                 arr = np.asarray(v, dtype=float).reshape(-1)
@@ -127,9 +133,10 @@ class BatchMpc:
         self._chk(pf, (N, 3, B)); self._chk(Cbits, (B,), torch.int64)
         H, g = self.empty(n, n, B), self.empty(n, B)
         lo, hi = self.empty(m, B), self.empty(m, B)
+        inf = self.empty(B, dtype=torch.int32)
         _lib.check(self.lib.hmpc_condense(self._h, _ptr(x_in), _ptr(x_guess), _ptr(x_ref), _ptr(pf),
-                                          _ptr(Cbits), _ptr(H), _ptr(g), _ptr(lo), _ptr(hi)))
-        return H, g, lo, hi
+                                          _ptr(Cbits), _ptr(H), _ptr(g), _ptr(lo), _ptr(hi), _ptr(inf)))
+        return H, g, lo, hi, inf
 
     def solve(self, x_in, x_ref, pf, Cbits, init, out=None):
         """mpcontrol for the batch.  Returns (U (N,6,B), Xsol (N+1,12,B), status (B,), iters (B,))."""
@@ -168,6 +175,14 @@ class BatchMpc:
                                          _ptr(out.get("X_log")), _ptr(out.get("U_log")),
                                          _ptr(out["status"]), _ptr(out["iters"])))
         return out
+
+    def solve_stats(self):
+        """Per-hopper (nfac, path, n_infeasible) of the last solve / accumulated over the last rollout."""
+        nf = self.empty(self.B, dtype=torch.int32)
+        pa = self.empty(self.B, dtype=torch.int32)
+        ni = self.empty(self.B, dtype=torch.int32)
+        _lib.check(self.lib.hmpc_solve_stats(self._h, _ptr(nf), _ptr(pa), _ptr(ni)))
+        return nf, pa, ni
 
     def launch_count(self):
         n = C.c_int64()

@@ -7,7 +7,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(_HERE, "csrc", "hmpc_api.cu")]
-DEPS = [os.path.join(_HERE, "csrc", f) for f in ("hmpc_api.cu", "hmpc_qp.cuh", "hmpc_sim.cuh")] + \
+DEPS = [os.path.join(_HERE, "csrc", f) for f in ("hmpc_api.cu", "hmpc_qp.cuh", "hmpc_mpc.cuh", "hmpc_sim.cuh")] + \
        [os.path.join(_HERE, "..", "include", "hmpc.h")]
 OUT = os.path.join(_HERE, "libhmpc_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -18,6 +18,7 @@
 #include "../../include/hmpc.h"
 #include "hmpc_sim.cuh"
 #include "hmpc_qp.cuh"
+#include "hmpc_mpc.cuh"
 
 namespace {
 
@@ -46,16 +47,22 @@ struct hmpc_handle {
     double* Rd = nullptr;     // [6][B]
     double* Xsol = nullptr;   // [N+1][12][B] previous QP state trajectory (x.value)
     double* Usol = nullptr;   // [N][6][B]    previous QP inputs (u.value)
+    int8_t* code = nullptr;   // [11N][B]     previous active set (+1 / -1 / 0 per constraint row)
+    int8_t* valid = nullptr;  // [B]          1: Xsol / Usol / code hold a solved previous tick
     double* xin = nullptr;    // [12][B]
     double* U0 = nullptr;     // [6][B]
     int32_t* st_tmp = nullptr;
     int32_t* it_tmp = nullptr;
+    int32_t* st_tick = nullptr;   // [B] status of the current tick (rollout: read by the simulator kernel)
+    int32_t* nfac = nullptr;      // [B]
+    int32_t* path = nullptr;      // [B]
+    int32_t* ninf = nullptr;      // [B]
     // solver launch geometry
     int mpc_threads = 128;
     int mpc_grid = 0;
     size_t mpc_smem = 0;
     bool mats_in_smem = false;
-    double* ws = nullptr;     // per-CTA matrix workspace (3 n^2 doubles each) when not in smem
+    double* ws = nullptr;     // per-CTA matrix workspace when the matrices do not fit in shared memory
     int64_t launches = 0;
 };
 
@@ -68,7 +75,8 @@ __global__ void __launch_bounds__(128)
 sim_kernel(SimConst c, int B, double* __restrict__ X, const double* __restrict__ U,
            const double* __restrict__ pfa, const double* __restrict__ pfb,
            const uint8_t* __restrict__ sw, int nsteps, double* __restrict__ xin_out,
-           double* __restrict__ Xlog, double* __restrict__ Ulog, double* __restrict__ Xsteps) {
+           double* __restrict__ Xlog, double* __restrict__ Ulog, double* __restrict__ Xsteps,
+           const int32_t* __restrict__ st_tick, const double* __restrict__ xref_next) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     double Xl[13], Ul[6], pa[3], pb[3];
@@ -79,11 +87,28 @@ sim_kernel(SimConst c, int B, double* __restrict__ X, const double* __restrict__
 #pragma unroll
     for (int i = 0; i < 3; ++i) { pa[i] = pfa[(size_t)i * B + b]; pb[i] = pfb ? pfb[(size_t)i * B + b] : pa[i]; }
     const int s = sw ? (int)sw[b] : nsteps;
-    for (int k = 0; k < nsteps; ++k) {
-        rk4_step(c, Xl, Ul, (k < s) ? pa : pb);
-        if (Xsteps) {
+    const bool respawn = st_tick && xref_next && st_tick[b] == HMPC_PRIMAL_INFEASIBLE;
+    if (respawn) {
+        // put the hopper back onto its reference at the next tick: position, yaw and world velocity of
+        // the reference row, level attitude, no body rates (HMPC_INFEASIBLE_RESPAWN)
+        double xr[12];
 #pragma unroll
-            for (int i = 0; i < 13; ++i) Xsteps[((size_t)k * 13 + i) * B + b] = Xl[i];
+        for (int i = 0; i < 12; ++i) xr[i] = xref_next[(size_t)i * B + b];
+        double sy, cy;
+        sincos(0.5 * xr[5], &sy, &cy);
+        Xl[0] = xr[0]; Xl[1] = xr[1]; Xl[2] = xr[2];
+        Xl[3] = cy; Xl[4] = 0.0; Xl[5] = 0.0; Xl[6] = sy;
+        double R[9];
+        quat_rotm(Xl + 3, R);
+        mat3T_vec(R, xr + 6, Xl + 7);
+        Xl[10] = Xl[11] = Xl[12] = 0.0;
+    } else {
+        for (int k = 0; k < nsteps; ++k) {
+            rk4_step(c, Xl, Ul, (k < s) ? pa : pb);
+            if (Xsteps) {
+#pragma unroll
+                for (int i = 0; i < 13; ++i) Xsteps[((size_t)k * 13 + i) * B + b] = Xl[i];
+            }
         }
     }
 #pragma unroll
@@ -116,140 +141,19 @@ __global__ void convert_kernel(int B, const double* __restrict__ X, double* __re
 }
 
 // ------------------------------------------------------------------------------------------------
-// shared set-up of one hopper's Work: carve shared memory, point the matrices
-// ------------------------------------------------------------------------------------------------
-__device__ inline void setup_work(Work& w, const QpConst& c, double* smem, double* ws, bool mats_in_smem) {
-    carve(w, smem, c.N);
-    const size_t n = 6 * (size_t)c.N;
-    double* mat = mats_in_smem ? smem + ((work_vec_doubles(c.N) + 1) & ~(size_t)1) : ws + (size_t)blockIdx.x * 3 * n * n;
-    w.H = mat; w.LC = mat + n * n; w.LR = mat + 2 * n * n;
-}
-
-__device__ inline void load_hopper(const QpConst& c, Work& w, int b, int B, const double* x_in,
-                                   const double* pf, const uint64_t* Cbits, const double* Qd,
-                                   const double* Rd) {
-    const int N = c.N, tid = threadIdx.x, T = blockDim.x;
-    for (int i = tid; i < 12; i += T) { w.xin[i] = x_in[(size_t)i * B + b]; w.Qd[i] = Qd[(size_t)i * B + b]; }
-    for (int i = tid; i < 6; i += T) w.Rd[i] = Rd[(size_t)i * B + b];
-    for (int i = tid; i < 3 * N; i += T) w.pfw[i] = pf[(size_t)i * B + b];
-    const uint64_t bits = Cbits[b];
-    for (int k = tid; k < N; k += T) w.stance[k] = (int)((bits >> k) & 1ull);
-}
-
-// linear rollout of the solution (mpc_cvx_euler_3f.py:133,140 dynamics rows): xs [(N+1)][12] in shared
-__device__ inline void rollout_solution(const QpConst& c, Work& w, const double* u, double* xs) {
-    const int N = c.N, tid = threadIdx.x;
-    const double dt = c.dt, gdt = -c.g * dt;
-    if (tid < 12) xs[tid] = w.xin[tid];
-    __syncthreads();
-    if (tid < 6) {
-        double acc = w.xin[6 + tid];
-        for (int k = 0; k < N; ++k) {
-            const double* uk = u + 6 * k;
-            if (tid < 3) {
-                const double* Bv = w.Bv + 9 * k + 3 * tid;
-                acc += Bv[0] * uk[0] + Bv[1] * uk[1] + Bv[2] * uk[2];
-                if (tid == 2) acc += gdt;
-            } else {
-                const double* Bw = w.Bw + 18 * k + 6 * (tid - 3);
-                acc += Bw[0] * uk[0] + Bw[1] * uk[1] + Bw[2] * uk[2] + Bw[3] * uk[3] + Bw[4] * uk[4] + Bw[5] * uk[5];
-            }
-            xs[12 * (k + 1) + 6 + tid] = acc;
-        }
-    }
-    __syncthreads();
-    if (tid < 6) {
-        double acc = w.xin[tid];
-        for (int k = 0; k < N; ++k) {
-            const double* xk = xs + 12 * k;
-            if (tid < 3) acc += dt * xk[6 + tid];
-            else {
-                const double cs = w.cz[k], sn = w.sz[k];
-                const double wx = xk[9], wy = xk[10], wz = xk[11];
-                const double r = (tid == 3) ? (cs * wx + sn * wy) : (tid == 4) ? (-sn * wx + cs * wy) : wz;
-                acc += dt * r;
-            }
-            xs[12 * (k + 1) + tid] = acc;
-        }
-    }
-    __syncthreads();
-}
-
-// ------------------------------------------------------------------------------------------------
-// K1+K2: mpcontrol for a batch (mpc_cvx_euler_3f.py:41-69)
+// K1+K2: mpcontrol for a batch (mpc_cvx_euler_3f.py:41-69).  Persistent CTAs, one hopper at a time.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-mpc_kernel(QpConst c, int B, int init, int mats_in_smem, double* __restrict__ ws,
-           const double* __restrict__ x_in, const double* __restrict__ x_ref,
-           const double* __restrict__ pf, const uint64_t* __restrict__ Cbits,
-           const double* __restrict__ Qd, const double* __restrict__ Rd,
-           double* __restrict__ Xsol /* handle state, in/out */, double* __restrict__ Usol,
-           double* __restrict__ U_out, double* __restrict__ X_out, double* __restrict__ U0_out,
-           int32_t* __restrict__ status, int32_t* __restrict__ iters, int accumulate) {
+mpc_kernel(QpConst c, int B, int mats_in_smem, double* __restrict__ ws, MpcIo io) {
     extern __shared__ double smem[];
     Work w;
     setup_work(w, c, smem, ws, mats_in_smem != 0);
-    const int N = c.N, n = 6 * N, m = 11 * N, tid = threadIdx.x, T = blockDim.x;
-    AOp A{N, n, c.dyn == 3 ? 1 : 0, c.mu, c.dt * c.dt / c.m, w.stance};
-    CholSys sys{n, w.LC, w.LR, w.dinv, w.H};
-    double* xs = w.err;   // reused after condense: solution trajectory [(N+1)][12]
-
+    const int N = c.N, n = 6 * N;
+    AOp A{N, n, c.dyn == 3 ? 1 : 0, c.mu, w.stance, w.hinv};
+    LinSys sys{n, w.ld, 0, 0, w.Lm, w.dinv, w.H, w.idx, w.grow};
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         __syncthreads();
-        load_hopper(c, w, b, B, x_in, pf, Cbits, Qd, Rd);
-        __syncthreads();
-        int st = 0, its = 0;
-        const int passes = init ? 2 : 1;
-        for (int pass = 0; pass < passes; ++pass) {
-            // linearisation point (mpc_cvx_euler_3f.py:50-62); only p and yaw of rows 0..N-1 matter
-            for (int k = tid; k < N; k += T) {
-                double* gp = w.gp + 4 * k;
-                if (k == 0) { gp[0] = w.xin[0]; gp[1] = w.xin[1]; gp[2] = w.xin[2]; gp[3] = w.xin[5]; }
-                else if (init && pass == 0) {
-                    const size_t o = (size_t)(k - 1) * 12;
-                    gp[0] = x_ref[(o + 0) * B + b]; gp[1] = x_ref[(o + 1) * B + b];
-                    gp[2] = x_ref[(o + 2) * B + b]; gp[3] = x_ref[(o + 5) * B + b];
-                } else if (init) {   // second pass of the first call: x_guess = x.value of pass 0
-                    gp[0] = xs[12 * k]; gp[1] = xs[12 * k + 1]; gp[2] = xs[12 * k + 2]; gp[3] = xs[12 * k + 5];
-                } else {             // time shift: x_guess[k] = x.value[k+1]
-                    const size_t o = (size_t)(k + 1) * 12;
-                    gp[0] = Xsol[(o + 0) * B + b]; gp[1] = Xsol[(o + 1) * B + b];
-                    gp[2] = Xsol[(o + 2) * B + b]; gp[3] = Xsol[(o + 5) * B + b];
-                }
-            }
-            __syncthreads();
-            const int infeasible = condense(c, w, x_ref + b, (size_t)B);
-            for (int i = tid; i < n; i += T) w.x[i] = 0.0;
-            for (int r = tid; r < m; r += T) w.y[r] = 0.0;
-            __syncthreads();
-            if (infeasible) {
-                st = 2;
-            } else {
-                SolveInfo info = admm_solve(c, w, sys, A);
-                its += info.iters;
-                if (info.status != 0 && st == 0) st = info.status;
-            }
-            rollout_solution(c, w, w.x, xs);
-        }
-        // outputs
-        for (int i = tid; i < (N + 1) * 12; i += T) {
-            Xsol[(size_t)i * B + b] = xs[i];
-            if (X_out) X_out[(size_t)i * B + b] = xs[i];
-        }
-        for (int i = tid; i < n; i += T) {
-            if (Usol) Usol[(size_t)i * B + b] = w.x[i];
-            if (U_out) U_out[(size_t)i * B + b] = w.x[i];
-        }
-        if (U0_out) for (int i = tid; i < 6; i += T) U0_out[(size_t)i * B + b] = w.x[i];
-        if (tid == 0) {
-            if (accumulate) {
-                if (status[b] == 0) status[b] = st;
-                iters[b] += its;
-            } else {
-                status[b] = st;
-                iters[b] = its;
-            }
-        }
+        mpc_hopper(c, w, sys, A, b, B, io);
     }
 }
 
@@ -295,7 +199,8 @@ __global__ void condense_kernel(QpConst c, int B, int mats_in_smem, double* __re
                                 const double* __restrict__ x_ref, const double* __restrict__ pf,
                                 const uint64_t* __restrict__ Cbits, const double* __restrict__ Qd,
                                 const double* __restrict__ Rd, double* __restrict__ H,
-                                double* __restrict__ g, double* __restrict__ lo, double* __restrict__ hi) {
+                                double* __restrict__ g, double* __restrict__ lo, double* __restrict__ hi,
+                                int32_t* __restrict__ infeasible) {
     extern __shared__ double smem[];
     Work w;
     setup_work(w, c, smem, ws, mats_in_smem != 0);
@@ -309,7 +214,8 @@ __global__ void condense_kernel(QpConst c, int B, int mats_in_smem, double* __re
             w.gp[4 * k + 2] = x_guess[(o + 2) * B + b]; w.gp[4 * k + 3] = x_guess[(o + 5) * B + b];
         }
         __syncthreads();
-        condense(c, w, x_ref + b, (size_t)B);
+        const int inf = condense(c, w, x_ref + b, (size_t)B);
+        if (infeasible && tid == 0) infeasible[b] = inf;
         for (int e = tid; e < n * n; e += T) H[(size_t)e * B + b] = w.H[e];
         for (int i = tid; i < n; i += T) g[(size_t)i * B + b] = w.g[i];
         for (int r = tid; r < m; r += T) { lo[(size_t)r * B + b] = w.lo[r]; hi[(size_t)r * B + b] = w.hi[r]; }
@@ -343,15 +249,16 @@ namespace {
 
 hmpc::QpConst make_qp_const(const hmpc_config& cfg) {
     hmpc::QpConst c;
-    c.N = cfg.N; c.dyn = cfg.dyn; c.uref_mode = cfg.uref_mode; c.mode = cfg.mode;
-    c.max_iter = cfg.max_iter; c.check = cfg.check_interval; c.polish = cfg.polish;
-    c.adaptive_rho = cfg.adaptive_rho;
+    c.N = cfg.N; c.dyn = cfg.dyn; c.uref_mode = cfg.uref_mode; c.solver = cfg.solver; c.mode = cfg.mode;
+    c.max_iter = cfg.max_iter; c.check = cfg.check_interval; c.first_check = cfg.first_check;
+    c.retries = cfg.polish_retries; c.adaptive_rho = cfg.adaptive_rho; c.warm_start = cfg.warm_start;
+    c.polish = cfg.polish; c.ipm_max_iter = cfg.ipm_max_iter;
     c.dt = cfg.mpc_dt; c.m = cfg.m; c.g = cfg.g; c.mu = cfg.mu;
     for (int i = 0; i < 9; ++i) c.Jinv[i] = cfg.Jinv[i];
     for (int i = 0; i < 3; ++i) { c.rh[i] = cfg.rh[i]; c.tau_max[i] = cfg.tau_max[i]; }
     c.fz_max = cfg.fz_max; c.z_min = cfg.z_min; c.kf = cfg.kf;
     c.eps_abs = cfg.eps_abs; c.eps_rel = cfg.eps_rel; c.rho0 = cfg.rho0; c.sigma = cfg.sigma;
-    c.alpha = cfg.alpha; c.delta = cfg.polish_delta; c.polish_tol = cfg.polish_tol;
+    c.alpha = cfg.alpha; c.kkt_eps = cfg.kkt_eps; c.polish_tol = cfg.polish_tol; c.ipm_tol = cfg.ipm_tol;
     return c;
 }
 
@@ -391,9 +298,11 @@ int hmpc_default_config(hmpc_config* cfg) {
     memset(cfg, 0, sizeof(*cfg));
     cfg->abi_version = HMPC_ABI_VERSION;
     cfg->device = 0; cfg->batch = 1; cfg->dyn = HMPC_DYN_3F; cfg->N = 60; cfg->mpc_factor = 20;
-    cfg->precision = HMPC_FP64; cfg->uref_mode = HMPC_UREF_ALIASED; cfg->mode = HMPC_MODE_EARLY_EXIT;
-    cfg->max_iter = 10000; cfg->check_interval = 25; cfg->polish = 1; cfg->adaptive_rho = 1;
-    cfg->warm_start = 0; cfg->linsys = 0;
+    cfg->precision = HMPC_FP64; cfg->uref_mode = HMPC_UREF_ALIASED;
+    cfg->solver = HMPC_SOLVER_EXACT; cfg->mode = HMPC_MODE_EARLY_EXIT;
+    cfg->max_iter = 10000; cfg->check_interval = 25; cfg->first_check = 25; cfg->polish = 1;   // cvxpy -> OSQP
+    cfg->adaptive_rho = 1; cfg->warm_start = 1; cfg->polish_retries = 8; cfg->ipm_max_iter = 40;
+    cfg->on_infeasible = HMPC_INFEASIBLE_HOLD;
     cfg->mpc_dt = 0.02; cfg->sim_dt = 1e-3; cfg->m = 7.5; cfg->g = 9.807; cfg->mu = 1.0;
     const double J[9] = {76148072.89e-9, 70089.52e-9, 2067970.36e-9, 70089.52e-9, 45477183.53e-9,
                          -87045.58e-9, 2067970.36e-9, -87045.58e-9, 76287220.47e-9};
@@ -403,7 +312,7 @@ int hmpc_default_config(hmpc_config* cfg) {
     cfg->tau_max[0] = 7.78; cfg->tau_max[1] = 7.78; cfg->tau_max[2] = 4.0;
     cfg->fz_max = 206.0; cfg->z_min = 0.1; cfg->kf = 100.0;
     cfg->eps_abs = 1e-5; cfg->eps_rel = 1e-5; cfg->rho0 = 0.1; cfg->sigma = 1e-6; cfg->alpha = 1.6;
-    cfg->polish_delta = 1e-5; cfg->polish_tol = 1e-9;
+    cfg->kkt_eps = 1e-9; cfg->polish_tol = 1e-9; cfg->ipm_tol = 1e-9;
     return HMPC_OK;
 }
 
@@ -416,7 +325,11 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
     if (cfg->dyn != HMPC_DYN_2F && cfg->dyn != HMPC_DYN_3F) return fail(HMPC_ERR_BAD_ARG, "dyn must be 2 or 3");
     if (cfg->precision != HMPC_FP64) return fail(HMPC_ERR_UNSUPPORTED, "only FP64 precision is implemented");
     if (cfg->mpc_factor < 1 || cfg->mpc_factor > 255) return fail(HMPC_ERR_BAD_ARG, "mpc_factor must be in [1,255]");
-    if (cfg->max_iter < 1 || cfg->check_interval < 1) return fail(HMPC_ERR_BAD_ARG, "max_iter/check_interval must be >= 1");
+    if (cfg->max_iter < 1 || cfg->check_interval < 1 || cfg->first_check < 1 || cfg->polish_retries < 0 ||
+        cfg->ipm_max_iter < 1)
+        return fail(HMPC_ERR_BAD_ARG, "max_iter/check_interval/first_check/ipm_max_iter must be >= 1, polish_retries >= 0");
+    if (cfg->solver != HMPC_SOLVER_EXACT && cfg->solver != HMPC_SOLVER_ADMM)
+        return fail(HMPC_ERR_BAD_ARG, "solver must be HMPC_SOLVER_EXACT or HMPC_SOLVER_ADMM");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(HMPC_ERR_NO_DEVICE, "no CUDA device available (there is no CPU fallback)");
@@ -435,12 +348,19 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
         (e = dalloc((void**)&h->Xsol, (N + 1) * 12 * B * 8)) != cudaSuccess ||
         (e = dalloc((void**)&h->Usol, N * 6 * B * 8)) != cudaSuccess ||
         (e = dalloc((void**)&h->xin, 12 * B * 8)) != cudaSuccess || (e = dalloc((void**)&h->U0, 6 * B * 8)) != cudaSuccess ||
-        (e = dalloc((void**)&h->st_tmp, B * 4)) != cudaSuccess || (e = dalloc((void**)&h->it_tmp, B * 4)) != cudaSuccess) {
+        (e = dalloc((void**)&h->st_tmp, B * 4)) != cudaSuccess || (e = dalloc((void**)&h->it_tmp, B * 4)) != cudaSuccess ||
+        (e = dalloc((void**)&h->st_tick, B * 4)) != cudaSuccess || (e = dalloc((void**)&h->nfac, B * 4)) != cudaSuccess ||
+        (e = dalloc((void**)&h->path, B * 4)) != cudaSuccess || (e = dalloc((void**)&h->ninf, B * 4)) != cudaSuccess ||
+        (e = dalloc((void**)&h->code, 11 * N * B)) != cudaSuccess || (e = dalloc((void**)&h->valid, B)) != cudaSuccess) {
         hmpc_destroy(h);
         return fail(HMPC_ERR_ALLOC, std::string("cudaMalloc: ") + cudaGetErrorString(e));
     }
     cudaMemset(h->Xsol, 0, (N + 1) * 12 * B * 8);
     cudaMemset(h->Usol, 0, N * 6 * B * 8);
+    cudaMemset(h->code, 0, 11 * N * B);
+    cudaMemset(h->valid, 0, B);
+    cudaMemset(h->st_tick, 0, B * 4); cudaMemset(h->nfac, 0, B * 4);
+    cudaMemset(h->path, 0, B * 4); cudaMemset(h->ninf, 0, B * 4);
     // default gains = the reference's (mpc_cvx_euler_3f.py:35,37)
     {
         const double Qref[12] = {50., 50., 2., 1., 1., 50., 1., 1., 1., 10., 10., 10.};
@@ -454,9 +374,9 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
     }
     // solver geometry
     const size_t vec_bytes = ((hmpc::work_vec_doubles((int)N) + 1) & ~(size_t)1) * 8;
-    const size_t mat_bytes = 3 * n * n * 8;
+    const size_t mat_bytes = hmpc::mat_doubles((int)N) * 8;
     const size_t smem_cap = (size_t)prop.sharedMemPerBlockOptin;
-    h->mats_in_smem = (vec_bytes + mat_bytes + 1024 <= smem_cap) && cfg->linsys != 3;
+    h->mats_in_smem = (vec_bytes + mat_bytes + 1024 <= smem_cap);
     h->mpc_smem = vec_bytes + (h->mats_in_smem ? mat_bytes : 0);
     if (h->mpc_smem > smem_cap) { hmpc_destroy(h); return fail(HMPC_ERR_UNSUPPORTED, "horizon too large for shared memory"); }
     h->mpc_threads = (n <= 128) ? 128 : 256;
@@ -489,6 +409,7 @@ int hmpc_destroy(hmpc_handle* h) {
     cudaSetDevice(h->cfg.device);
     cudaFree(h->Qd); cudaFree(h->Rd); cudaFree(h->Xsol); cudaFree(h->Usol); cudaFree(h->xin);
     cudaFree(h->U0); cudaFree(h->st_tmp); cudaFree(h->it_tmp); cudaFree(h->ws);
+    cudaFree(h->code); cudaFree(h->valid); cudaFree(h->st_tick); cudaFree(h->nfac); cudaFree(h->path); cudaFree(h->ninf);
     delete h;
     return HMPC_OK;
 }
@@ -528,7 +449,7 @@ int hmpc_rk4(hmpc_handle* h, double* X, const double* U, const double* pf, int n
     if (!X || !U || !pf || nsteps < 0) return fail(HMPC_ERR_BAD_ARG, "bad argument");
     const int B = h->cfg.batch;
     hmpc::sim_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(make_sim_const(h->cfg), B, X, U, pf, nullptr,
-                                                              nullptr, nsteps, nullptr, nullptr, nullptr, X_steps);
+                                                              nullptr, nsteps, nullptr, nullptr, nullptr, X_steps, nullptr, nullptr);
     ++h->launches;
     HMPC_CUDA(cudaGetLastError());
     return HMPC_OK;
@@ -546,25 +467,43 @@ int hmpc_linearize(hmpc_handle* h, const double* x_guess, const double* pf, doub
 }
 
 int hmpc_condense(hmpc_handle* h, const double* x_in, const double* x_guess, const double* x_ref,
-                  const double* pf, const uint64_t* Cbits, double* H, double* g, double* lo, double* hi) {
+                  const double* pf, const uint64_t* Cbits, double* H, double* g, double* lo, double* hi,
+                  int32_t* infeasible) {
     if (int rc = check_handle(h)) return rc;
     if (!x_in || !x_guess || !x_ref || !pf || !Cbits || !H || !g || !lo || !hi)
         return fail(HMPC_ERR_BAD_ARG, "null array");
     hmpc::condense_kernel<<<h->mpc_grid, h->mpc_threads, h->mpc_smem, h->stream>>>(
         make_qp_const(h->cfg), h->cfg.batch, h->mats_in_smem ? 1 : 0, h->ws, x_in, x_guess, x_ref, pf, Cbits,
-        h->Qd, h->Rd, H, g, lo, hi);
+        h->Qd, h->Rd, H, g, lo, hi, infeasible);
     ++h->launches;
     HMPC_CUDA(cudaGetLastError());
     return HMPC_OK;
 }
 
+namespace {
+hmpc::MpcIo make_io(hmpc_handle* h, const double* x_in, const double* x_ref, const double* pf,
+                    const uint64_t* Cbits, int init, int accumulate, double* U, double* Xsol, double* U0,
+                    int32_t* status, int32_t* iters) {
+    hmpc::MpcIo io;
+    io.x_in = x_in; io.x_ref = x_ref; io.pf = pf; io.Cbits = Cbits; io.Qd = h->Qd; io.Rd = h->Rd;
+    io.Xsol = h->Xsol; io.Usol = h->Usol; io.code = h->code; io.valid = h->valid;
+    io.U_out = U; io.X_out = Xsol; io.U0_out = U0;
+    io.status = status ? status : h->st_tmp; io.iters = iters ? iters : h->it_tmp;
+    io.st_tick = h->st_tick; io.nfac = h->nfac; io.path = h->path; io.ninf = h->ninf;
+    io.init = init; io.accumulate = accumulate;
+    io.respawn = (h->cfg.on_infeasible == HMPC_INFEASIBLE_RESPAWN) ? 1 : 0;
+    return io;
+}
+}  // namespace
+
 int hmpc_solve(hmpc_handle* h, const double* x_in, const double* x_ref, const double* pf,
                const uint64_t* Cbits, int init, double* U, double* Xsol, int32_t* status, int32_t* iters) {
     if (int rc = check_handle(h)) return rc;
     if (!x_in || !x_ref || !pf || !Cbits) return fail(HMPC_ERR_BAD_ARG, "null input array");
+    hmpc::MpcIo io = make_io(h, x_in, x_ref, pf, Cbits, init ? 1 : 0, 0, U, Xsol, nullptr, status, iters);
+    io.respawn = 0;   // per-hopper re-initialisation only exists inside hmpc_rollout
     hmpc::mpc_kernel<<<h->mpc_grid, h->mpc_threads, h->mpc_smem, h->stream>>>(
-        make_qp_const(h->cfg), h->cfg.batch, init ? 1 : 0, h->mats_in_smem ? 1 : 0, h->ws, x_in, x_ref, pf, Cbits,
-        h->Qd, h->Rd, h->Xsol, h->Usol, U, Xsol, nullptr, status ? status : h->st_tmp, iters ? iters : h->it_tmp, 0);
+        make_qp_const(h->cfg), h->cfg.batch, h->mats_in_smem ? 1 : 0, h->ws, io);
     ++h->launches;
     HMPC_CUDA(cudaGetLastError());
     return HMPC_OK;
@@ -582,26 +521,39 @@ int hmpc_rollout(hmpc_handle* h, double* X, const double* xref_tab, const double
     int32_t* it = iters ? iters : h->it_tmp;
     HMPC_CUDA(cudaMemsetAsync(st, 0, B * 4, h->stream));
     HMPC_CUDA(cudaMemsetAsync(it, 0, B * 4, h->stream));
+    HMPC_CUDA(cudaMemsetAsync(h->nfac, 0, B * 4, h->stream));
+    HMPC_CUDA(cudaMemsetAsync(h->ninf, 0, B * 4, h->stream));
     const hmpc::QpConst qc = make_qp_const(h->cfg);
     const hmpc::SimConst sc = make_sim_const(h->cfg);
     const int sim_grid = (Bi + 127) / 128;
+    const bool respawn = h->cfg.on_infeasible == HMPC_INFEASIBLE_RESPAWN;
     // x_in for the first tick; afterwards sim_kernel emits it fused with the integration
     hmpc::convert_kernel<<<sim_grid, 128, 0, h->stream>>>(Bi, X, h->xin);
     ++h->launches;
     if (X_log) HMPC_CUDA(cudaMemcpyAsync(X_log, X, 13 * B * 8, cudaMemcpyDeviceToDevice, h->stream));
     for (int t = 0; t < n_ticks; ++t) {
         const size_t row = (size_t)(tick0 + t);
+        hmpc::MpcIo io = make_io(h, h->xin, xref_tab + row * 12 * B, pf_tab + row * 3 * B, C_tab + row * B,
+                                 (init && t == 0) ? 1 : 0, 1, nullptr, nullptr, h->U0, st, it);
         hmpc::mpc_kernel<<<h->mpc_grid, h->mpc_threads, h->mpc_smem, h->stream>>>(
-            qc, Bi, (init && t == 0) ? 1 : 0, h->mats_in_smem ? 1 : 0, h->ws, h->xin, xref_tab + row * 12 * B,
-            pf_tab + row * 3 * B, C_tab + row * B, h->Qd, h->Rd, h->Xsol, h->Usol, nullptr, nullptr, h->U0, st, it, 1);
+            qc, Bi, h->mats_in_smem ? 1 : 0, h->ws, io);
         hmpc::sim_kernel<<<sim_grid, 128, 0, h->stream>>>(
             sc, Bi, X, h->U0, pf_tab + row * 3 * B, pf_tab + (row + 1) * 3 * B,
             pf_switch ? pf_switch + row * B : nullptr, h->cfg.mpc_factor, h->xin,
             X_log ? X_log + (size_t)(t + 1) * 13 * B : nullptr, U_log ? U_log + (size_t)t * 6 * B : nullptr,
-            nullptr);
+            nullptr, respawn ? h->st_tick : nullptr, respawn ? xref_tab + (row + 1) * 12 * B : nullptr);
         h->launches += 2;
     }
     HMPC_CUDA(cudaGetLastError());
+    return HMPC_OK;
+}
+
+int hmpc_solve_stats(hmpc_handle* h, int32_t* nfac, int32_t* path, int32_t* n_infeasible) {
+    if (int rc = check_handle(h)) return rc;
+    const size_t B = (size_t)h->cfg.batch;
+    if (nfac) HMPC_CUDA(cudaMemcpyAsync(nfac, h->nfac, B * 4, cudaMemcpyDeviceToDevice, h->stream));
+    if (path) HMPC_CUDA(cudaMemcpyAsync(path, h->path, B * 4, cudaMemcpyDeviceToDevice, h->stream));
+    if (n_infeasible) HMPC_CUDA(cudaMemcpyAsync(n_infeasible, h->ninf, B * 4, cudaMemcpyDeviceToDevice, h->stream));
     return HMPC_OK;
 }
 

@@ -1,8 +1,8 @@
-// hmpc_qp.cuh -- per-hopper MPC QP on the device: linearise, condense, ADMM + verified polish.
+// hmpc_qp.cuh -- per-hopper MPC QP on the device: linearise, condense, solve.
 //
-// One CTA owns one hopper's QP.  All vectors live in shared memory; the condensed Hessian H and the
-// factor of the KKT operator live in shared memory when they fit, else in a per-CTA slice of a global
-// workspace that stays L2-resident (persistent grid).
+// One CTA owns one hopper's QP.  Every vector lives in shared memory; the condensed Hessian H and the
+// triangular factor of the current KKT operator live in shared memory when they fit (N <= 10 at FP64),
+// else in a per-CTA slice of a global workspace that stays L2-resident (persistent grid).
 //
 // What is computed (reference file:line into the reference's src/):
 //   linearise   gen_dt_dynamics          mpc_cvx_euler_3f.py:71-94 / mpc_cvx_euler_2f.py:70-94
@@ -14,6 +14,16 @@
 //     p-rows  dt (i-a-1) Bv_a     theta-rows  dt W_{a+1,i} Bw_a     v-rows  Bv_a     w-rows  Bw_a
 // with W_{a+1,i} = sum_{l=a+1}^{i-1} Rz_l, so H is assembled block-by-block without forming S.
 // Constraint rows use a fixed slot layout (m = 11N):  [6N identity box | 4N friction | N height].
+// Height row k (k >= 2) is stored NORMALISED by its largest coefficient dt^2 (k-1)/m:
+//     sum_{j<=k-2} (k-j-1)/(k-1) fz_j  >=  (z_min - c_z[k]) m / (dt^2 (k-1)).
+//
+// Solvers (oracle/device_port.py is the numpy statement of the same algorithms):
+//   solve_exact   warm-started verified primal-dual active-set refinement; Mehrotra interior point as
+//                 the cold start / fallback; every accepted point passes the KKT test of the ORIGINAL QP
+//   admm_solve    OSQP iteration in the dense condensed form, fixed-iteration or
+//                 early-exit, residual-balancing rho adaptation
+// Linear algebra: one signed Cholesky  K = L S L'  (S = diag(+-1)) of the compacted operator -- the
+// positive definite  H + A'WA  (IPM, ADMM) or the quasi-definite  [[H_FF, G'],[G, -eps I]]  (polish).
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -24,13 +34,18 @@ namespace hmpc {
 constexpr double kInf = 1e30;
 constexpr double kInfThresh = 1e26;   // OSQP: OSQP_INFTY * MIN_SCALING
 constexpr double kRhoMin = 1e-6, kRhoMax = 1e6;
+constexpr int kNumMVec = 13;          // m-sized scratch vectors shared by the solvers
+
+enum { ST_SOLVED = 0, ST_MAX_ITER = 1, ST_INFEASIBLE = 2, ST_NON_FINITE = 3, ST_INEXACT = 4 };
+enum { PATH_NONE = 0, PATH_WARM = 1, PATH_IPM_POLISH = 2, PATH_IPM = 3, PATH_ADMM = 4 };
 
 struct QpConst {
-    int N, dyn, uref_mode, mode, max_iter, check, polish, adaptive_rho;
+    int N, dyn, uref_mode, solver, mode, max_iter, check, first_check, retries, adaptive_rho, warm_start;
+    int ipm_max_iter, polish;
     double dt, m, g, mu;
     double Jinv[9], rh[3], tau_max[3];
     double fz_max, z_min, kf;
-    double eps_abs, eps_rel, rho0, sigma, alpha, delta, polish_tol;
+    double eps_abs, eps_rel, rho0, sigma, alpha, kkt_eps, polish_tol, ipm_tol;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -46,34 +61,42 @@ struct Work {
     double *pfw;     // [N][3]
     double *xin;     // [12]
     double *cfree;   // [N+1][12] free response
-    double *err;     // [N+1][12] cfree[i] - xref[i-1]  (row 0 unused)
+    double *err;     // [N+1][12] cfree[i] - xref[i-1]  (row 0 unused); later the solution trajectory
     double *Qd, *Rd; // [12], [6]
-    // QP vectors
-    double *g, *lo, *hi, *rv;          // [n] [m] [m] [m]
-    double *x, *xt, *rhs, *z, *y, *wv; // n n n m m m
-    double *xp, *mul, *wp, *bnd, *tmp; // n m m m n   (polish: point, multipliers, penalties, bounds)
-    double *ts, *sc;                   // [m] scratch rows, [n] solve scratch
-    double *dinv;                      // [n]
-    double *red;                       // [64] reduction scratch
-    int *fixed;                        // [n]  1: variable eliminated a priori (lo == hi)
-    int *pin;                          // [n]  polish: variable pinned at a bound
-    int *code;                         // [m]  polish: +1 upper active, -1 lower active, 0 inactive
+    double *hinv;    // [N]  1/(k-1) height-row normalisation (k >= 2)
+    // QP data
+    double *g, *lo, *hi;               // [n] [m] [m]
+    // solver vectors
+    double *x, *xt, *rhs, *tmp, *xp, *sc, *dinv;   // [n] each
+    double *mv[kNumMVec];                          // [m] each (roles differ per solver)
+    double *red;                                   // [160] reduction scratch
+    int *fixed;                        // [n]  1: variable eliminated a priori (lo == hi == 0)
+    int *pin;                          // [n]  polish: variable pinned (fixed or at a bound)
+    int *idx;                          // [n]  compact list of the variables in the current system
+    int *grow;                         // [n]  polish: active general rows in the current system
+    int *code;                         // [m]  +1 upper active, -1 lower active, 0 inactive
+    int *side;                         // [m]  IPM: bit0 finite upper side, bit1 finite lower side
     int *stance;                       // [N]
-    // matrices (shared or global)
-    double *H, *LC, *LR;
+    int *cnt;                          // [4]  nF, ng, ...
+    // matrices (shared or global): H n x n row-major (symmetric, full); Lm n x ld column-major factor
+    double *H, *Lm;
+    int ld;
 };
 
+__host__ __device__ inline int factor_ld(int N) { return (6 * N) | 1; }   // odd -> conflict-free both ways
+__host__ __device__ inline size_t mat_doubles(int N) {
+    const size_t n = 6 * (size_t)N;
+    return n * n + n * (size_t)factor_ld(N);
+}
 __host__ __device__ inline size_t work_vec_doubles(int N) {
     const int n = 6 * N, m = 11 * N;
     size_t d = 0;
-    d += 4 * N + 2 * N + 2 * (N + 1) + 9 * N + 18 * N + 3 * N + 12 + 2 * 12 * (N + 1) + 12 + 6;
-    d += n + 3 * m;           // g lo hi rv
-    d += 3 * n + 3 * m;       // x xt rhs z y wv
-    d += n + 3 * m + n;       // xp mul wp bnd tmp
-    d += m + n;               // ts sc
-    d += n;                   // dinv
-    d += 64;                  // red
-    d += (2 * n + m + N + 1) / 2 + 1; // fixed, pin, code, stance (ints)
+    d += 4 * N + 2 * N + 2 * (N + 1) + 9 * N + 18 * N + 3 * N + 12 + 2 * 12 * (N + 1) + 12 + 6 + N;
+    d += n + 2 * m;           // g lo hi
+    d += 7 * n;               // x xt rhs tmp xp sc dinv
+    d += kNumMVec * m;
+    d += 160;                 // red
+    d += (4 * n + 2 * m + N + 4 + 1) / 2 + 1;   // ints
     return d;
 }
 
@@ -84,31 +107,40 @@ __device__ inline void carve(Work& w, double* base, int N) {
     w.gp = take(4 * N); w.cz = take(N); w.sz = take(N); w.PC = take(N + 1); w.PS = take(N + 1);
     w.Bv = take(9 * N); w.Bw = take(18 * N); w.pfw = take(3 * N); w.xin = take(12);
     w.cfree = take(12 * (N + 1)); w.err = take(12 * (N + 1)); w.Qd = take(12); w.Rd = take(6);
-    w.g = take(n); w.lo = take(m); w.hi = take(m); w.rv = take(m);
-    w.x = take(n); w.xt = take(n); w.rhs = take(n); w.z = take(m); w.y = take(m); w.wv = take(m);
-    w.xp = take(n); w.mul = take(m); w.wp = take(m); w.bnd = take(m); w.tmp = take(n);
-    w.ts = take(m); w.sc = take(n);
-    w.dinv = take(n); w.red = take(64);
+    w.hinv = take(N);
+    w.g = take(n); w.lo = take(m); w.hi = take(m);
+    w.x = take(n); w.xt = take(n); w.rhs = take(n); w.tmp = take(n); w.xp = take(n); w.sc = take(n);
+    w.dinv = take(n);
+    for (int i = 0; i < kNumMVec; ++i) w.mv[i] = take(m);
+    w.red = take(160);
     w.fixed = reinterpret_cast<int*>(p);
     w.pin = w.fixed + n;
-    w.code = w.pin + n;
-    w.stance = w.code + m;
+    w.idx = w.pin + n;
+    w.grow = w.idx + n;
+    w.code = w.grow + n;
+    w.side = w.code + m;
+    w.stance = w.side + m;
+    w.cnt = w.stance + N;
+    w.ld = factor_ld(N);
 }
 
 // ------------------------------------------------------------------------------------------------
-// block reductions (max) -- warp shuffles + one shared round
+// block reductions -- warp shuffles + one shared round.  OP: 0 max, 1 min, 2 sum.  Result in all threads.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double warp_max(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
+template <int OP>
+__device__ __forceinline__ double red_op(double a, double b) {
+    return OP == 0 ? fmax(a, b) : (OP == 1 ? fmin(a, b) : a + b);
 }
-// reduces K values at once; result valid in all threads. NaN-propagating via flag in slot K.
-template <int K>
-__device__ inline void block_max(double (&v)[K], double* red) {
+template <int K, int OP>
+__device__ inline void block_reduce(double (&v)[K], double* red) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#ifndef HMPC_HOST_EMUL   // tests/emul runs this source as one serial "thread" on the CPU
 #pragma unroll
-    for (int k = 0; k < K; ++k) v[k] = warp_max(v[k]);
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] = red_op<OP>(v[k], __shfl_xor_sync(0xffffffffu, v[k], o));
+    }
+#endif
     __syncthreads();
     if (lane == 0) {
 #pragma unroll
@@ -118,7 +150,7 @@ __device__ inline void block_max(double (&v)[K], double* red) {
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         double r = red[k];
-        for (int q = 1; q < nw; ++q) r = fmax(r, red[q * K + k]);
+        for (int q = 1; q < nw; ++q) r = red_op<OP>(r, red[q * K + k]);
         v[k] = r;
     }
 }
@@ -128,12 +160,13 @@ __device__ inline void block_max(double (&v)[K], double* red) {
 //   rows 0..n-1        identity
 //   rows n+4k+s        friction, stance stages only:  s=0: fx-mu fz, 1: -fx-mu fz, 2: fy-mu fz, 3: -fy-mu fz
 //                      (s>=2 disabled for 2f)
-//   rows n+4N+k        height z_k (k>=2):  sum_{j<=k-2} dt^2 (k-j-1)/m * fz_j
+//   rows n+4N+k        height z_k (k>=2), normalised:  sum_{j<=k-2} (k-j-1)/(k-1) * fz_j
 // ------------------------------------------------------------------------------------------------
 struct AOp {
     int N, n, fy_rows;   // fy_rows: 1 for 3f
-    double mu, zc;       // zc = dt^2/m
+    double mu;
     const int* stance;
+    const double* hinv;  // [N] 1/(k-1)
     __device__ __forceinline__ bool fr_on(int k, int s) const { return stance[k] && (s < 2 || fy_rows); }
     __device__ inline double row(int r, const double* x) const {
         if (r < n) return x[r];
@@ -145,9 +178,25 @@ struct AOp {
             return sg * x[6 * k + (s >> 1)] - mu * x[6 * k + 2];
         }
         const int k = r - 4 * N;
+        if (k < 2) return 0.0;
         double acc = 0.0;
-        for (int j = 0; j + 2 <= k; ++j) acc += zc * (double)(k - j - 1) * x[6 * j + 2];
-        return acc;
+        for (int j = 0; j + 2 <= k; ++j) acc += (double)(k - j - 1) * x[6 * j + 2];
+        return acc * hinv[k];
+    }
+    // coefficient of general row r (r >= n) at variable v
+    __device__ inline double coef(int r, int v) const {
+        r -= n;
+        const int kv = v / 6, cv = v - 6 * kv;
+        if (r < 4 * N) {
+            const int k = r >> 2, s = r & 3;
+            if (k != kv || !fr_on(k, s)) return 0.0;
+            if (cv == 2) return -mu;
+            if (cv == (s >> 1)) return (s & 1) ? -1.0 : 1.0;
+            return 0.0;
+        }
+        const int k = r - 4 * N;
+        if (cv != 2 || k < 2 || kv + 2 > k) return 0.0;
+        return (double)(k - kv - 1) * hinv[k];
     }
     // (A^T v)_i
     __device__ inline double colT(int i, const double* v) const {
@@ -162,7 +211,7 @@ struct AOp {
         }
         if (c == 2) {
             const double* zr = v + n + 4 * N;
-            for (int kk = k + 2; kk < N; ++kk) acc += zc * (double)(kk - k - 1) * zr[kk];
+            for (int kk = k + 2; kk < N; ++kk) acc += (double)(kk - k - 1) * hinv[kk] * zr[kk];
         }
         return acc;
     }
@@ -184,8 +233,10 @@ struct AOp {
         if (ci == 2 && cj == 2) {
             const double* zr = w + n + 4 * N;
             const int k0 = (ki > kj ? ki : kj) + 2;
-            for (int kk = k0; kk < N; ++kk)
-                acc += zr[kk] * zc * zc * (double)(kk - ki - 1) * (double)(kk - kj - 1);
+            for (int kk = k0; kk < N; ++kk) {
+                const double h = hinv[kk];
+                acc += zr[kk] * h * h * (double)(kk - ki - 1) * (double)(kk - kj - 1);
+            }
         }
         return acc;
     }
@@ -268,7 +319,10 @@ __device__ inline void linearize_stage(const QpConst& c, int k, Work& w) {
 // ------------------------------------------------------------------------------------------------
 __device__ inline int condense(const QpConst& c, Work& w, const double* xref, size_t xs) {
     const int N = c.N, n = 6 * N, m = 11 * N, tid = threadIdx.x, T = blockDim.x;
-    for (int k = tid; k < N; k += T) linearize_stage(c, k, w);
+    for (int k = tid; k < N; k += T) {
+        linearize_stage(c, k, w);
+        w.hinv[k] = (k >= 2) ? 1.0 / (double)(k - 1) : 0.0;
+    }
     __syncthreads();
     if (tid == 0) {
         double pc = 0, ps = 0;
@@ -311,9 +365,18 @@ __device__ inline int condense(const QpConst& c, Work& w, const double* xref, si
         w.lo[r] = lo; w.hi[r] = hi;
     }
     __syncthreads();
-    // height rows need cfree
-    int infeasible = (w.cfree[2] < c.z_min) || (N >= 1 && w.cfree[12 + 2] < c.z_min);
-    for (int k = 2 + tid; k < N; k += T) w.lo[n + 4 * N + k] = c.z_min - w.cfree[12 * k + 2];
+    // height rows need cfree.  Exact feasibility (all-threads result): the height rows are monotone in
+    // the stance fz and fz = fz_max, fx = fy = 0 satisfies every other row, so the QP is feasible iff
+    // z_k(fz = fz_max on stance stages) >= z_min for k = 0..N-1 (k = 0, 1 are u-independent, App. D2).
+    const double zc = dt * dt / c.m;
+    int infeasible = 0;
+    for (int k = tid; k < N; k += T) {
+        double up = 0.0;
+        for (int j = 0; j + 2 <= k; ++j) if (w.stance[j]) up += (double)(k - j - 1);
+        if (w.cfree[12 * k + 2] + zc * c.fz_max * up < c.z_min) infeasible = 1;
+        if (k >= 2) w.lo[n + 4 * N + k] = (c.z_min - w.cfree[12 * k + 2]) / (zc * (double)(k - 1));
+    }
+    infeasible = __syncthreads_or(infeasible);
     // Hessian blocks, lower block-triangle a >= b
     const int nblk = N * (N + 1) / 2;
     const double q3 = w.Qd[3], q4 = w.Qd[4], q5 = w.Qd[5];
@@ -392,61 +455,80 @@ __device__ inline int condense(const QpConst& c, Work& w, const double* xref, si
 }
 
 // ------------------------------------------------------------------------------------------------
-// Generic linear-system policy: dense Cholesky of
-//     K = H + dadd I + diag(wbox) + A_g' diag(w_g) A_g       with eliminated variables as identity rows
-// stored column-major in LC and row-major in LR (so both substitutions stream contiguous memory).
+// Signed Cholesky  K = L S L'  (S = diag(+1 ... +1, -1 ... -1)) of the compact system, nk = nF + ng:
+//   variables  idx[0..nF)   full variable indices kept in the system
+//   rows       grow[0..ng)  active general rows (polish only); they follow the variables
+//   K_vv = H[idx_i][idx_j] + (wts ? (A' diag(wts) A)_ij : 0) + dadd [i==j];  K_rv = A.coef;  K_rr = -eps I
+// With ng = 0 this is the plain Cholesky of the positive definite IPM / ADMM operator; with ng > 0 the
+// matrix is quasi-definite and the signed factorisation exists for every ordering (no pivoting).
+// L is stored column-major with an odd leading dimension so that column (forward substitution) and
+// row (backward substitution) accesses are both free of shared-memory bank conflicts.
 // ------------------------------------------------------------------------------------------------
-struct CholSys {
-    int n;
-    double *LC, *LR, *dinv;
+struct LinSys {
+    int n, ld, nF, ng;
+    double *Lm, *dinv;
     const double* H;
-    // wts: [m] row weights (identity rows first).  fixed: variables pinned -> identity row/col.
-    __device__ inline int factor(const AOp& A, const double* wts, double dadd, const int* fixed, double* red) {
-        const int tid = threadIdx.x, T = blockDim.x;
+    const int *idx, *grow;
+
+    __device__ inline double entry(const AOp& A, const double* wts, double dadd, double eps, int i, int j) const {
+        if (i < nF) {   // i >= j
+            const int vi = idx[i], vj = idx[j];
+            double s = H[(size_t)vj * n + vi];
+            if (wts) { s += A.gram(vi, vj, wts); if (i == j) s += wts[vi]; }
+            if (i == j) s += dadd;
+            return s;
+        }
+        if (j < nF) return A.coef(grow[i - nF], idx[j]);
+        return (i == j) ? -eps : 0.0;
+    }
+
+    // Returns nonzero (same value in all threads) when a pivot has the wrong sign or is not finite.
+    __device__ inline int factor(const AOp& A, const double* wts, double dadd, double eps, double* red) {
+        const int tid = threadIdx.x, T = blockDim.x, nk = nF + ng;
         int bad = 0;
-        for (int j = 0; j < n; ++j) {
-            const bool fj = fixed[j] != 0;
-            for (int i = j + tid; i < n; i += T) {
-                double s;
-                if (fj || fixed[i]) s = (i == j) ? 1.0 : 0.0;
-                else {
-                    s = H[(size_t)j * n + i] + A.gram(i, j, wts);
-                    if (i == j) s += dadd + wts[i];
-                    const double* li = LC + i; const double* lj = LC + j;
-                    for (int k = 0; k < j; ++k) s -= li[(size_t)k * n] * lj[(size_t)k * n];
-                }
-                LC[(size_t)j * n + i] = s;
+        for (int j = 0; j < nk; ++j) {
+            const int kpos = j < nF ? j : nF;   // columns k < kpos carry S = +1, columns kpos..j-1 carry -1
+            for (int i = j + tid; i < nk; i += T) {
+                const double* li = Lm + i;
+                const double* lj = Lm + j;
+                double acc = 0.0, acn = 0.0;
+                for (int k = 0; k < kpos; ++k) acc += li[(size_t)k * ld] * lj[(size_t)k * ld];
+                for (int k = kpos; k < j; ++k) acn += li[(size_t)k * ld] * lj[(size_t)k * ld];
+                const double s = entry(A, wts, dadd, eps, i, j) - acc + acn;
+                Lm[(size_t)j * ld + i] = s;
                 if (i == j) red[0] = s;
             }
             __syncthreads();
-            const double piv = red[0];
-            if (!(piv > 0.0)) bad = 1;
-            const double inv = rsqrt(piv > 0.0 ? piv : 1.0);
-            for (int i = j + tid; i < n; i += T) {
-                const double v = LC[(size_t)j * n + i] * inv;
-                LC[(size_t)j * n + i] = v;
-                LR[(size_t)i * n + j] = v;
-                if (i == j) dinv[j] = 1.0 / v;
+            const double sg = (j < nF) ? 1.0 : -1.0;
+            const double ap = red[0] * sg;
+            if (!(ap > 0.0) || !(ap < 1e300)) bad = 1;
+            const double inv = rsqrt((ap > 0.0 && ap < 1e300) ? ap : 1.0);
+            for (int i = j + tid; i < nk; i += T) {
+                const double s = Lm[(size_t)j * ld + i];
+                Lm[(size_t)j * ld + i] = (i == j) ? ap * inv : s * sg * inv;
+                if (i == j) dinv[j] = inv;
             }
             __syncthreads();
         }
         return bad;
     }
-    // solves K out = b; b is destroyed; out may not alias b.  Ends with a __syncthreads().
-    __device__ inline void solve(double* b, double* out, double* scratch) {
-        const int tid = threadIdx.x, T = blockDim.x;
+
+    // Solves K out = b for compact vectors of length nk.  b is destroyed, sc is scratch; out may alias b.
+    // Ends with a __syncthreads().
+    __device__ inline void solve(double* b, double* out, double* sc) const {
+        const int tid = threadIdx.x, T = blockDim.x, nk = nF + ng;
         __syncthreads();
-        for (int j = 0; j < n; ++j) {
-            const double wj = b[j] * dinv[j];
-            const double* col = LC + (size_t)j * n;
-            for (int i = j + 1 + tid; i < n; i += T) b[i] -= col[i] * wj;
-            if (tid == 0) scratch[j] = wj;
+        for (int j = 0; j < nk; ++j) {            // L y = b
+            const double yj = b[j] * dinv[j];
+            const double* col = Lm + (size_t)j * ld;
+            for (int i = j + 1 + tid; i < nk; i += T) b[i] -= col[i] * yj;
+            if (tid == 0) sc[j] = (j < nF) ? yj : -yj;   // z = S y
             __syncthreads();
         }
-        for (int j = n - 1; j >= 0; --j) {
-            const double xj = scratch[j] * dinv[j];
-            const double* row = LR + (size_t)j * n;
-            for (int i = tid; i < j; i += T) scratch[i] -= row[i] * xj;
+        for (int j = nk - 1; j >= 0; --j) {       // L' x = z
+            const double xj = sc[j] * dinv[j];
+            const double* rowj = Lm + j;
+            for (int i = tid; i < j; i += T) sc[i] -= rowj[(size_t)i * ld] * xj;
             if (tid == 0) out[j] = xj;
             __syncthreads();
         }
@@ -461,193 +543,464 @@ __device__ inline void sym_matvec(const double* H, int n, const double* x, doubl
     }
 }
 
-struct SolveInfo { int status, iters, nfac, npolish; double rho; };
+struct SolveInfo { int status, iters, nfac, path; double rho; };
 
 // ------------------------------------------------------------------------------------------------
-// Verified active-set polish.  Guess the active set from the ADMM iterate (z, y) with OSQP's rule,
-// pin box-active variables exactly (identity rows), put a 1/delta penalty on active friction/height
-// rows and run a few method-of-multipliers steps in correction form (each step is also a step of
-// iterative refinement).  The result is ACCEPTED only if it passes the KKT conditions of the original
-// QP: stationarity on free variables, feasibility of every row, equality on active rows and the sign
-// of every multiplier.  On success x <- solution, y <- multipliers and 1 is returned (all threads).
-// The system factor is overwritten either way.
+// Verified primal-dual active-set refinement (numpy statement: oracle/device_port.py polish_verified).
+//
+// w.code holds the active-set guess, w.xp the starting point.  Box-active and a-priori fixed variables
+// are pinned exactly; the active friction / height rows G enter the quasi-definite KKT system
+// [[H_FF, G'],[G, -eps I]], factorised once per trial and applied in correction form (iterative
+// refinement removes the eps perturbation) until the residuals stagnate.  The KKT conditions of the
+// ORIGINAL QP are then checked: stationarity on free variables, feasibility of every row, equality on
+// active rows, sign of every multiplier.  All satisfied -> accept (exact optimum).  Otherwise rows
+// whose multiplier has the wrong sign are released, violated rows are activated, and the trial is
+// repeated, at most c.retries times.
+// On success: w.x <- solution, w.mv[0] <- multipliers, w.code <- active set; returns 1 (all threads).
 // ------------------------------------------------------------------------------------------------
-template <class Sys>
-__device__ inline int polish_verified(const QpConst& c, Work& w, Sys& sys, const AOp& A, int& nfac) {
+__device__ inline int polish_verified(const QpConst& c, Work& w, LinSys& sys, const AOp& A, SolveInfo& info) {
     const int N = c.N, n = 6 * N, m = 11 * N, tid = threadIdx.x, T = blockDim.x;
-    int ngen_loc = 0;
-    for (int r = tid; r < m; r += T) {
-        const double z = w.z[r], y = w.y[r], lo = w.lo[r], hi = w.hi[r];
-        const bool low = (z - lo) < -y, upp = (hi - z) < y;
-        const int code = low ? -1 : (upp ? 1 : 0);
-        w.code[r] = code;
-        w.bnd[r] = low ? lo : hi;
-        w.mul[r] = 0.0;
-        if (r < n) {
-            const int pin = (w.fixed[r] || code != 0) ? 1 : 0;
-            w.pin[r] = pin;
-            w.wp[r] = 0.0;
-            w.xp[r] = pin ? (w.fixed[r] ? lo : (low ? lo : hi)) : w.x[r];
-        } else {
-            w.wp[r] = code ? 1.0 / c.delta : 0.0;
-            ngen_loc += (code != 0);
-        }
-    }
-    const int ngen = __syncthreads_or(ngen_loc);
-    const double dprox = ngen ? c.delta : 0.0;
-    ++nfac;
-    if (sys.factor(A, w.wp, dprox, w.pin, w.red)) return 0;
-    const int kmom = ngen ? 8 : 2;
-    for (int k = 0; k < kmom; ++k) {
-        // Newton step on the augmented Lagrangian at xp (exact for a quadratic; step 2+ also refines)
-        sym_matvec(w.H, n, w.xp, w.tmp);
-        for (int r = tid; r < m; r += T)
-            w.ts[r] = (r >= n && w.code[r]) ? w.mul[r] + w.wp[r] * (A.row(r, w.xp) - w.bnd[r]) : 0.0;
-        __syncthreads();
-        for (int i = tid; i < n; i += T)
-            w.rhs[i] = w.pin[i] ? 0.0 : -(w.tmp[i] + w.g[i] + A.colT(i, w.ts));
-        sys.solve(w.rhs, w.xt, w.sc);
-        for (int i = tid; i < n; i += T) w.xp[i] += w.xt[i];
-        __syncthreads();
-        for (int r = n + tid; r < m; r += T)
-            if (w.code[r]) w.mul[r] += w.wp[r] * (A.row(r, w.xp) - w.bnd[r]);
-        __syncthreads();
-    }
-    sym_matvec(w.H, n, w.xp, w.tmp);
-    for (int r = tid; r < m; r += T) w.ts[r] = (r >= n && w.code[r]) ? w.mul[r] : 0.0;
-    __syncthreads();
-    // ---- KKT verification on the ORIGINAL problem (ts = multipliers of general rows, tmp = H xp) ----
-    double v[5] = {0, 0, 0, 0, 0};   // stat, scale, feas, sign, |mult|
-    for (int i = tid; i < n; i += T) {
-        const double G = w.tmp[i] + w.g[i] + A.colT(i, w.ts);   // ts[i] == 0 on box rows
-        v[1] = fmax(v[1], fmax(fabs(w.tmp[i]), fabs(w.g[i])));
-        if (!w.pin[i]) v[0] = fmax(v[0], fabs(G));
-        else {
-            const double lam = -G;   // box multiplier from stationarity
-            w.mul[i] = lam;
-            v[4] = fmax(v[4], fabs(lam));
-            if (!w.fixed[i]) v[3] = fmax(v[3], w.code[i] > 0 ? -lam : lam);
-        }
-    }
-    for (int r = tid; r < m; r += T) {
-        const double ax = A.row(r, w.xp), lo = w.lo[r], hi = w.hi[r];
-        double f = fmax(lo - ax, ax - hi) / (1.0 + fmin(fabs(lo), fabs(hi)));
-        if (r >= n && w.code[r]) {
-            f = fmax(f, fabs(ax - w.bnd[r]) / (1.0 + fabs(w.bnd[r])));
-            const double lam = w.mul[r];
-            v[4] = fmax(v[4], fabs(lam));
-            v[3] = fmax(v[3], w.code[r] > 0 ? -lam : lam);
-        }
-        v[2] = fmax(v[2], f);
-    }
-    block_max<5>(v, w.red);
-    const double scale = fmax(1.0, v[1]);
     const double tol = c.polish_tol;
-    const bool ok = (v[0] <= tol * scale) && (v[2] <= tol) && (v[3] <= tol * fmax(scale, v[4])) &&
-                    (v[0] == v[0]) && (v[2] == v[2]) && (v[3] == v[3]);
-    if (ok) {
-        for (int i = tid; i < n; i += T) { w.x[i] = w.xp[i]; w.y[i] = w.pin[i] ? w.mul[i] : 0.0; }
-        for (int r = n + tid; r < m; r += T) w.y[r] = w.code[r] ? w.mul[r] : 0.0;
-        __syncthreads();
-        for (int r = tid; r < m; r += T) w.z[r] = A.row(r, w.x);
-        __syncthreads();
+    double* mul = w.mv[0];
+    double* bnd = w.mv[1];
+    for (int r = tid; r < m; r += T) {
+        int cd = w.code[r];
+        if (cd > 0 && w.hi[r] > kInfThresh) cd = 0;
+        if (cd < 0 && w.lo[r] < -kInfThresh) cd = 0;
+        if (r < n && w.fixed[r]) cd = 0;
+        w.code[r] = cd;
     }
-    return ok ? 1 : 0;
+    __syncthreads();
+    for (int trial = 0; trial <= c.retries; ++trial) {
+        for (int r = tid; r < m; r += T) {
+            const int cd = w.code[r];
+            bnd[r] = cd < 0 ? w.lo[r] : w.hi[r];
+            mul[r] = 0.0;
+            if (r < n) {
+                const int pin = (w.fixed[r] || cd != 0) ? 1 : 0;
+                w.pin[r] = pin;
+                if (pin) w.xp[r] = w.fixed[r] ? 0.0 : bnd[r];
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int nF = 0, ng = 0;
+            for (int i = 0; i < n; ++i) if (!w.pin[i]) w.idx[nF++] = i;
+            for (int r = n; r < m; ++r) if (w.code[r] != 0) { if (ng < n) w.grow[ng] = r; ++ng; }
+            w.cnt[0] = nF; w.cnt[1] = ng;
+        }
+        __syncthreads();
+        const int nF = w.cnt[0], ng = w.cnt[1], nk = nF + ng;
+        if (nk > n) return 0;
+        sys.nF = nF; sys.ng = ng;
+        ++info.nfac;
+        if (sys.factor(A, nullptr, 0.0, c.kkt_eps, w.red)) return 0;
+        double prev = 1e300;
+        for (int k = 0; k < 6; ++k) {
+            sym_matvec(w.H, n, w.xp, w.tmp);
+            double v[1] = {0.0};
+            for (int i = tid; i < nk; i += T) {
+                double r_;
+                if (i < nF) { const int vi = w.idx[i]; r_ = -(w.tmp[vi] + w.g[vi] + A.colT(vi, mul)); }
+                else { const int rr = w.grow[i - nF]; r_ = bnd[rr] - A.row(rr, w.xp); }
+                w.rhs[i] = r_;
+                v[0] = fmax(v[0], fabs(r_));
+            }
+            block_reduce<1, 0>(v, w.red);
+            if (!(v[0] == v[0])) return 0;
+            if (k >= 2 && v[0] > 0.25 * prev) break;
+            prev = v[0];
+            sys.solve(w.rhs, w.xt, w.sc);
+            for (int i = tid; i < nk; i += T) {
+                if (i < nF) w.xp[w.idx[i]] += w.xt[i];
+                else mul[w.grow[i - nF]] += w.xt[i];
+            }
+            __syncthreads();
+        }
+        // ---- pass 1: multipliers of pinned variables, scales ----
+        sym_matvec(w.H, n, w.xp, w.tmp);
+        double v[3] = {0, 0, 0};   // stat, scale, |mult|
+        for (int i = tid; i < n; i += T) {
+            const double aty = A.colT(i, mul);   // mul[i] == 0 on box rows at this point
+            const double G = w.tmp[i] + w.g[i] + aty;
+            v[1] = fmax(v[1], fmax(fabs(w.tmp[i]), fmax(fabs(w.g[i]), fabs(aty))));
+            if (!w.pin[i]) v[0] = fmax(v[0], fabs(G));
+            else { w.sc[i] = -G; v[2] = fmax(v[2], fabs(G)); }
+        }
+        for (int r = n + tid; r < m; r += T) if (w.code[r]) v[2] = fmax(v[2], fabs(mul[r]));
+        block_reduce<3, 0>(v, w.red);
+        for (int i = tid; i < n; i += T) mul[i] = w.pin[i] ? w.sc[i] : 0.0;
+        __syncthreads();
+        const double scale = fmax(1.0, v[1]);
+        const double stol = tol * fmax(scale, v[2]);
+        // ---- pass 2: per-row verdicts and the refined active set ----
+        int bad = (v[0] <= 1e-10 * scale) ? 0 : 1, changed = 0;
+        if (!(v[0] == v[0]) || !(v[2] == v[2])) bad = 2;
+        for (int r = tid; r < m; r += T) {
+            const double ax = A.row(r, w.xp), lo = w.lo[r], hi = w.hi[r];
+            const int cd = w.code[r];
+            const bool apriori = (r < n) && w.fixed[r];
+            int ncode = cd;
+            if (cd != 0) {
+                const double lam = mul[r];
+                if ((cd > 0 && lam < -stol) || (cd < 0 && lam > stol)) { ncode = 0; bad |= 1; }
+                if (r >= n && fabs(ax - bnd[r]) > tol * (1.0 + fabs(bnd[r]))) bad |= 1;   // singular / inconsistent set
+            } else if (!apriori) {
+                if (lo - ax > tol * (1.0 + fabs(lo))) { ncode = -1; bad |= 1; }
+                else if (ax - hi > tol * (1.0 + fabs(hi))) { ncode = 1; bad |= 1; }
+            }
+            if (ncode != cd) { changed = 1; w.code[r] = ncode; }
+        }
+        bad = __syncthreads_or(bad);
+        changed = __syncthreads_or(changed);
+        if (!bad) {
+            for (int i = tid; i < n; i += T) w.x[i] = w.xp[i];
+            for (int r = n + tid; r < m; r += T) if (!w.code[r]) mul[r] = 0.0;
+            __syncthreads();
+            return 1;
+        }
+        if (!changed || (bad & 2)) return 0;
+    }
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
-// ADMM (OSQP iteration, SURVEY App. C2, dense-friendly form) + verified polish.
-// On entry: H, g, lo, hi, fixed set; x, y hold the warm start (or zeros).  On exit x = solution,
-// y = multipliers.  Variables with lo == hi (swing forces, 2f's fy) are eliminated exactly.
+// Mehrotra predictor-corrector interior point in the fixed row layout (numpy statement:
+// oracle/device_port.py ipm_solve).  Every row keeps an upper and a lower slack / multiplier pair;
+// sides at +-inf, rows of a-priori fixed variables and height rows without a free variable are masked.
+// Start: one Newton step of the quadratic penalty towards the row mid-points.
+// On exit w.x = iterate, w.code = active-set estimate (lambda > slack).  Returns 1 when converged.
 // ------------------------------------------------------------------------------------------------
-template <class Sys>
-__device__ inline SolveInfo admm_solve(const QpConst& c, Work& w, Sys& sys, const AOp& A) {
+__device__ inline int ipm_solve(const QpConst& c, Work& w, LinSys& sys, const AOp& A, SolveInfo& info) {
     const int N = c.N, n = 6 * N, m = 11 * N, tid = threadIdx.x, T = blockDim.x;
-    SolveInfo info{1 /*HMPC_MAX_ITER*/, 0, 0, 0, c.rho0};
+    double *su = w.mv[0], *sl = w.mv[1], *lu = w.mv[2], *ll = w.mv[3], *rpu = w.mv[4], *rpl = w.mv[5];
+    double *pu = w.mv[6], *pl = w.mv[7], *tv = w.mv[8], *adx = w.mv[9], *wts = w.mv[10];
+    const double s0 = 0.1;
+    // ---- sides ----
+    double cntv[1] = {0.0};
+    for (int r = tid; r < m; r += T) {
+        int s = 0;
+        bool on = true;
+        if (r < n) on = !w.fixed[r];
+        else if (r >= n + 4 * N) {
+            const int k = r - n - 4 * N;
+            on = false;
+            for (int j = 0; j + 2 <= k; ++j) on = on || (w.stance[j] != 0);
+        }
+        if (on) {
+            if (w.hi[r] < kInfThresh) s |= 1;
+            if (w.lo[r] > -kInfThresh) s |= 2;
+        }
+        w.side[r] = s;
+        cntv[0] += (double)((s & 1) + ((s >> 1) & 1));
+    }
+    block_reduce<1, 2>(cntv, w.red);
+    const double ni = cntv[0];
+    if (tid == 0) {
+        int nF = 0;
+        for (int i = 0; i < n; ++i) if (!w.fixed[i]) w.idx[nF++] = i;
+        w.cnt[0] = nF; w.cnt[1] = 0;
+    }
+    for (int i = tid; i < n; i += T) { w.x[i] = 0.0; w.xt[i] = 0.0; }
+    __syncthreads();
+    const int nF = w.cnt[0];
+    sys.nF = nF; sys.ng = 0;
+    // ---- start: minimise  1/2 x'Hx + g'x + 1/2 sum_r (a_r x - mid_r)^2  over the free variables ----
+    for (int r = tid; r < m; r += T) {
+        const int s = w.side[r];
+        const double lo = w.lo[r], hi = w.hi[r];
+        const double mid = (s == 3) ? 0.5 * (lo + hi) : (s == 1 ? hi - 1.0 : (s == 2 ? lo + 1.0 : 0.0));
+        wts[r] = s ? 1.0 : 0.0;
+        tv[r] = s ? -mid : 0.0;     // w0 (a_r x - mid) at x = 0
+        w.code[r] = 0;
+    }
+    __syncthreads();
+    ++info.nfac;
+    if (sys.factor(A, ni > 0.0 ? wts : nullptr, 0.0, 0.0, w.red)) return 0;
+    for (int i = tid; i < nF; i += T) { const int vi = w.idx[i]; w.rhs[i] = -w.g[vi] - (ni > 0.0 ? A.colT(vi, tv) : 0.0); }
+    sys.solve(w.rhs, w.rhs, w.sc);
+    for (int i = tid; i < nF; i += T) w.x[w.idx[i]] = w.rhs[i];
+    __syncthreads();
+    if (!(ni > 0.0)) return 1;   // no inequality at all: the Newton step is the optimum
+    double mn[1] = {1e300};
+    for (int r = tid; r < m; r += T) {
+        const int s = w.side[r];
+        const double ax = A.row(r, w.x);
+        const double a = (s & 1) ? w.hi[r] - ax : 1.0, b = (s & 2) ? ax - w.lo[r] : 1.0;
+        su[r] = a; sl[r] = b;
+        if (s & 1) mn[0] = fmin(mn[0], a);
+        if (s & 2) mn[0] = fmin(mn[0], b);
+    }
+    block_reduce<1, 1>(mn, w.red);
+    const double shift = fmax(0.0, -1.5 * mn[0]);
+    double gsv[1] = {0.0};
+    for (int i = tid; i < n; i += T) gsv[0] = fmax(gsv[0], fabs(w.g[i]));
+    for (int r = tid; r < m; r += T) {
+        const int s = w.side[r];
+        su[r] = fmax(su[r] + shift, s0); sl[r] = fmax(sl[r] + shift, s0);
+        lu[r] = (s & 1) ? s0 : 0.0; ll[r] = (s & 2) ? s0 : 0.0;
+    }
+    block_reduce<1, 0>(gsv, w.red);
+    const double gs = fmax(1.0, gsv[0]);
+    int conv = 0;
+    for (int it = 0; it <= c.ipm_max_iter; ++it) {
+        // ---- residuals ----
+        sym_matvec(w.H, n, w.x, w.tmp);
+        for (int r = tid; r < m; r += T) tv[r] = lu[r] - ll[r];
+        __syncthreads();
+        double v[2] = {0.0, 0.0};
+        double sm[1] = {0.0};
+        for (int i = tid; i < nF; i += T) {
+            const int vi = w.idx[i];
+            const double rd = w.tmp[vi] + w.g[vi] + A.colT(vi, tv);
+            w.xp[vi] = rd;                       // rd kept in xp (full index)
+            v[0] = fmax(v[0], fabs(rd));
+        }
+        for (int r = tid; r < m; r += T) {
+            const int s = w.side[r];
+            const double ax = A.row(r, w.x);
+            const double a = (s & 1) ? ax + su[r] - w.hi[r] : 0.0;
+            const double b = (s & 2) ? -ax + sl[r] + w.lo[r] : 0.0;
+            rpu[r] = a; rpl[r] = b;
+            v[1] = fmax(v[1], fmax(fabs(a), fabs(b)));
+            if (s & 1) sm[0] += su[r] * lu[r];
+            if (s & 2) sm[0] += sl[r] * ll[r];
+        }
+        block_reduce<2, 0>(v, w.red);
+        block_reduce<1, 2>(sm, w.red);
+        const double mu = sm[0] / ni;
+        if (!(mu == mu) || !(v[0] == v[0]) || !(v[1] == v[1])) break;
+        if (v[0] < c.ipm_tol * gs && v[1] < c.ipm_tol && mu < c.ipm_tol) { conv = 1; break; }
+        if (it == c.ipm_max_iter) break;
+        info.iters = it + 1;
+        // ---- factor  H + A' diag(lambda/s) A ----
+        for (int r = tid; r < m; r += T) {
+            const int s = w.side[r];
+            wts[r] = ((s & 1) ? lu[r] / su[r] : 0.0) + ((s & 2) ? ll[r] / sl[r] : 0.0);
+        }
+        __syncthreads();
+        ++info.nfac;
+        if (sys.factor(A, wts, 0.0, 0.0, w.red)) break;
+        double alpha = 1.0, sigmu = 0.0;
+        for (int phase = 0; phase < 2; ++phase) {
+            // complementarity targets: predictor rc = s*lam ; corrector rc = s*lam + ds*dlam - sigma*mu
+            for (int r = tid; r < m; r += T) {
+                const int s = w.side[r];
+                double tu = 0.0, tl = 0.0;
+                if (s & 1) { const double rc = su[r] * lu[r] + (phase ? pu[r] - sigmu : 0.0); tu = (lu[r] * rpu[r] - rc) / su[r]; }
+                if (s & 2) { const double rc = sl[r] * ll[r] + (phase ? pl[r] - sigmu : 0.0); tl = (ll[r] * rpl[r] - rc) / sl[r]; }
+                tv[r] = tu - tl;
+            }
+            __syncthreads();
+            for (int i = tid; i < nF; i += T) { const int vi = w.idx[i]; w.rhs[i] = -w.xp[vi] - A.colT(vi, tv); }
+            sys.solve(w.rhs, w.rhs, w.sc);
+            for (int i = tid; i < nF; i += T) w.xt[w.idx[i]] = w.rhs[i];
+            __syncthreads();
+            double rmin[1] = {1.0};
+            for (int r = tid; r < m; r += T) {
+                const int s = w.side[r];
+                const double ad = A.row(r, w.xt);
+                adx[r] = ad;
+                if (s & 1) {
+                    const double rc = su[r] * lu[r] + (phase ? pu[r] - sigmu : 0.0);
+                    const double ds = -rpu[r] - ad, dl = -(rc + lu[r] * ds) / su[r];
+                    if (ds < 0.0) rmin[0] = fmin(rmin[0], -su[r] / ds);
+                    if (dl < 0.0) rmin[0] = fmin(rmin[0], -lu[r] / dl);
+                }
+                if (s & 2) {
+                    const double rc = sl[r] * ll[r] + (phase ? pl[r] - sigmu : 0.0);
+                    const double ds = -rpl[r] + ad, dl = -(rc + ll[r] * ds) / sl[r];
+                    if (ds < 0.0) rmin[0] = fmin(rmin[0], -sl[r] / ds);
+                    if (dl < 0.0) rmin[0] = fmin(rmin[0], -ll[r] / dl);
+                }
+            }
+            block_reduce<1, 1>(rmin, w.red);
+            if (phase == 0) {
+                const double a = rmin[0];
+                double ma[1] = {0.0};
+                for (int r = tid; r < m; r += T) {
+                    const int s = w.side[r];
+                    const double ad = adx[r];
+                    if (s & 1) {
+                        const double ds = -rpu[r] - ad, dl = -(su[r] * lu[r] + lu[r] * ds) / su[r];
+                        pu[r] = ds * dl;
+                        ma[0] += (su[r] + a * ds) * (lu[r] + a * dl);
+                    }
+                    if (s & 2) {
+                        const double ds = -rpl[r] + ad, dl = -(sl[r] * ll[r] + ll[r] * ds) / sl[r];
+                        pl[r] = ds * dl;
+                        ma[0] += (sl[r] + a * ds) * (ll[r] + a * dl);
+                    }
+                }
+                block_reduce<1, 2>(ma, w.red);
+                const double ratio = (ma[0] / ni) / mu;
+                sigmu = ratio * ratio * ratio * mu;
+            } else {
+                alpha = fmin(1.0, 0.99 * rmin[0]);
+            }
+        }
+        // ---- step ----
+        for (int r = tid; r < m; r += T) {
+            const int s = w.side[r];
+            const double ad = adx[r];
+            if (s & 1) {
+                const double rc = su[r] * lu[r] + pu[r] - sigmu;
+                const double ds = -rpu[r] - ad, dl = -(rc + lu[r] * ds) / su[r];
+                su[r] += alpha * ds; lu[r] += alpha * dl;
+            }
+            if (s & 2) {
+                const double rc = sl[r] * ll[r] + pl[r] - sigmu;
+                const double ds = -rpl[r] + ad, dl = -(rc + ll[r] * ds) / sl[r];
+                sl[r] += alpha * ds; ll[r] += alpha * dl;
+            }
+        }
+        for (int i = tid; i < nF; i += T) { const int vi = w.idx[i]; w.x[vi] += alpha * w.xt[vi]; }
+        __syncthreads();
+    }
+    for (int r = tid; r < m; r += T) {
+        const int s = w.side[r];
+        w.code[r] = ((s & 1) && lu[r] > su[r]) ? 1 : (((s & 2) && ll[r] > sl[r]) ? -1 : 0);
+    }
+    __syncthreads();
+    return conv;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Default solver: warm-started verified active-set refinement, interior-point fallback, verified polish.
+// On entry (warm != 0): w.xp = time-shifted previous solution, w.code = time-shifted previous active set.
+// On exit: w.x = solution, w.code = active set (for the next tick's warm start).
+// ------------------------------------------------------------------------------------------------
+__device__ inline SolveInfo solve_exact(const QpConst& c, Work& w, LinSys& sys, const AOp& A, int warm) {
+    const int n = 6 * c.N, tid = threadIdx.x, T = blockDim.x;
+    SolveInfo info{ST_MAX_ITER, 0, 0, PATH_NONE, 0.0};
+    if (warm) {
+        if (polish_verified(c, w, sys, A, info)) { info.status = ST_SOLVED; info.path = PATH_WARM; return info; }
+        __syncthreads();
+    }
+    const int conv = ipm_solve(c, w, sys, A, info);
+    int nonfinite = 0;
+    for (int i = tid; i < n; i += T) {
+        const double v = w.x[i];
+        if (!(fabs(v) < 1e300)) nonfinite = 1;
+        w.xp[i] = v;
+    }
+    nonfinite = __syncthreads_or(nonfinite);
+    if (nonfinite) {
+        for (int i = tid; i < n; i += T) w.x[i] = 0.0;
+        __syncthreads();
+        info.status = ST_NON_FINITE; info.path = PATH_IPM;
+        return info;
+    }
+    if (polish_verified(c, w, sys, A, info)) { info.status = ST_SOLVED; info.path = PATH_IPM_POLISH; return info; }
+    info.status = conv ? ST_INEXACT : ST_MAX_ITER;
+    info.path = PATH_IPM;
+    return info;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ADMM (OSQP iteration, SURVEY App. C2, dense condensed form, no Ruiz scaling; numpy statement:
+// oracle/device_port.py admm_solve):
+//     x~ = K^-1 (sigma x - g + A'(rho z - y)),  K = H + sigma I + A' diag(rho) A   (free variables only)
+//     x+ = alpha x~ + (1-alpha) x ;  z+ = clip(alpha A x~ + (1-alpha) z + y/rho) ;  y+ = y + rho (.. - z+)
+// mode FIXED_ITER: exactly max_iter iterations, no checks.  mode EARLY_EXIT: OSQP's residual test every
+// c.check iterations after c.first_check, rho re-balanced (and K re-factorised) when it moves by > 5x.
+// On entry w.x / w.mv[2] hold the warm start (x, y) or zeros.  On exit w.x, w.mv[2] = (x, y) and
+// w.code = OSQP's polish guess of the active set.
+// ------------------------------------------------------------------------------------------------
+__device__ inline SolveInfo admm_solve(const QpConst& c, Work& w, LinSys& sys, const AOp& A) {
+    const int N = c.N, n = 6 * N, m = 11 * N, tid = threadIdx.x, T = blockDim.x;
+    SolveInfo info{ST_MAX_ITER, 0, 0, PATH_ADMM, c.rho0};
+    double *rv = w.mv[0], *z = w.mv[1], *y = w.mv[2], *wv = w.mv[3];
     double rho = c.rho0;
     const double sigma = c.sigma, alpha = c.alpha;
-
     auto set_rho = [&](double r) {
         for (int i = tid; i < m; i += T) {
             const double lo = w.lo[i], hi = w.hi[i];
             double v = r;
             if (lo < -kInfThresh && hi > kInfThresh) v = kRhoMin;
             else if (hi - lo < 1e-4) v = fmin(1e3 * r, kRhoMax);
-            w.rv[i] = v;
+            rv[i] = v;
         }
         __syncthreads();
     };
     set_rho(rho);
-    for (int i = tid; i < n; i += T) if (w.fixed[i]) w.x[i] = w.lo[i];
+    if (tid == 0) {
+        int nF = 0;
+        for (int i = 0; i < n; ++i) if (!w.fixed[i]) w.idx[nF++] = i;
+        w.cnt[0] = nF; w.cnt[1] = 0;
+    }
+    for (int i = tid; i < n; i += T) {
+        const double v = w.fixed[i] ? 0.0 : w.x[i];
+        w.x[i] = fmin(fmax(v, w.lo[i]), w.hi[i]);
+        w.xt[i] = 0.0;
+    }
     __syncthreads();
-    for (int r = tid; r < m; r += T) w.z[r] = fmin(fmax(A.row(r, w.x), w.lo[r]), w.hi[r]);
+    const int nF = w.cnt[0];
+    sys.nF = nF; sys.ng = 0;
+    for (int r = tid; r < m; r += T) z[r] = fmin(fmax(A.row(r, w.x), w.lo[r]), w.hi[r]);
     __syncthreads();
     info.nfac = 1;
-    if (sys.factor(A, w.rv, sigma, w.fixed, w.red)) { info.status = 3; return info; }
-
+    if (sys.factor(A, rv, sigma, 0.0, w.red)) { info.status = ST_NON_FINITE; return info; }
     const int last_it = c.max_iter;
-    bool conv = false;
+    int next_check = (c.mode == 1) ? last_it : min(c.first_check, last_it);
     for (int it = 1; it <= last_it; ++it) {
-        for (int r = tid; r < m; r += T) w.wv[r] = w.rv[r] * w.z[r] - w.y[r];
+        for (int r = tid; r < m; r += T) wv[r] = rv[r] * z[r] - y[r];
         __syncthreads();
-        for (int i = tid; i < n; i += T)
-            w.rhs[i] = w.fixed[i] ? w.lo[i] : (sigma * w.x[i] - w.g[i] + A.colT(i, w.wv));
-        sys.solve(w.rhs, w.xt, w.sc);
+        for (int i = tid; i < nF; i += T) { const int vi = w.idx[i]; w.rhs[i] = sigma * w.x[vi] - w.g[vi] + A.colT(vi, wv); }
+        sys.solve(w.rhs, w.rhs, w.sc);
+        for (int i = tid; i < nF; i += T) w.xt[w.idx[i]] = w.rhs[i];
+        __syncthreads();
         for (int r = tid; r < m; r += T) {
             const double zt = A.row(r, w.xt);
-            const double zr = alpha * zt + (1.0 - alpha) * w.z[r];
-            const double rv = w.rv[r];
-            const double zn = fmin(fmax(zr + w.y[r] / rv, w.lo[r]), w.hi[r]);
-            w.y[r] += rv * (zr - zn);
-            w.z[r] = zn;
+            const double zr = alpha * zt + (1.0 - alpha) * z[r];
+            const double rr = rv[r];
+            const double zn = fmin(fmax(zr + y[r] / rr, w.lo[r]), w.hi[r]);
+            y[r] += rr * (zr - zn);
+            z[r] = zn;
         }
         for (int i = tid; i < n; i += T) w.x[i] = alpha * w.xt[i] + (1.0 - alpha) * w.x[i];
         __syncthreads();
         info.iters = it;
-        const bool do_check = (c.mode == 1) ? (it == last_it) : (it % c.check == 0 || it == last_it);
-        if (!do_check) continue;
-
+        if (it != next_check && it != last_it) continue;
+        next_check = it + c.check;
         // ---- residuals of the unscaled problem (OSQP termination test) ----
         sym_matvec(w.H, n, w.x, w.tmp);
-        __syncthreads();
         double v[6] = {0, 0, 0, 0, 0, 0};   // pri, npri, dua, |Hx|, |A'y|, |g|
         for (int r = tid; r < m; r += T) {
             const double ax = A.row(r, w.x);
-            v[0] = fmax(v[0], fabs(ax - w.z[r]));
-            v[1] = fmax(v[1], fmax(fabs(ax), fabs(w.z[r])));
+            v[0] = fmax(v[0], fabs(ax - z[r]));
+            v[1] = fmax(v[1], fmax(fabs(ax), fabs(z[r])));
         }
         for (int i = tid; i < n; i += T) {
             if (w.fixed[i]) continue;   // eliminated variables carry an implicit multiplier
-            const double aty = A.colT(i, w.y);
+            const double aty = A.colT(i, y);
             v[2] = fmax(v[2], fabs(w.tmp[i] + w.g[i] + aty));
             v[3] = fmax(v[3], fabs(w.tmp[i]));
             v[4] = fmax(v[4], fabs(aty));
             v[5] = fmax(v[5], fabs(w.g[i]));
         }
-        block_max<6>(v, w.red);
+        block_reduce<6, 0>(v, w.red);
         const double pri = v[0], npri = v[1], dua = v[2], ndua = fmax(v[3], fmax(v[4], v[5]));
-        if (!(pri == pri) || !(dua == dua)) { info.status = 3; break; }
-        conv = pri <= c.eps_abs + c.eps_rel * npri && dua <= c.eps_abs + c.eps_rel * ndua;
-        if (!c.polish) {
-            if (conv) { info.status = 4; break; }
-        } else {
-            ++info.npolish;
-            if (polish_verified(c, w, sys, A, info.nfac)) { info.status = 0; break; }
-        }
+        if (!(pri == pri) || !(dua == dua)) { info.status = ST_NON_FINITE; break; }
+        if (c.mode == 1) break;
+        if (pri <= c.eps_abs + c.eps_rel * npri && dua <= c.eps_abs + c.eps_rel * ndua) { info.status = ST_INEXACT; break; }
         if (it == last_it) break;
-        // ---- rho adaptation (OSQP residual balancing), and restore of the ADMM factor ----
-        bool refactor = c.polish != 0;
         if (c.adaptive_rho) {
             double rn = rho * sqrt((pri / fmax(npri, 1e-10)) / fmax(dua / fmax(ndua, 1e-10), 1e-10));
             rn = fmin(fmax(rn, kRhoMin), kRhoMax);
-            if (rn > 5.0 * rho || rn < 0.2 * rho) { rho = rn; set_rho(rho); refactor = true; }
-        }
-        if (refactor) {
-            ++info.nfac;
-            if (sys.factor(A, w.rv, sigma, w.fixed, w.red)) { info.status = 3; break; }
+            if (rn > 5.0 * rho || rn < 0.2 * rho) {
+                rho = rn;
+                set_rho(rho);
+                ++info.nfac;
+                if (sys.factor(A, rv, sigma, 0.0, w.red)) { info.status = ST_NON_FINITE; break; }
+            }
         }
     }
-    if (info.status == 1 && conv) info.status = 4;
+    for (int r = tid; r < m; r += T) {
+        const double zz = z[r], yy = y[r];
+        w.code[r] = ((zz - w.lo[r]) < -yy) ? -1 : (((w.hi[r] - zz) < yy) ? 1 : 0);
+    }
+    __syncthreads();
     info.rho = rho;
     return info;
 }

@@ -81,7 +81,7 @@ def run_clock(n_steps, dt, t_start):
     return t
 
 
-def mpc_tables(x_ref, pf_ref, n_ticks, N, mpc_factor, dt, mpc_dt, t_start):
+def mpc_tables(x_ref, pf_ref, n_ticks, N, mpc_factor, dt, mpc_dt, t_start, t_p=T_P, phi_switch=PHI_SWITCH):
     """MPC-rate tables of one hopper for ``hmpc_rollout``.
 
     Returns xref_tab (n_ticks+N, 12), pf_tab (n_ticks+N+1, 3), C (n_ticks, N) and pf_switch (n_ticks,)
@@ -91,7 +91,7 @@ def mpc_tables(x_ref, pf_ref, n_ticks, N, mpc_factor, dt, mpc_dt, t_start):
     xref_tab = x_ref[rows[:-1]]
     pf_tab = pf_ref[rows]
     t = run_clock(n_ticks * mpc_factor, dt, t_start)
-    C = gait_map(N, mpc_dt, t[::mpc_factor], 0.0)
+    C = gait_map(N, mpc_dt, t[::mpc_factor], 0.0, t_p, phi_switch)
     sw = np.full(n_ticks, mpc_factor, dtype=np.uint8)
     for j in range(n_ticks):
         seg = pf_ref[j * mpc_factor:(j + 1) * mpc_factor]
@@ -114,102 +114,82 @@ def _parabola(y0, y1, y2, T, k):
     return y0 * (1 - s) * (1 - 2 * s) + y1 * 4 * s * (1 - s) + y2 * s * (2 * s - 1)
 
 
-def batch_tables(x0, xf, curve, t_start, N_run, n_ticks, N, mpc_factor=20, dt=1e-3, mpc_dt=0.02,
-                 t_p=T_P, phi_switch=PHI_SWITCH, step_adjustment=STEP_ADJUSTMENT):
-    """Planner + gait for B hoppers at once.
+def batch_tables(x0, xf, curve, tick_offset, N_run, n_ticks, N, mpc_factor=20, dt=1e-3, mpc_dt=0.02,
+                 t_start=0.5 * T_P * PHI_SWITCH, t_p=T_P, phi_switch=PHI_SWITCH,
+                 step_adjustment=STEP_ADJUSTMENT):
+    """Planner + gait for B hoppers at once, MPC-rate rows only.
 
-    x0, xf (B,12) start / goal MPC states, curve (B,) bool, t_start (B,) gait phase offsets.
+    Every hopper follows the reference's planner formulas (path_plan_init) between its own start x0[b]
+    and goal xf[b] (B,12), optionally with the --curve yaw profile, and enters the run at its own tick
+    ``tick_offset[b]`` (so the batch covers all gait phases at any instant).  The gait clock (common
+    t_start, running sums) is the reference's.
     Returns dict of numpy arrays in the SoA layout of include/hmpc.h:
       xref_tab (n_ticks+N, 12, B), pf_tab (n_ticks+N+1, 3, B), C_tab (n_ticks, B) uint64,
       pf_switch (n_ticks, B) uint8, C (n_ticks, B, N) float."""
     x0 = np.asarray(x0, float); xf = np.asarray(xf, float)
     B = x0.shape[0]
-    curve = np.asarray(curve, bool); t_start = np.asarray(t_start, float)
+    curve = np.asarray(curve, bool)
+    off = np.asarray(tick_offset, dtype=np.int64)
     N_k = N * mpc_factor
     t_ref = N_run + N_k
-    n_sim = n_ticks * mpc_factor
     amp = t_p / 4
+    max_tick = int(off.max()) + n_ticks
+    step = (xf - x0) / (N_run - 1)
+    s45 = np.sin(45 * np.pi / 180)
 
     def ref_rows(i):
-        """x_ref rows (len(i), B, 12) without the velocity columns, i = array of sim indices."""
-        i = np.asarray(i)
-        ii = np.minimum(i, t_ref - 1)[:, None, None].astype(float)
-        step = (xf - x0) / (N_run - 1)
+        """x_ref[i[r, b]] for hopper b -> (R, B, 12), velocity columns (6:9) not filled."""
+        ii = np.minimum(i, t_ref - 1).astype(float)[..., None]           # (R,B,1)
+        k = ii[..., 0]
         lin = ii * step[None] + x0[None]
-        last = (ii == N_run - 1)
-        lin = np.where(last, xf[None], lin)
+        lin = np.where(ii == N_run - 1, xf[None], lin)                    # linspace endpoint is exact
         out = lin.copy()
         T = float(N_run)
-        k = ii[..., 0]
-        s45 = np.sin(45 * np.pi / 180)
-        cx = _parabola(x0[None, :, 1], 0.9 * xf[None, :, 1], xf[None, :, 1], T, k)
-        cpsi = _parabola(0.0, -0.4 * s45, -s45, T, k)
-        out[..., 0] = np.where(curve[None], cx, lin[..., 0])
-        out[..., 5] = np.where(curve[None], cpsi, lin[..., 5])
-        d11 = np.where(k < N_run - 1, (((ii[..., 0] + 1) * step[None, :, 11] + x0[None, :, 11])
-                                        - lin[..., 11]) / dt, lin[..., 11])
-        # the row N_run-2 difference uses the exact endpoint xf
-        d11 = np.where(k == N_run - 2, (xf[None, :, 11] - lin[..., 11]) / dt, d11)
+        out[..., 0] = np.where(curve[None], _parabola(x0[None, :, 1], 0.9 * xf[None, :, 1], xf[None, :, 1], T, k),
+                               lin[..., 0])
+        out[..., 5] = np.where(curve[None], _parabola(0.0, -0.4 * s45, -s45, T, k), lin[..., 5])
+        nxt = np.where(k + 1 == N_run - 1, xf[None, :, 11], (k + 1) * step[None, :, 11] + x0[None, :, 11])
+        d11 = np.where(k < N_run - 1, (nxt - lin[..., 11]) / dt, lin[..., 11])
         out[..., 11] = np.where(curve[None], d11, lin[..., 11])
-        goal = (ii[..., 0] >= N_run)
-        out = np.where(goal[..., None], xf[None], out)
-        out[..., 2] = x0[None, :, 2] + amp + amp * np.sin(2 * np.pi / t_p * (ii[..., 0] * dt) + np.pi * 3 / 2)
+        out = np.where((k >= N_run)[..., None], xf[None], out)
+        out[..., 2] = x0[None, :, 2] + amp + amp * np.sin(2 * np.pi / t_p * (k * dt) + np.pi * 3 / 2)
         return out
 
-    rows = np.minimum(np.arange(n_ticks + N + 1) * mpc_factor, t_ref - 1)
+    rows = np.minimum((off[None, :] + np.arange(n_ticks + N + 1)[:, None]) * mpc_factor, t_ref - 1)  # (R,B)
     r0 = ref_rows(rows)
     r1 = ref_rows(rows + 1)
     vel = (r1[..., 0:3] - r0[..., 0:3]) / dt
-    # the very last reference row keeps the goal's own velocity (x_ref[:-1, 6:9] assignment)
-    is_last = (rows == t_ref - 1)[:, None, None]
-    r0[..., 6:9] = np.where(is_last, xf[None, :, 6:9], vel)
+    r0[..., 6:9] = np.where((rows == t_ref - 1)[..., None], xf[None, :, 6:9], vel)   # last row keeps xf's
     xref_tab = r0[:-1]
 
-    # footsteps: contact map at 1 kHz from t_start with running sums, stance->swing edge counter
-    n_need = int(rows[-1]) + 1
-    ts = t_start.copy()
-    prev = gait_scheduler(ts, 0.0, t_p, phi_switch)
-    kf = np.zeros(B, dtype=np.int64)
-    # footstep sample indices: minima of z at i = 800 k (k >= 1), shifted; first 0, last t_ref-1
+    # common clocks: 1 kHz contact map from t_start (planner) and the run clock t_k (robotrunner.py:97)
+    n_need = min(int(rows.max()) + 1, t_ref)
+    cmap = gait_map(n_need, dt, t_start, 0.0, t_p, phi_switch)
+    edges = np.zeros(n_need, dtype=np.int64)
+    edges[1:] = (cmap[:-1] == 1) & (cmap[1:] == 0)
     period = int(round(t_p / dt))
-    minima = np.arange(period, t_ref - 1, period)
-    # find_peaks needs a strict interior maximum of -z; i = multiples of the period qualify
-    idx_pf = np.hstack((0, minima + step_adjustment, t_ref - 1))
-    kf_rows = np.zeros((n_need, B), dtype=np.int64)
-    for k in range(1, n_need):
-        ts = ts + dt
-        cur = gait_scheduler(ts, 0.0, t_p, phi_switch)
-        kf = kf + ((prev == 1) & (cur == 0))
-        prev = cur
-        kf_rows[k] = kf
-    kf_rows = np.minimum(kf_rows, idx_pf.shape[0] - 1)
-    pf_idx = idx_pf[kf_rows]                       # (n_need, B) sim index whose xy is the footstep
-    uniq = np.unique(pf_idx)
-    xy_at = {int(u): ref_rows(np.array([u]))[0][:, 0:2] for u in uniq}   # (B,2) each
-    pf_tab = np.zeros((len(rows), B, 3))
-    for j, r in enumerate(rows):
-        sel = pf_idx[r]
-        for u in np.unique(sel):
-            msk = sel == u
-            pf_tab[j, msk, 0:2] = xy_at[int(u)][msk]
-    # switch step inside each tick (pf_ref[k] for k = 20 j + i); row 0 follows the same rule as the
-    # others, which equals the reference's all-zero pf_ref[0] whenever the start xy is the origin
-    sw = np.full((n_ticks, B), mpc_factor, dtype=np.uint8)
-    for j in range(n_ticks):
-        base = j * mpc_factor
-        seg = pf_idx[base:base + mpc_factor]            # (20, B)
-        diff = seg != pf_idx[base][None]
-        anyd = diff.any(axis=0)
-        sw[j, anyd] = np.argmax(diff, axis=0)[anyd].astype(np.uint8)
-        sw[j, np.all(pf_tab[j] == pf_tab[j + 1], axis=-1)] = mpc_factor   # same footstep either side
-
+    idx_pf = np.hstack((0, np.arange(period, t_ref - 1, period) + step_adjustment, t_ref - 1))
+    kf = np.minimum(np.cumsum(edges), idx_pf.shape[0] - 1)
+    pf_idx = idx_pf[kf]                                   # (n_need,) sim index whose xy is the footstep
+    sel = pf_idx[np.minimum(rows, n_need - 1)]            # (R,B)
+    pf_tab = np.zeros(rows.shape + (3,))
+    pf_tab[..., 0:2] = ref_rows(sel)[..., 0:2]
+    # switch step inside each tick: pf_ref[20 (off+j) + i] == pf_tab[j] if i < sw else pf_tab[j+1]
+    sw_glob = np.full(max_tick, mpc_factor, dtype=np.uint8)
+    for J in range(max_tick):
+        base = J * mpc_factor
+        if base + mpc_factor > n_need:
+            break
+        d = pf_idx[base:base + mpc_factor] != pf_idx[base]
+        if d.any():
+            sw_glob[J] = np.argmax(d)
+    jj = off[None, :] + np.arange(n_ticks)[:, None]       # (n_ticks,B) global tick index
+    sw = sw_glob[jj]
+    sw[np.all(pf_tab[:n_ticks] == pf_tab[1:n_ticks + 1], axis=-1)] = mpc_factor
     # MPC contact windows from the run clock
-    t = t_start.copy()
-    C = np.zeros((n_ticks, B, N))
-    for k in range(n_sim):
-        t = t + dt
-        if k % mpc_factor == 0:
-            C[k // mpc_factor] = gait_map(N, mpc_dt, t, 0.0, t_p, phi_switch)
+    tk = run_clock(max_tick * mpc_factor, dt, t_start)
+    Cglob = gait_map(N, mpc_dt, tk[::mpc_factor], 0.0, t_p, phi_switch)      # (max_tick, N)
+    C = Cglob[jj]                                                             # (n_ticks,B,N)
     w = (np.uint64(1) << np.arange(N, dtype=np.uint64))
     C_tab = ((C != 0).astype(np.uint64) * w).sum(axis=-1).astype(np.uint64)
     return dict(xref_tab=np.ascontiguousarray(xref_tab.transpose(0, 2, 1)),

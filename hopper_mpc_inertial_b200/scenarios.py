@@ -14,6 +14,15 @@ Q_REF = np.array([50., 50., 2., 1., 1., 50., 1., 1., 1., 10., 10., 10.])
 R_REF = np.full(6, 0.001)
 
 
+def default_gait_period(N, mpc_dt=0.02):
+    """Gait period used for synthetic batches: one MPC horizon (N * mpc_dt), capped at the reference's
+    0.8 s (robotrunner.py:43).  The reference runs N=60 (1.2 s horizon) over a 0.8 s gait, so its
+    horizon always sees the next stance; a 10-stage horizon over the 0.8 s gait cannot see across the
+    0.4 s swing and its height rows (z >= 0.1) become infeasible -- the reference raises 'QP FAILED'
+    there too."""
+    return min(planner.T_P, N * mpc_dt)
+
+
 def _uniforms(seed, idx0, count, k):
     """(count, k) uniforms in [0,1): row i depends only on (seed, idx0 + i)."""
     out = np.empty((count, k))
@@ -26,10 +35,25 @@ def _uniforms(seed, idx0, count, k):
     return out
 
 
-def make_batch(B, idx0=0, seed=1234, N=10, n_ticks=100, N_run=2000, mpc_factor=20, dt=1e-3, mpc_dt=0.02,
-               randomize_gains=True):
-    """Scenario for hoppers idx0 .. idx0+B-1.  Returns numpy arrays in the SoA layout of include/hmpc.h:
+def make_batch(B, idx0=0, seed=1234, N=10, n_ticks=100, N_run=None, mpc_factor=20, dt=1e-3, mpc_dt=0.02,
+               randomize_gains=True, phase_ticks=None, t_p=None, z_base=(0.30, 0.45), gain_spread=1.25,
+               dyn="3f", perturb=0.5, speed_range=(0.2, 1.0), curve_prob=0.5):
+    """Scenario for hoppers idx0 .. idx0+B-1.
+
+    Each hopper gets its own straight or curved reference (goal speed 0.2..1.0 x the reference's
+    0.4 m/s, random heading), its own gains (reference x logU(0.5,2)), its own entry point into the gait
+    cycle (tick offset 0..phase_ticks-1, i.e. a uniformly random gait phase) and starts near its
+    reference state at that instant (position +-3 cm, height -2..+3 cm, roll/pitch +-0.05 rad, yaw
+    +-0.2 rad, velocity +-0.2 m/s, body rates +-0.3 rad/s) -- close enough that the height rows stay
+    feasible through the swing phases, as in the reference's own runs.
+    Returns numpy arrays in the SoA layout of include/hmpc.h:
     X0 (13,B), Qdiag (12,B), Rdiag (6,B), xref_tab, pf_tab, C_tab (uint64), pf_switch (uint8), C."""
+    if t_p is None:
+        t_p = default_gait_period(N, mpc_dt)
+    if phase_ticks is None:
+        phase_ticks = max(1, int(round(t_p / mpc_dt)))
+    if N_run is None:
+        N_run = (n_ticks + phase_ticks + 20) * mpc_factor
     u = _uniforms(seed, idx0, B, 40)
     c = 0
 
@@ -42,39 +66,61 @@ def make_batch(B, idx0=0, seed=1234, N=10, n_ticks=100, N_run=2000, mpc_factor=2
     def rng(lo, hi, n):
         return lo + (hi - lo) * take(n)
 
-    p_xy = rng(-0.5, 0.5, 2)
-    z0 = rng(0.22, 0.45, 1)
-    rp = rng(-0.1, 0.1, 2)
-    yaw = rng(-np.pi / 4, np.pi / 4, 1)
-    v_b = rng(-0.5, 0.5, 3)
-    w_b = rng(-0.5, 0.5, 3)
-    gq = np.exp(rng(np.log(0.5), np.log(2.0), 12)) if randomize_gains else np.ones((B, 12))
-    gr = np.exp(rng(np.log(0.5), np.log(2.0), 6)) if randomize_gains else np.ones((B, 6))
+    p_xy0 = rng(-0.5, 0.5, 2)
+    dp = rng(-0.03, 0.03, 2) * perturb
+    dz = rng(-0.02, 0.03, 1) * perturb
+    rp = rng(-0.05, 0.05, 2) * perturb
+    dyaw = rng(-0.2, 0.2, 1) * perturb
+    dv = rng(-0.2, 0.2, 3) * perturb
+    w_b = rng(-0.3, 0.3, 3) * perturb
+    gq = np.exp(rng(-np.log(gain_spread), np.log(gain_spread), 12))
+    gr = np.exp(rng(-np.log(gain_spread), np.log(gain_spread), 6))
     if not randomize_gains:
-        c += 18
-    speed = rng(0.2, 1.0, 1)[:, 0]
+        gq[:] = 1.0; gr[:] = 1.0
+    speed = rng(speed_range[0], speed_range[1], 1)[:, 0]
     heading = rng(-np.pi, np.pi, 1)[:, 0]
-    curve = take(1)[:, 0] < 0.5
-    t_start = rng(0.0, planner.T_P, 1)[:, 0]
+    curve = take(1)[:, 0] < curve_prob
+    if dyn == "2f":
+        # 2f has no body-y force (mpc_cvx_euler_2f.py:129): the hopper can only be pushed in its own
+        # x-z plane, so -- as in the reference's 2f run -- the goal lies straight ahead along +x
+        heading[:] = 0.0
+        dp[:, 1] = 0.0
+        dv[:, 1] = 0.0
+    off = np.minimum((take(1)[:, 0] * phase_ticks).astype(np.int64), phase_ticks - 1)
+    zb = rng(z_base[0], z_base[1], 1)[:, 0]
 
-    # quaternion from ZYX Euler angles (roll, pitch, yaw)
-    cr, sr = np.cos(rp[:, 0] / 2), np.sin(rp[:, 0] / 2)
-    cp, sp = np.cos(rp[:, 1] / 2), np.sin(rp[:, 1] / 2)
-    cy, sy = np.cos(yaw[:, 0] / 2), np.sin(yaw[:, 0] / 2)
-    q = np.stack([cr * cp * cy + sr * sp * sy, sr * cp * cy - cr * sp * sy,
-                  cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy], axis=1)
-    X0 = np.concatenate([p_xy, z0, q, v_b, w_b], axis=1)          # (B,13)
-
-    # planner end points: reference-style start (upright, at rest, nominal height) and goal
+    # --curve writes the y-spline into the x column; start those hoppers on the
+    # diagonal so that the quirk does not put a jump between the initial state and the reference
+    p_xy0 = np.where(curve[:, None], p_xy0[:, 0:1], p_xy0)
     T = N_run * dt
     x0p = np.zeros((B, 12)); xfp = np.zeros((B, 12))
-    x0p[:, 0:2] = p_xy; x0p[:, 2] = 0.27
-    dist = speed * T * 0.4 / 0.4
-    xfp[:, 0] = p_xy[:, 0] + dist * np.cos(heading)
-    xfp[:, 1] = p_xy[:, 1] + dist * np.sin(heading)
-    xfp[:, 2] = 0.27
-    tabs = planner.batch_tables(x0p, xfp, curve, t_start, N_run, n_ticks, N, mpc_factor, dt, mpc_dt)
+    x0p[:, 0:2] = p_xy0; x0p[:, 2] = zb
+    dist = 0.4 * speed * T
+    xfp[:, 0] = p_xy0[:, 0] + dist * np.cos(heading)
+    xfp[:, 1] = p_xy0[:, 1] + dist * np.sin(heading)
+    xfp[:, 2] = zb
+    tabs = planner.batch_tables(x0p, xfp, curve, off, N_run, n_ticks, N, mpc_factor, dt, mpc_dt,
+                                t_start=0.5 * t_p * planner.PHI_SWITCH, t_p=t_p,
+                                step_adjustment=int(round(planner.STEP_ADJUSTMENT * t_p / planner.T_P)))
+
+    # initial simulator state: the reference state at the hopper's entry tick plus a perturbation
+    r = tabs["xref_tab"][0]                       # (12,B) reference row at the entry tick
+    pos = r[0:3].T + np.concatenate([dp, dz], axis=1)
+    roll, pitch, yaw = rp[:, 0], rp[:, 1], r[5] + dyaw[:, 0]
+    cr, sr = np.cos(roll / 2), np.sin(roll / 2)
+    cp, sp = np.cos(pitch / 2), np.sin(pitch / 2)
+    cy, sy = np.cos(yaw / 2), np.sin(yaw / 2)
+    q = np.stack([cr * cp * cy + sr * sp * sy, sr * cp * cy - cr * sp * sy,
+                  cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy], axis=1)
+    v_w = r[6:9].T + dv
+    # world -> body: v_b = R(q)^T v_w
+    qw, qx, qy, qz = q.T
+    R = np.stack([np.stack([1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qw * qz), 2 * (qx * qz + qw * qy)], -1),
+                  np.stack([2 * (qx * qy + qw * qz), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qw * qx)], -1),
+                  np.stack([2 * (qx * qz - qw * qy), 2 * (qy * qz + qw * qx), 1 - 2 * (qx * qx + qy * qy)], -1)], -2)
+    v_b = np.einsum("bji,bj->bi", R, v_w)
+    X0 = np.concatenate([pos, q, v_b, w_b], axis=1)
     out = dict(X0=np.ascontiguousarray(X0.T), Qdiag=np.ascontiguousarray((Q_REF[None] * gq).T),
-               Rdiag=np.ascontiguousarray((R_REF[None] * gr).T), curve=curve, t_start=t_start)
+               Rdiag=np.ascontiguousarray((R_REF[None] * gr).T), curve=curve, tick_offset=off, t_p=t_p)
     out.update(tabs)
     return out

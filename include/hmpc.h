@@ -43,18 +43,25 @@ typedef enum hmpc_error {
 
 /* per-hopper solve status (device int32 arrays) */
 typedef enum hmpc_status {
-    HMPC_SOLVED = 0,           /* KKT-verified optimum (polish accepted)                               */
-    HMPC_SOLVED_INEXACT = 4,   /* ADMM residual test met (eps_abs/eps_rel) but polish not verified     */
+    HMPC_SOLVED = 0,           /* exact optimum: passed the KKT test of the original QP                */
     HMPC_MAX_ITER = 1,
-    HMPC_PRIMAL_INFEASIBLE = 2,/* x[0,2] or x[1,2] below z_min: u-independent rows;
+    HMPC_PRIMAL_INFEASIBLE = 2,/* some height row x[k,2] >= z_min cannot be met by any admissible
+                                  input (includes the u-independent rows k = 0, 1);
                                   the reference raises "QP FAILED" (mpc_cvx_euler_3f.py:158-159)       */
-    HMPC_NON_FINITE = 3
+    HMPC_NON_FINITE = 3,
+    HMPC_SOLVED_INEXACT = 4    /* residual test met (ADMM eps_abs/eps_rel, or interior-point tolerance)
+                                  but the point did not pass the exact KKT verification                */
 } hmpc_status;
+
+/* which branch of the solver produced the result (hmpc_solve_stats) */
+enum { HMPC_PATH_NONE = 0, HMPC_PATH_WARM = 1, HMPC_PATH_IPM_POLISH = 2, HMPC_PATH_IPM = 3, HMPC_PATH_ADMM = 4 };
 
 enum { HMPC_DYN_2F = 2, HMPC_DYN_3F = 3 };                 /* mpc_cvx_euler_2f / mpc_cvx_euler_3f      */
 enum { HMPC_FP64 = 0, HMPC_FP32 = 1 };
 enum { HMPC_UREF_ALIASED = 0, HMPC_UREF_PER_STAGE = 1 };   /* SURVEY App. D1                           */
+enum { HMPC_SOLVER_EXACT = 0, HMPC_SOLVER_ADMM = 1 };
 enum { HMPC_MODE_EARLY_EXIT = 0, HMPC_MODE_FIXED_ITER = 1 };
+enum { HMPC_INFEASIBLE_HOLD = 0, HMPC_INFEASIBLE_RESPAWN = 1 };
 
 /* Constants of Mpc.__init__ (mpc_cvx_euler_3f.py:12-39), Runner.__init__ (robotrunner.py:37-79) and
  * the literals inside build_qp (mpc_cvx_euler_3f.py:113-146), plus solver settings. */
@@ -67,13 +74,20 @@ typedef struct hmpc_config {
     int32_t mpc_factor;    /* sim steps per MPC tick (robotrunner.py:48) = 20 */
     int32_t precision;     /* HMPC_FP64 | HMPC_FP32 (FP32 not implemented yet -> HMPC_ERR_UNSUPPORTED) */
     int32_t uref_mode;     /* HMPC_UREF_ALIASED (reference-faithful) | HMPC_UREF_PER_STAGE */
-    int32_t mode;          /* HMPC_MODE_EARLY_EXIT | HMPC_MODE_FIXED_ITER */
-    int32_t max_iter;      /* ADMM iteration cap (cvxpy passes 10000) */
-    int32_t check_interval;/* residual / polish / rho-adaptation cadence (OSQP: 25) */
-    int32_t polish;        /* 1: verified active-set polish (exact optimum); 0: plain ADMM */
-    int32_t adaptive_rho;  /* 1: OSQP residual-balancing rho update at check time */
-    int32_t warm_start;    /* 1: rollout warm-starts ADMM from the time-shifted previous (u,y) */
-    int32_t linsys;        /* 0 auto; 1 generic (Cholesky in smem/L2); 2 register-resident inverse */
+    int32_t solver;        /* HMPC_SOLVER_EXACT: warm-started verified active-set refinement with an
+                              interior-point fallback -> the exact optimum (default);
+                              HMPC_SOLVER_ADMM: OSQP-style ADMM (cvxpy's settings below) */
+    int32_t mode;          /* ADMM: HMPC_MODE_EARLY_EXIT | HMPC_MODE_FIXED_ITER */
+    int32_t max_iter;      /* ADMM iteration cap (cvxpy passes 10000) / exact iteration count in FIXED_ITER */
+    int32_t check_interval;/* ADMM residual-test / rho-adaptation cadence after the first check (OSQP: 25) */
+    int32_t first_check;   /* ADMM iterations before the first residual test */
+    int32_t polish;        /* ADMM: 1 = verified active-set polish after termination (OSQP polish=True) */
+    int32_t adaptive_rho;  /* ADMM: OSQP residual-balancing rho update at check time */
+    int32_t warm_start;    /* 1: start from the time-shifted previous solution / active set */
+    int32_t polish_retries;/* active-set refinements per polish attempt */
+    int32_t ipm_max_iter;  /* interior-point iteration cap */
+    int32_t on_infeasible; /* rollout: HMPC_INFEASIBLE_HOLD (apply U = 0) | HMPC_INFEASIBLE_RESPAWN
+                              (reset the hopper onto its reference at the next tick and re-initialise) */
     int32_t reserved0;
     double mpc_dt;         /* robotrunner.py:47  0.02  */
     double sim_dt;         /* run.py:24          1e-3  */
@@ -87,8 +101,9 @@ typedef struct hmpc_config {
     double kf;             /* terminal state-cost factor, mpc_cvx_euler_3f.py:113 (100); input factor kuf=0 */
     double eps_abs, eps_rel;   /* ADMM residual test (cvxpy: 1e-5 each) */
     double rho0, sigma, alpha; /* OSQP defaults 0.1, 1e-6, 1.6 */
-    double polish_delta;       /* OSQP default 1e-6 */
-    double polish_tol;         /* KKT acceptance tolerance of the polish (relative), default 1e-9 */
+    double kkt_eps;            /* regularisation of the quasi-definite polish system (removed by refinement) */
+    double polish_tol;         /* relative KKT acceptance tolerance of the verification, default 1e-9 */
+    double ipm_tol;            /* interior-point residual / complementarity tolerance, default 1e-9 */
 } hmpc_config;
 
 typedef struct hmpc_handle hmpc_handle;
@@ -120,9 +135,13 @@ int hmpc_linearize(hmpc_handle* h, const double* x_guess, const double* pf, doub
 
 /* Condensed QP data for parity tests: given the linearisation point, emit
  * H [n][n][B], g [n][B], lo/hi [m][B] in the slot layout  rows = [6N box | 4N friction | N height]
- * (n = 6N, m = 11N).  Built from build_qp (mpc_cvx_euler_3f.py:96-153). */
+ * (n = 6N, m = 11N).  Built from build_qp (mpc_cvx_euler_3f.py:96-153).
+ * Height row k >= 2 is normalised by its largest coefficient dt^2 (k-1)/m, so its bound reads
+ * lo = (z_min - c_z[k]) m / (dt^2 (k-1)).  infeasible [B] (int32, may be NULL): 1 when some height row
+ * cannot be met by any admissible input. */
 int hmpc_condense(hmpc_handle* h, const double* x_in, const double* x_guess, const double* x_ref,
-                  const double* pf, const uint64_t* Cbits, double* H, double* g, double* lo, double* hi);
+                  const double* pf, const uint64_t* Cbits, double* H, double* g, double* lo, double* hi,
+                  int32_t* infeasible);
 
 /* Mpc.mpcontrol (mpc_cvx_euler_3f.py:41-69): linearise, build and solve the QP for every hopper.
  *   x_in  [12][B]        convert()ed current state
@@ -133,7 +152,8 @@ int hmpc_condense(hmpc_handle* h, const double* x_in, const double* x_guess, con
  *                        previous solution (mpc_cvx_euler_3f.py:50-62)
  *   U     [N][6][B]      out: u.value
  *   Xsol  [N+1][12][B]   out: x.value (also kept inside the handle for the next time shift)
- *   status, iters [B]    out: hmpc_status and ADMM iterations (int32)
+ *   status, iters [B]    out: hmpc_status and solver iterations (ADMM or interior-point; 0 when the
+ *                        warm-started active-set refinement succeeded) (int32)
  */
 int hmpc_solve(hmpc_handle* h, const double* x_in, const double* x_ref, const double* pf,
                const uint64_t* Cbits, int init, double* U, double* Xsol, int32_t* status,
@@ -150,11 +170,18 @@ int hmpc_solve(hmpc_handle* h, const double* x_in, const double* x_ref, const do
  *   tick0                          index of the first tick in the tables; init = 1 on the run's first tick
  *   X_log    [n_ticks+1][13][B]    optional (may be NULL): state at every tick boundary
  *   U_log    [n_ticks][6][B]       optional: applied control per tick (f_hist, robotrunner.py:111)
- *   status   [B], iters [B]        worst status / accumulated iterations over the ticks
+ *   status   [B], iters [B]        first non-zero status / accumulated iterations over the ticks
+ * A hopper whose QP is infeasible gets U = 0 for that tick (HOLD) or is put back onto its reference
+ * (RESPAWN, hmpc_config.on_infeasible); hmpc_solve_stats reports how often that happened.
  */
 int hmpc_rollout(hmpc_handle* h, double* X, const double* xref_tab, const double* pf_tab,
                  const uint64_t* C_tab, const uint8_t* pf_switch, int tick0, int n_ticks, int init,
                  double* X_log, double* U_log, int32_t* status, int32_t* iters);
+
+/* Per-hopper statistics of the most recent hmpc_solve (or accumulated over the most recent
+ * hmpc_rollout): nfac [B] = matrix factorisations, path [B] = HMPC_PATH_* of the last solve,
+ * n_infeasible [B] = ticks flagged HMPC_PRIMAL_INFEASIBLE.  Device int32 arrays, each may be NULL. */
+int hmpc_solve_stats(hmpc_handle* h, int32_t* nfac, int32_t* path, int32_t* n_infeasible);
 
 /* Counters since handle creation: kernels launched by this library (for bench gpu_launches). */
 int hmpc_launch_count(hmpc_handle* h, int64_t* n_launches);

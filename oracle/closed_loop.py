@@ -32,7 +32,7 @@ class OracleMpc:
         if self.solver == "exact":
             qp = ho.build_qp_condensed(x_in, x_ref, Ad, Bd, Gd, C, prm)
             if qp["infeasible"]:
-                raise QPFailed("height rows k=0,1 infeasible")
+                raise QPFailed("infeasible: height rows z_k >= z_min cannot be met (min slack %.4g)" % float(np.min(qp["zmax"]) - prm.z_min))
             res = qs.exact_qp(qp["H"], qp["g"], qp["A"], qp["l"], qp["u"])
             if not res["ok"]:
                 raise QPFailed(f"exact_qp not certified: {res['cert']}")

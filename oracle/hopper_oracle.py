@@ -405,7 +405,17 @@ def build_qp_condensed(x_in, x_ref, Ad, Bd, Gd, C, prm: Params):
         else:
             if c[k][2] < prm.z_min:
                 infeasible = True  # App. D2: u-independent height rows k=0,1
-    return dict(H=Hm, g=g, A=A, l=lo, u=hi, c=c, S=S, infeasible=infeasible)
+    # exact feasibility: the height rows are monotone in the stance fz (all coefficients >= 0) and
+    # fz = fz_max, fx = fy = 0 satisfies every other row, so the QP is feasible iff z_k(fz_max) >= z_min
+    zmax = np.zeros(N)
+    for k in range(N):
+        zr = n + 4 * N + k
+        ub = np.where(hi[:n] > 1e20, 0.0, hi[:n])
+        coef = S[k][2]
+        zmax[k] = c[k][2] + np.sum(np.where(coef > 0, coef * ub, coef * np.where(lo[:n] < -1e20, 0.0, lo[:n])))
+    height_infeasible = bool(np.any(zmax < prm.z_min))
+    return dict(H=Hm, g=g, A=A, l=lo, u=hi, c=c, S=S, infeasible=infeasible or height_infeasible,
+                infeasible_const=infeasible, zmax=zmax)
 
 
 def rollout_linear(x_in, U, Ad, Bd, Gd, prm: Params):

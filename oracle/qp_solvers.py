@@ -204,91 +204,121 @@ def _active_set_solve(H, g, A, b, fixed_tol=0.0):
     return sol[:n], sol[n:]
 
 
-def exact_qp(H, g, A, l, u, tol=1e-11, max_iter=200):
-    """Exact optimum of the strictly convex QP  min 1/2 x'Hx + g'x, l <= Ax <= u.
-
-    Mehrotra predictor-corrector interior point on {equalities, one-sided inequalities}, followed by
-    an active-set KKT solve that is accepted only when it passes the KKT certificate.  Independent of
-    the ADMM code path on purpose.  Returns dict(x, y, cert, ok)."""
-    H = np.asarray(H, float); A = np.asarray(A, float)
-    n = H.shape[0]
-    eq = (u - l) < 1e-12
-    fin_l = (l > -_INF_THRESH) & ~eq
-    fin_u = (u < _INF_THRESH) & ~eq
-    Aeq, beq = A[eq], l[eq]
-    G = np.vstack((A[fin_u], -A[fin_l]))
-    h = np.concatenate((u[fin_u], -l[fin_l]))
-    ne, ni = Aeq.shape[0], G.shape[0]
-    x = np.zeros(n)
-    nu = np.zeros(ne)
-    s = np.maximum(h - G @ x, 1.0)
+def _ipm(H, g, G, h, tol=1e-11, max_iter=100):
+    """Mehrotra predictor-corrector primal-dual interior point for  min 1/2 x'Hx + g'x, G x <= h
+    (H positive definite).  Returns (x, lam, s, iters)."""
+    n, ni = H.shape[0], G.shape[0]
+    if ni == 0:
+        return -sla.cho_solve(sla.cho_factor(H), g), np.zeros(0), np.zeros(0), 0
+    x = sla.cho_solve(sla.cho_factor(H + G.T @ G), -g + G.T @ h)
+    s = h - G @ x
+    s = np.maximum(s + max(-1.5 * s.min(), 0.0), 1e-2)
     lam = np.ones(ni)
+    gs, hs = max(1.0, np.abs(g).max()), max(1.0, np.abs(h).max())
+
+    def step_len(v, dv):
+        neg = dv < 0
+        return min(1.0, float(np.min(-v[neg] / dv[neg]))) if neg.any() else 1.0
+
+    it = 0
     for it in range(max_iter):
-        rd = H @ x + g + G.T @ lam + Aeq.T @ nu
+        rd = H @ x + g + G.T @ lam
         rp = G @ x + s - h
-        re = Aeq @ x - beq
-        mu_ = (s @ lam) / max(ni, 1)
-        if max(np.max(np.abs(rd)), np.max(np.abs(rp), initial=0.0), np.max(np.abs(re), initial=0.0)) < tol \
-                and mu_ < tol:
+        mu_ = (s @ lam) / ni
+        if np.abs(rd).max() < tol * gs and np.abs(rp).max() < tol * hs and mu_ < tol:
             break
         W = lam / s
         Hs = H + G.T @ (W[:, None] * G)
-        K = np.block([[Hs, Aeq.T], [Aeq, -1e-14 * np.eye(ne)]]) if ne else Hs
-        lu = sla.lu_factor(K)
+        try:
+            cf = sla.cho_factor(Hs)
+        except sla.LinAlgError:
+            break
 
         def newton(rc):
-            # rc: complementarity residual target  (s*lam + ... = rc form)
             r1 = -rd - G.T @ ((lam * rp - rc) / s)
-            sol = sla.lu_solve(lu, np.concatenate((r1, -re)) if ne else r1)
-            dx = sol[:n]
-            dnu = sol[n:] if ne else np.zeros(0)
+            dx = sla.cho_solve(cf, r1)
+            dx += sla.cho_solve(cf, r1 - Hs @ dx)
             ds = -rp - G @ dx
-            dlam = -(rc + lam * ds) / s
-            return dx, dnu, ds, dlam
+            return dx, ds, -(rc + lam * ds) / s
 
-        def step_len(v, dv):
-            neg = dv < 0
-            return min(1.0, float(np.min(-v[neg] / dv[neg]))) if neg.any() else 1.0
-
-        dx, dnu, ds, dlam = newton(s * lam)
+        dx, ds, dlam = newton(s * lam)
         a_aff = min(step_len(s, ds), step_len(lam, dlam))
-        mu_aff = ((s + a_aff * ds) @ (lam + a_aff * dlam)) / max(ni, 1)
+        mu_aff = ((s + a_aff * ds) @ (lam + a_aff * dlam)) / ni
         sig = (mu_aff / mu_) ** 3 if mu_ > 0 else 0.0
-        dx, dnu, ds, dlam = newton(s * lam + ds * dlam - sig * mu_)
-        a = 0.995 * min(step_len(s, ds), step_len(lam, dlam)) if ni else 1.0
-        a = min(a, 1.0)
-        x = x + a * dx; nu = nu + a * dnu; s = s + a * ds; lam = lam + a * dlam
-    # assemble multipliers in the l<=Ax<=u convention
-    y = np.zeros(A.shape[0])
-    nu_u = int(fin_u.sum())
-    y[np.where(fin_u)[0]] += lam[:nu_u]
-    y[np.where(fin_l)[0]] -= lam[nu_u:]
-    y[eq] = nu
-    # active-set refinement
-    act_u = np.zeros(A.shape[0], bool); act_l = np.zeros(A.shape[0], bool)
-    act_u[np.where(fin_u)[0]] = lam[:nu_u] > s[:nu_u]
-    act_l[np.where(fin_l)[0]] = lam[nu_u:] > s[nu_u:]
-    act = act_u | act_l | eq
-    b = np.where(act_u, u, l)[act]
-    Aa = A[act]
-    # drop linearly dependent active rows (e.g. fz=0 makes both friction rows and fx=0 redundant)
-    keep = []
-    if Aa.shape[0]:
+        dx, ds, dlam = newton(s * lam + ds * dlam - sig * mu_)
+        a = min(1.0, 0.99 * min(step_len(s, ds), step_len(lam, dlam)))
+        x = x + a * dx; s = s + a * ds; lam = lam + a * dlam
+    return x, lam, s, it
+
+
+def exact_qp(H, g, A, l, u, tol=1e-11, max_iter=100):
+    """Exact optimum of the strictly convex QP  min 1/2 x'Hx + g'x, l <= Ax <= u  whose first n rows of A
+    are the identity (the condensed layout of hopper_oracle.build_qp_condensed).
+
+    Variables with l == u on their identity row are eliminated, a Mehrotra interior point runs on the
+    remaining inequality-only problem, then an active-set KKT solve is accepted only if it improves the
+    KKT certificate.  Independent of the ADMM code path on purpose.  Returns dict(x, y, cert, ok)."""
+    H = np.asarray(H, float); A = np.asarray(A, float)
+    l = np.asarray(l, float); u = np.asarray(u, float); g = np.asarray(g, float)
+    n, m = H.shape[0], A.shape[0]
+    assert m >= n and np.array_equal(A[:n], np.eye(n)), "identity box rows expected first"
+    fixed = (u[:n] - l[:n]) < 1e-12
+    fr = ~fixed
+    xfix = np.where(fixed, l[:n], 0.0)
+    Hr = H[np.ix_(fr, fr)]
+    gr = g[fr] + H[np.ix_(fr, fixed)] @ xfix[fixed]
+    off = A[:, fixed] @ xfix[fixed]
+    Ar_all, lr_all, ur_all = A[:, fr], l - off, u - off
+    rows = np.ones(m, bool); rows[:n] = fr
+    rows &= np.abs(Ar_all).sum(axis=1) > 0
+    ridx = np.where(rows)[0]
+    Ar, lr, ur = Ar_all[rows], lr_all[rows], ur_all[rows]
+    # rows without support but with violated constant bounds -> infeasible
+    dead = ~rows; dead[:n] = False
+    infeasible_const = bool(np.any(lr_all[dead] > 1e-12) or np.any(ur_all[dead] < -1e-12))
+    fu, fl = ur < _INF_THRESH, lr > -_INF_THRESH
+    G = np.vstack((Ar[fu], -Ar[fl]))
+    h = np.concatenate((ur[fu], -lr[fl]))
+    x_r, lam, s, it = _ipm(Hr, gr, G, h, tol, max_iter)
+    nu_u = int(fu.sum())
+    yr = np.zeros(Ar.shape[0])
+    yr[np.where(fu)[0]] += lam[:nu_u]
+    yr[np.where(fl)[0]] -= lam[nu_u:]
+
+    def full(xr, yrow):
+        x = xfix.copy(); x[fr] = xr
+        y = np.zeros(m); y[ridx] = yrow
+        grad = H @ x + g + A.T @ y
+        y[:n][fixed] = -grad[fixed]      # multiplier of the eliminated variable's equality row
+        return x, y
+
+    cands = [full(x_r, yr)]
+    # active-set refinement on the reduced problem
+    act_u = np.zeros(Ar.shape[0], bool); act_l = np.zeros(Ar.shape[0], bool)
+    act_u[np.where(fu)[0]] = lam[:nu_u] > s[:nu_u]
+    act_l[np.where(fl)[0]] = lam[nu_u:] > s[nu_u:]
+    act = act_u | act_l
+    if act.any():
+        Aa = Ar[act]; b = np.where(act_u, ur, lr)[act]
         Qr, Rr, piv = sla.qr(Aa.T, mode="economic", pivoting=True)
         rank = int(np.sum(np.abs(np.diag(Rr)) > 1e-10 * max(1.0, abs(Rr[0, 0]))))
         keep = np.sort(piv[:rank])
-    xa, ya = _active_set_solve(H, g, Aa[keep], b[keep]) if len(keep) else _active_set_solve(H, g, Aa[:0], b[:0])
-    best = dict(x=x, y=y)
-    if xa is not None:
-        y2 = np.zeros(A.shape[0])
-        idx = np.where(act)[0]
-        if len(keep):
-            y2[idx[keep]] = ya
-        c_ipm = kkt_certificate(H, g, A, l, u, x, y)
-        c_as = kkt_certificate(H, g, A, l, u, xa, y2)
-        sign_ok = np.all(y2[act_u & ~eq] >= -1e-9) and np.all(y2[act_l & ~eq] <= 1e-9)
-        if sign_ok and max(c_as["stat"], c_as["prim"]) <= max(c_ipm["stat"], c_ipm["prim"], 1e-9):
-            best = dict(x=xa, y=y2)
-    cert = kkt_certificate(H, g, A, l, u, best["x"], best["y"])
-    ok = cert["stat"] < 1e-7 and cert["prim"] < 1e-8 and cert["sign"] < 1e-7
-    return dict(x=best["x"], y=best["y"], cert=cert, ok=bool(ok), ipm_iters=it)
+        xa, ya = _active_set_solve(Hr, gr, Aa[keep], b[keep])
+        if xa is not None:
+            y2 = np.zeros(Ar.shape[0])
+            y2[np.where(act)[0][keep]] = ya
+            if np.all(y2[act_u] >= -1e-9) and np.all(y2[act_l] <= 1e-9):
+                cands.append(full(xa, y2))
+    else:
+        xa, _ = _active_set_solve(Hr, gr, Ar[:0], lr[:0])
+        cands.append(full(xa, np.zeros(Ar.shape[0])))
+    best, best_cert = None, None
+    for x, y in cands:
+        c = kkt_certificate(H, g, A, l, u, x, y)
+        score = max(c["stat"] / max(1.0, np.abs(g).max()), c["prim"], c["sign"], c["comp"])
+        if best is None or score < best[0]:
+            best, best_cert = (score, x, y), c
+    gs = max(1.0, float(np.abs(g).max()))
+    ok = (not infeasible_const) and best_cert["stat"] < 1e-9 * gs and best_cert["prim"] < 1e-9 \
+        and best_cert["sign"] < 1e-7 and best_cert["comp"] < 1e-6 * gs
+    return dict(x=best[1], y=best[2], cert=best_cert, ok=bool(ok), ipm_iters=it)

@@ -1,0 +1,105 @@
+// tests/emul/emul.cpp -- TEST INFRASTRUCTURE.  Compiles the product's device source
+// (hopper_mpc_inertial_b200/csrc/hmpc_{sim,qp,mpc}.cuh) with g++ and runs it as ONE serial thread per
+// hopper, so that the CPU test-suite (no GPU in the build container) exercises the very code the CUDA
+// kernels execute: arithmetic, control flow, indexing.  It cannot see races or barrier bugs -- those
+// are covered by the -m gpu tests and compute-sanitizer runs on the GPU box.  Never shipped, never
+// loaded by the product package.
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "cuda_runtime.h"   // tests/emul/fake_cuda
+#include "../../hopper_mpc_inertial_b200/csrc/hmpc_sim.cuh"
+#include "../../hopper_mpc_inertial_b200/csrc/hmpc_mpc.cuh"
+
+using namespace hmpc;
+
+static QpConst qp_const(const hmpc_config& cfg) {
+    QpConst c;
+    c.N = cfg.N; c.dyn = cfg.dyn; c.uref_mode = cfg.uref_mode; c.solver = cfg.solver; c.mode = cfg.mode;
+    c.max_iter = cfg.max_iter; c.check = cfg.check_interval; c.first_check = cfg.first_check;
+    c.retries = cfg.polish_retries; c.adaptive_rho = cfg.adaptive_rho; c.warm_start = cfg.warm_start;
+    c.polish = cfg.polish; c.ipm_max_iter = cfg.ipm_max_iter;
+    c.dt = cfg.mpc_dt; c.m = cfg.m; c.g = cfg.g; c.mu = cfg.mu;
+    for (int i = 0; i < 9; ++i) c.Jinv[i] = cfg.Jinv[i];
+    for (int i = 0; i < 3; ++i) { c.rh[i] = cfg.rh[i]; c.tau_max[i] = cfg.tau_max[i]; }
+    c.fz_max = cfg.fz_max; c.z_min = cfg.z_min; c.kf = cfg.kf;
+    c.eps_abs = cfg.eps_abs; c.eps_rel = cfg.eps_rel; c.rho0 = cfg.rho0; c.sigma = cfg.sigma;
+    c.alpha = cfg.alpha; c.kkt_eps = cfg.kkt_eps; c.polish_tol = cfg.polish_tol; c.ipm_tol = cfg.ipm_tol;
+    return c;
+}
+
+extern "C" {
+
+// Same contract as hmpc_solve, all pointers HOST memory, state arrays owned by the caller:
+// Xsol_state [N+1][12][B], Usol_state [N][6][B], code_state int8 [11N][B], valid_state int8 [B].
+int emul_solve(const hmpc_config* cfg, const double* Qd, const double* Rd, const double* x_in,
+               const double* x_ref, const double* pf, const uint64_t* Cbits, int init, double* Xsol_state,
+               double* Usol_state, int8_t* code_state, int8_t* valid_state, double* U, double* Xsol,
+               int32_t* status, int32_t* iters, int32_t* nfac, int32_t* path) {
+    const QpConst c = qp_const(*cfg);
+    const int B = cfg->batch, N = cfg->N, n = 6 * N;
+    std::vector<double> smem(((work_vec_doubles(N) + 1) & ~(size_t)1) + mat_doubles(N) + 8);
+    std::vector<int32_t> st_tick(B), ninf(B);
+    Work w;
+    setup_work(w, c, smem.data(), nullptr, true);
+    AOp A{N, n, c.dyn == 3 ? 1 : 0, c.mu, w.stance, w.hinv};
+    LinSys sys{n, w.ld, 0, 0, w.Lm, w.dinv, w.H, w.idx, w.grow};
+    MpcIo io;
+    io.x_in = x_in; io.x_ref = x_ref; io.pf = pf; io.Cbits = Cbits; io.Qd = Qd; io.Rd = Rd;
+    io.Xsol = Xsol_state; io.Usol = Usol_state; io.code = code_state; io.valid = valid_state;
+    io.U_out = U; io.X_out = Xsol; io.U0_out = nullptr;
+    io.status = status; io.iters = iters; io.st_tick = st_tick.data(); io.nfac = nfac; io.path = path;
+    io.ninf = ninf.data(); io.init = init; io.accumulate = 0; io.respawn = 0;
+    for (int b = 0; b < B; ++b) mpc_hopper(c, w, sys, A, b, B, io);
+    return 0;
+}
+
+// condense only: H [n][n][B], g [n][B], lo/hi [m][B], infeasible [B]
+int emul_condense(const hmpc_config* cfg, const double* Qd, const double* Rd, const double* x_in,
+                  const double* x_guess, const double* x_ref, const double* pf, const uint64_t* Cbits,
+                  double* H, double* g, double* lo, double* hi, int32_t* infeasible) {
+    const QpConst c = qp_const(*cfg);
+    const int B = cfg->batch, N = cfg->N, n = 6 * N, m = 11 * N;
+    std::vector<double> smem(((work_vec_doubles(N) + 1) & ~(size_t)1) + mat_doubles(N) + 8);
+    Work w;
+    setup_work(w, c, smem.data(), nullptr, true);
+    for (int b = 0; b < B; ++b) {
+        load_hopper(c, w, b, B, x_in, pf, Cbits, Qd, Rd);
+        for (int k = 0; k < N; ++k) {
+            const size_t o = (size_t)k * 12;
+            w.gp[4 * k] = x_guess[(o + 0) * B + b]; w.gp[4 * k + 1] = x_guess[(o + 1) * B + b];
+            w.gp[4 * k + 2] = x_guess[(o + 2) * B + b]; w.gp[4 * k + 3] = x_guess[(o + 5) * B + b];
+        }
+        infeasible[b] = condense(c, w, x_ref + b, (size_t)B);
+        for (int e = 0; e < n * n; ++e) H[(size_t)e * B + b] = w.H[e];
+        for (int i = 0; i < n; ++i) g[(size_t)i * B + b] = w.g[i];
+        for (int r = 0; r < m; ++r) { lo[(size_t)r * B + b] = w.lo[r]; hi[(size_t)r * B + b] = w.hi[r]; }
+    }
+    return 0;
+}
+
+// rk4_normalized x nsteps (+ optional convert): X [13][B] in/out, U [6][B], pf [3][B], x_out [12][B] or NULL
+int emul_rk4(const hmpc_config* cfg, double* X, const double* U, const double* pf, int nsteps, double* x_out) {
+    SimConst s;
+    s.m = cfg->m; s.g = cfg->g; s.h = cfg->sim_dt;
+    for (int i = 0; i < 9; ++i) { s.J[i] = cfg->J[i]; s.Jinv[i] = cfg->Jinv[i]; }
+    for (int i = 0; i < 3; ++i) s.rh[i] = cfg->rh[i];
+    const int B = cfg->batch;
+    for (int b = 0; b < B; ++b) {
+        double Xl[13], Ul[6], p[3];
+        for (int i = 0; i < 13; ++i) Xl[i] = X[(size_t)i * B + b];
+        for (int i = 0; i < 6; ++i) Ul[i] = U[(size_t)i * B + b];
+        for (int i = 0; i < 3; ++i) p[i] = pf[(size_t)i * B + b];
+        for (int k = 0; k < nsteps; ++k) rk4_step(s, Xl, Ul, p);
+        for (int i = 0; i < 13; ++i) X[(size_t)i * B + b] = Xl[i];
+        if (x_out) {
+            double x[12];
+            convert_state(Xl, x);
+            for (int i = 0; i < 12; ++i) x_out[(size_t)i * B + b] = x[i];
+        }
+    }
+    return 0;
+}
+
+}  // extern "C"
