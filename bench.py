@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- closed-loop hopper-MPC throughput on B200 (BASELINE.json metric) + reference arm.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # product arm (1 GPU by default)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference [--gpus N] --steps K --warmup W   # CPU arm: the reference's algorithm
+
+One "step" is one closed-loop MPC tick of EVERY hopper of the batch: time shift + linearise + condense +
+QP solve (mpcontrol, mpc_cvx_euler_3f.py:41-69) followed by mpc_factor = 20 RK4 simulator steps with the
+zero-order-held control and the state conversion for the next tick (robotrunner.py:101-113).
+Metric: hopper-MPC steps/s = hoppers x ticks / time, whole job over all ranks (weak scaling: the per-GPU
+batch is fixed, hoppers are sharded by global index, no collective on the data path).
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "hopper_mpc_steps_per_s"
+UNIT = "closed-loop MPC steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--batch", type=int, default=131072, help="hoppers per GPU (1M over 8 GPUs = BASELINE config 4)")
+    ap.add_argument("--horizon", type=int, default=10)
+    ap.add_argument("--dyn", choices=["2f", "3f"], default="3f")
+    ap.add_argument("--solver", choices=["exact", "admm"], default="exact")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="wall-clock budget of the CPU baseline sample")
+    return ap.parse_args()
+
+
+def workload_name(args, world):
+    return (f"{args.dyn} batch, {args.batch} hoppers/GPU x {world} GPU(s) = {args.batch * world} hoppers "
+            f"(BASELINE configs[3]: 1M hoppers sharded over 8 B200 -> 131072 per GPU), horizon {args.horizon}, "
+            f"randomised initial states, gains and references, FP64")
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                parts = [p.strip() for p in out.split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm (oracle port) on the host cores, one process per core
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    """One hopper's closed loop with the reference's own per-tick recipe: a fresh cvxpy-shaped QP every tick,
+    OSQP cold start at cvxpy's settings (eps 1e-5, polish) -- oracle/closed_loop.py solver='osqp' -- plus
+    20 numpy RK4 steps.  Returns (ticks done, seconds)."""
+    idx, dyn, N, seconds, max_ticks = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    from hopper_mpc_inertial_b200 import scenarios
+    from oracle import hopper_oracle as ho
+    from oracle.closed_loop import OracleMpc, QPFailed
+    sc = scenarios.make_batch(1, idx0=idx, N=N, n_ticks=max_ticks, dyn=dyn)
+    prm = ho.Params(dyn=dyn, N=N, Qdiag=sc["Qdiag"][:, 0].copy(), Rdiag=sc["Rdiag"][:, 0].copy())
+    mpc = OracleMpc(prm, solver="osqp")
+    X = sc["X0"][:, 0].copy()
+    t0 = time.perf_counter()
+    done = 0
+    for t in range(max_ticks):
+        x_in = ho.convert(X)
+        try:
+            U = mpc.mpcontrol(x_in, sc["xref_tab"][t:t + N, :, 0], sc["pf_tab"][t:t + N, :, 0], sc["C"][t, 0], t == 0)
+        except QPFailed:
+            break
+        for i in range(prm.mpc_factor):
+            pf = sc["pf_tab"][t, :, 0] if i < sc["pf_switch"][t, 0] else sc["pf_tab"][t + 1, :, 0]
+            X = ho.rk4_normalized(X, U[0], pf, prm)
+        done += 1
+        if time.perf_counter() - t0 > seconds:
+            break
+    return done, time.perf_counter() - t0
+
+
+def cpu_reference_sample(dyn, N, seconds, cores=None):
+    import multiprocessing as mp
+    cores = cores or os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(i, dyn, N, seconds, 400) for i in range(cores)])
+    wall = time.perf_counter() - t0
+    ticks = sum(r[0] for r in res)
+    # per-core rates add up: every process ran for its own measured time
+    value = sum(r[0] / r[1] for r in res if r[1] > 0)
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "wall_s": wall,
+            "sample": (f"{cores} hoppers (one process per core), {ticks} closed-loop ticks in total, "
+                       f"{seconds:.0f} s budget each ({wall:.1f} s wall incl. process start); numpy restatement of the "
+                       f"reference's per-tick recipe: cvxpy-shaped full QP rebuilt every tick, OSQP algorithm cold "
+                       f"start, eps_abs=eps_rel=1e-5, polish, + 20 numpy RK4 steps; horizon {N}, {dyn}")}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    cores = os.cpu_count() or 1
+    per = []
+    for s in range(args.warmup + args.steps):
+        budget = max(2.0, min(args.cpu_seconds, 120.0 / max(1, args.warmup + args.steps)))
+        r = cpu_reference_sample(args.dyn, args.horizon, budget, cores)
+        if s >= args.warmup:
+            per.append(r)
+    value = float(np.mean([r["value"] for r in per]))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": float(np.mean([r["wall_s"] for r in per])) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args, world), "note": "CPU arm: each step is a bounded sample of the same workload"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": per[-1]["sample"]},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# product arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    from hopper_mpc_inertial_b200 import scenarios, sharding
+    from hopper_mpc_inertial_b200.batch import BatchMpc
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    rank, world, local = sharding.init_from_env("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B, N, K, W = args.batch, args.horizon, args.steps, max(args.warmup, 3)
+    n_ticks = W + K
+    idx0 = rank * B                                   # contiguous global hopper range of this rank
+
+    # ---- synthetic scenario for this shard (host, numpy), tables resident in HBM ----
+    sc = scenarios.make_batch(B, idx0=idx0, N=N, n_ticks=2 * n_ticks + 2, dyn=args.dyn)
+    bm = BatchMpc(B, dyn=args.dyn, N=N, device=local, solver=args.solver,
+                  on_infeasible="respawn")
+    T = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
+    bm.set_gains(T(sc["Qdiag"]), T(sc["Rdiag"]))
+    xref_h = torch.from_numpy(np.ascontiguousarray(sc["xref_tab"])).pin_memory()
+    pf_h = torch.from_numpy(np.ascontiguousarray(sc["pf_tab"])).pin_memory()
+    C_h = torch.from_numpy(np.ascontiguousarray(sc["C_tab"]).view(np.int64)).pin_memory()
+    sw_h = torch.from_numpy(np.ascontiguousarray(sc["pf_switch"])).pin_memory()
+    xref_d, pf_d, C_d, sw_d = xref_h.to(dev), pf_h.to(dev), C_h.to(dev), sw_h.to(dev)
+    X = T(sc["X0"]).clone()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (first tick is the init tick with two solves) ----
+    bm.rollout(X, xref_d, pf_d, C_d, sw_d, 0, W, True)
+    barrier()
+
+    # ---- timed region 1: K ticks, inputs resident in HBM ----
+    bm.set_timing(True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = bm.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    out = bm.rollout(X, xref_d, pf_d, C_d, sw_d, W, K, False)
+    e1.record()
+    barrier()
+    launches = bm.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    mpc_ms, sim_ms, nt = bm.kernel_times()
+    bm.set_timing(False)
+    st = out["status"].cpu().numpy()
+    it = out["iters"].cpu().numpy()
+    nf, pa, ni = [a.cpu().numpy() for a in bm.solve_stats()]
+    flops = float(bm.solve_flops().sum().item())
+    ms_max = sharding.max_over_ranks(ms, dev)
+
+    # ---- timed region 2 (e2e): host buffers, per-step H2D of the step's inputs and D2H of its results ----
+    # The reference-facing call per tick is mpcontrol(x_in, x_ref window, pf window, C) -> U followed by the
+    # simulator; here every step uploads its reference rows from pinned host memory, runs one tick through
+    # the same C ABI (hmpc_rollout over the 1-tick staging tables) and downloads the applied control, the
+    # new state and the status.
+    st_x = torch.empty(N + 1, 12, B, dtype=torch.float64, device=dev)
+    st_p = torch.empty(N + 2, 3, B, dtype=torch.float64, device=dev)
+    st_c = torch.empty(1, B, dtype=torch.int64, device=dev)
+    st_s = torch.empty(1, B, dtype=torch.uint8, device=dev)
+    u_h = torch.empty(6, B, dtype=torch.float64).pin_memory()
+    x_h = torch.empty(13, B, dtype=torch.float64).pin_memory()
+    s_h = torch.empty(B, dtype=torch.int32).pin_memory()
+    o2 = dict(status=bm.empty(B, dtype=torch.int32), iters=bm.empty(B, dtype=torch.int32),
+              X_log=bm.empty(2, 13, B), U_log=bm.empty(1, 6, B))
+    h2d = (st_x[:N].numel() + st_p[:N + 1].numel()) * 8 + st_c.numel() * 8 + st_s.numel()
+    d2h = (u_h.numel() + x_h.numel()) * 8 + s_h.numel() * 4
+
+    def e2e_step(t):
+        st_x[:N].copy_(xref_h[t:t + N], non_blocking=True)
+        st_p[:N + 1].copy_(pf_h[t:t + N + 1], non_blocking=True)
+        st_c.copy_(C_h[t:t + 1], non_blocking=True)
+        st_s.copy_(sw_h[t:t + 1], non_blocking=True)
+        bm.rollout(X, st_x, st_p, st_c, st_s, 0, 1, False, log=True, out=o2)
+        u_h.copy_(o2["U_log"][0], non_blocking=True)
+        x_h.copy_(X, non_blocking=True)
+        s_h.copy_(o2["status"], non_blocking=True)
+
+    t_base = W + K
+    for t in range(2):
+        e2e_step(t_base + t)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for t in range(K):
+        e2e_step(t_base + 2 + t)
+    f1.record()
+    barrier()
+    e2e_ms = sharding.max_over_ranks(f0.elapsed_time(f1), dev)
+    clocks = sampler.stop()
+
+    # ---- aggregate over ranks ----
+    tot = lambda v: sharding.sum_over_ranks(v, dev)
+    n_hop = tot(B)
+    value = n_hop * K / (ms_max * 1e-3)
+    e2e_value = n_hop * K / (e2e_ms * 1e-3)
+    solved = tot(float(np.sum(st == 0))) / n_hop
+    inf_ticks = tot(float(ni.sum()))
+    launches_all = tot(launches)
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (mpc_kernel: K1 condense + K2 solve), this rank ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    m_rows = 11 * N
+    # algorithmic HBM bytes per hopper-tick of mpc_kernel (DESIGN.md "Kernels"): x_in 12, gains 18, reference
+    # window 15 N, contact mask 1, previous trajectory (p, yaw of N stages) 4 N read; trajectory 12 (N+1),
+    # inputs 6 N + 6 written; warm start: inputs 6 N read, active-set codes 11 N bytes read + written; 4 int32 stats
+    bytes_tick = 8 * (12 + 18 + 15 * N + 1 + 4 * N + 12 * (N + 1) + 6 * N + 6 + 6 * N) + 2 * m_rows + 6 * 4
+    mpc_s = mpc_ms * 1e-3 / max(nt, 1)
+    ach_gbs = bytes_tick * B / mpc_s / 1e9
+    fp64_peak = bm.measure_fp64_peak()
+    ach_tf = flops / max(nt, 1) / mpc_s / 1e12
+    prof = {}
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "mpc_kernel", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ach_gbs / hbm_peak, "traffic": prof.get("mpc_kernel_dram_bytes_per_launch"),
+                "peak_source": hbm_src, "algorithmic_bytes_per_launch": bytes_tick * B,
+                "avg_launch_ms": mpc_s * 1e3, "share_of_step": mpc_ms / ms,
+                "note": "not HBM-bound (arithmetic intensity >> machine balance); the binding resource is FP64 "
+                        "issue latency / shared memory, see roofline_fp64 and DESIGN.md"}
+    roofline_fp64 = {"bound": "fp64_fma", "kernel": "mpc_kernel", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                     "frac": ach_tf / fp64_peak if fp64_peak else None,
+                     "peak_source": "measured here: dependent-chain-free DFMA microbenchmark (hmpc_measure_fp64_peak)",
+                     "algorithmic_flops_per_hopper_tick": flops / max(nt, 1) / B}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args, world), "dyn": args.dyn, "horizon": N, "batch_per_gpu": B,
+                       "solver": args.solver, "mpc_factor": 20, "parallelism": f"shard-by-hopper x{world}, no data-path collective",
+                       "cache": "inputs larger than L2 (per-tick working set %.0f MB per GPU > 126 MB L2)"
+                                % (B * (bytes_tick + 13 * 16 + 15 * 8 * 2) / 1e6),
+                       "on_infeasible": "respawn"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_ms / K},
+            "gpu_launches": int(launches_all),
+            "clocks": clocks,
+            "roofline": roofline, "roofline_fp64": roofline_fp64,
+            "solver_stats": {"solved_exact_frac": solved, "infeasible_ticks": int(inf_ticks),
+                             "ipm_iters_per_tick": float(it.mean() / K), "factorisations_per_tick": float(nf.mean() / K),
+                             "warm_path_frac_last_tick": float(np.mean(pa == 1)),
+                             "mpc_kernel_ms_per_tick": mpc_ms / max(nt, 1), "sim_kernel_ms_per_tick": sim_ms / max(nt, 1)}}
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_reference_sample(args.dyn, N, args.cpu_seconds)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -24,7 +24,7 @@ ON_INFEASIBLE = {"hold": 0, "respawn": 1}
 SYMBOLS = [
     "hmpc_default_config", "hmpc_create", "hmpc_destroy", "hmpc_set_stream", "hmpc_synchronize",
     "hmpc_set_gains", "hmpc_convert", "hmpc_rk4", "hmpc_linearize", "hmpc_condense", "hmpc_solve",
-    "hmpc_rollout", "hmpc_solve_stats", "hmpc_launch_count", "hmpc_measure_fp64_peak", "hmpc_last_error",
+    "hmpc_rollout", "hmpc_solve_stats", "hmpc_set_timing", "hmpc_kernel_times", "hmpc_launch_count", "hmpc_measure_fp64_peak", "hmpc_last_error",
     "hmpc_abi_version",
 ]
 
@@ -78,7 +78,9 @@ def load():
     lib.hmpc_condense.argtypes = [vp] + [vp] * 10
     lib.hmpc_solve.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]
     lib.hmpc_rollout.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]
-    lib.hmpc_solve_stats.argtypes = [vp, vp, vp, vp]
+    lib.hmpc_solve_stats.argtypes = [vp, vp, vp, vp, vp]
+    lib.hmpc_set_timing.argtypes = [vp, i32]
+    lib.hmpc_kernel_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
     lib.hmpc_launch_count.argtypes = [vp, i64p]
     lib.hmpc_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
     for name in SYMBOLS:

@@ -181,8 +181,23 @@ class BatchMpc:
         nf = self.empty(self.B, dtype=torch.int32)
         pa = self.empty(self.B, dtype=torch.int32)
         ni = self.empty(self.B, dtype=torch.int32)
-        _lib.check(self.lib.hmpc_solve_stats(self._h, _ptr(nf), _ptr(pa), _ptr(ni)))
+        _lib.check(self.lib.hmpc_solve_stats(self._h, _ptr(nf), _ptr(pa), _ptr(ni), None))
         return nf, pa, ni
+
+    def solve_flops(self):
+        """Per-hopper algorithmic FLOPs of the solver kernel (last solve / accumulated over the last rollout)."""
+        fl = self.empty(self.B)
+        _lib.check(self.lib.hmpc_solve_stats(self._h, None, None, None, _ptr(fl)))
+        return fl
+
+    def set_timing(self, enable=True):
+        _lib.check(self.lib.hmpc_set_timing(self._h, 1 if enable else 0))
+
+    def kernel_times(self):
+        """(mpc_ms, sim_ms, n_ticks) summed over the most recent rollout (needs set_timing(True))."""
+        a, b, n = C.c_double(), C.c_double(), C.c_int()
+        _lib.check(self.lib.hmpc_kernel_times(self._h, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
 
     def launch_count(self):
         n = C.c_int64()

@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/hmpc.h"
 #include "hmpc_sim.cuh"
@@ -57,6 +58,11 @@ struct hmpc_handle {
     int32_t* nfac = nullptr;      // [B]
     int32_t* path = nullptr;      // [B]
     int32_t* ninf = nullptr;      // [B]
+    double* flops = nullptr;      // [B] algorithmic FLOPs of the solver kernel
+    // optional per-kernel device timing of hmpc_rollout (hmpc_set_timing)
+    int timing = 0;
+    std::vector<cudaEvent_t> ev;
+    int ev_ticks = 0;
     // solver launch geometry
     int mpc_threads = 128;
     int mpc_grid = 0;
@@ -351,7 +357,8 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
         (e = dalloc((void**)&h->st_tmp, B * 4)) != cudaSuccess || (e = dalloc((void**)&h->it_tmp, B * 4)) != cudaSuccess ||
         (e = dalloc((void**)&h->st_tick, B * 4)) != cudaSuccess || (e = dalloc((void**)&h->nfac, B * 4)) != cudaSuccess ||
         (e = dalloc((void**)&h->path, B * 4)) != cudaSuccess || (e = dalloc((void**)&h->ninf, B * 4)) != cudaSuccess ||
-        (e = dalloc((void**)&h->code, 11 * N * B)) != cudaSuccess || (e = dalloc((void**)&h->valid, B)) != cudaSuccess) {
+        (e = dalloc((void**)&h->code, 11 * N * B)) != cudaSuccess || (e = dalloc((void**)&h->valid, B)) != cudaSuccess ||
+        (e = dalloc((void**)&h->flops, B * 8)) != cudaSuccess) {
         hmpc_destroy(h);
         return fail(HMPC_ERR_ALLOC, std::string("cudaMalloc: ") + cudaGetErrorString(e));
     }
@@ -360,7 +367,7 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
     cudaMemset(h->code, 0, 11 * N * B);
     cudaMemset(h->valid, 0, B);
     cudaMemset(h->st_tick, 0, B * 4); cudaMemset(h->nfac, 0, B * 4);
-    cudaMemset(h->path, 0, B * 4); cudaMemset(h->ninf, 0, B * 4);
+    cudaMemset(h->path, 0, B * 4); cudaMemset(h->ninf, 0, B * 4); cudaMemset(h->flops, 0, B * 8);
     // default gains = the reference's (mpc_cvx_euler_3f.py:35,37)
     {
         const double Qref[12] = {50., 50., 2., 1., 1., 50., 1., 1., 1., 10., 10., 10.};
@@ -409,7 +416,8 @@ int hmpc_destroy(hmpc_handle* h) {
     cudaSetDevice(h->cfg.device);
     cudaFree(h->Qd); cudaFree(h->Rd); cudaFree(h->Xsol); cudaFree(h->Usol); cudaFree(h->xin);
     cudaFree(h->U0); cudaFree(h->st_tmp); cudaFree(h->it_tmp); cudaFree(h->ws);
-    cudaFree(h->code); cudaFree(h->valid); cudaFree(h->st_tick); cudaFree(h->nfac); cudaFree(h->path); cudaFree(h->ninf);
+    cudaFree(h->code); cudaFree(h->valid); cudaFree(h->st_tick); cudaFree(h->nfac); cudaFree(h->path); cudaFree(h->ninf); cudaFree(h->flops);
+    for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     delete h;
     return HMPC_OK;
 }
@@ -489,7 +497,7 @@ hmpc::MpcIo make_io(hmpc_handle* h, const double* x_in, const double* x_ref, con
     io.Xsol = h->Xsol; io.Usol = h->Usol; io.code = h->code; io.valid = h->valid;
     io.U_out = U; io.X_out = Xsol; io.U0_out = U0;
     io.status = status ? status : h->st_tmp; io.iters = iters ? iters : h->it_tmp;
-    io.st_tick = h->st_tick; io.nfac = h->nfac; io.path = h->path; io.ninf = h->ninf;
+    io.st_tick = h->st_tick; io.nfac = h->nfac; io.path = h->path; io.ninf = h->ninf; io.flops = h->flops;
     io.init = init; io.accumulate = accumulate;
     io.respawn = (h->cfg.on_infeasible == HMPC_INFEASIBLE_RESPAWN) ? 1 : 0;
     return io;
@@ -523,6 +531,15 @@ int hmpc_rollout(hmpc_handle* h, double* X, const double* xref_tab, const double
     HMPC_CUDA(cudaMemsetAsync(it, 0, B * 4, h->stream));
     HMPC_CUDA(cudaMemsetAsync(h->nfac, 0, B * 4, h->stream));
     HMPC_CUDA(cudaMemsetAsync(h->ninf, 0, B * 4, h->stream));
+    HMPC_CUDA(cudaMemsetAsync(h->flops, 0, B * 8, h->stream));
+    if (h->timing) {
+        while ((int)h->ev.size() < 3 * n_ticks) {
+            cudaEvent_t e;
+            HMPC_CUDA(cudaEventCreate(&e));
+            h->ev.push_back(e);
+        }
+    }
+    h->ev_ticks = h->timing ? n_ticks : 0;
     const hmpc::QpConst qc = make_qp_const(h->cfg);
     const hmpc::SimConst sc = make_sim_const(h->cfg);
     const int sim_grid = (Bi + 127) / 128;
@@ -535,22 +552,48 @@ int hmpc_rollout(hmpc_handle* h, double* X, const double* xref_tab, const double
         const size_t row = (size_t)(tick0 + t);
         hmpc::MpcIo io = make_io(h, h->xin, xref_tab + row * 12 * B, pf_tab + row * 3 * B, C_tab + row * B,
                                  (init && t == 0) ? 1 : 0, 1, nullptr, nullptr, h->U0, st, it);
+        if (h->timing) cudaEventRecord(h->ev[3 * t], h->stream);
         hmpc::mpc_kernel<<<h->mpc_grid, h->mpc_threads, h->mpc_smem, h->stream>>>(
             qc, Bi, h->mats_in_smem ? 1 : 0, h->ws, io);
+        if (h->timing) cudaEventRecord(h->ev[3 * t + 1], h->stream);
         hmpc::sim_kernel<<<sim_grid, 128, 0, h->stream>>>(
             sc, Bi, X, h->U0, pf_tab + row * 3 * B, pf_tab + (row + 1) * 3 * B,
             pf_switch ? pf_switch + row * B : nullptr, h->cfg.mpc_factor, h->xin,
             X_log ? X_log + (size_t)(t + 1) * 13 * B : nullptr, U_log ? U_log + (size_t)t * 6 * B : nullptr,
             nullptr, respawn ? h->st_tick : nullptr, respawn ? xref_tab + (row + 1) * 12 * B : nullptr);
+        if (h->timing) cudaEventRecord(h->ev[3 * t + 2], h->stream);
         h->launches += 2;
     }
     HMPC_CUDA(cudaGetLastError());
     return HMPC_OK;
 }
 
-int hmpc_solve_stats(hmpc_handle* h, int32_t* nfac, int32_t* path, int32_t* n_infeasible) {
+int hmpc_set_timing(hmpc_handle* h, int enable) {
+    if (int rc = check_handle(h)) return rc;
+    h->timing = enable ? 1 : 0;
+    return HMPC_OK;
+}
+
+int hmpc_kernel_times(hmpc_handle* h, double* mpc_ms, double* sim_ms, int* n_ticks) {
+    if (int rc = check_handle(h)) return rc;
+    HMPC_CUDA(cudaStreamSynchronize(h->stream));
+    double a = 0.0, b = 0.0;
+    for (int t = 0; t < h->ev_ticks; ++t) {
+        float m1 = 0, m2 = 0;
+        HMPC_CUDA(cudaEventElapsedTime(&m1, h->ev[3 * t], h->ev[3 * t + 1]));
+        HMPC_CUDA(cudaEventElapsedTime(&m2, h->ev[3 * t + 1], h->ev[3 * t + 2]));
+        a += m1; b += m2;
+    }
+    if (mpc_ms) *mpc_ms = a;
+    if (sim_ms) *sim_ms = b;
+    if (n_ticks) *n_ticks = h->ev_ticks;
+    return HMPC_OK;
+}
+
+int hmpc_solve_stats(hmpc_handle* h, int32_t* nfac, int32_t* path, int32_t* n_infeasible, double* flops) {
     if (int rc = check_handle(h)) return rc;
     const size_t B = (size_t)h->cfg.batch;
+    if (flops) HMPC_CUDA(cudaMemcpyAsync(flops, h->flops, B * 8, cudaMemcpyDeviceToDevice, h->stream));
     if (nfac) HMPC_CUDA(cudaMemcpyAsync(nfac, h->nfac, B * 4, cudaMemcpyDeviceToDevice, h->stream));
     if (path) HMPC_CUDA(cudaMemcpyAsync(path, h->path, B * 4, cudaMemcpyDeviceToDevice, h->stream));
     if (n_infeasible) HMPC_CUDA(cudaMemcpyAsync(n_infeasible, h->ninf, B * 4, cudaMemcpyDeviceToDevice, h->stream));

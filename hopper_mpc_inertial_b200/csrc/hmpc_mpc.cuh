@@ -76,6 +76,7 @@ struct MpcIo {
     int8_t *code, *valid;         // handle state, in/out
     double *U_out, *X_out, *U0_out;
     int32_t *status, *iters, *st_tick, *nfac, *path, *ninf;
+    double* flops;                // [B] algorithmic FLOPs (may be null)
     int init, accumulate, respawn;
 };
 
@@ -90,6 +91,7 @@ __device__ inline void mpc_hopper(const QpConst& c, Work& w, LinSys& sys, const 
     const int init = io.init || (io.respawn && !io.valid[b]);
     __syncthreads();
     int st = 0, its = 0, nfac = 0, path = 0;
+    sys.flops = 0.0;
     const int passes = init ? 2 : 1;
     for (int pass = 0; pass < passes; ++pass) {
         // linearisation point (mpc_cvx_euler_3f.py:50-62); only p and yaw of rows 0..N-1 matter
@@ -110,6 +112,7 @@ __device__ inline void mpc_hopper(const QpConst& c, Work& w, LinSys& sys, const 
         }
         __syncthreads();
         const int infeasible = condense(c, w, io.x_ref + b, (size_t)B);
+        sys.flops += flops_condense(N);
         // warm start: second init pass re-uses pass 0's solution as is; later ticks shift the
         // previous tick's solution and active set by one stage (last stage repeated)
         int warm = 0;
@@ -172,6 +175,7 @@ __device__ inline void mpc_hopper(const QpConst& c, Work& w, LinSys& sys, const 
     if (io.U0_out) for (int i = tid; i < 6; i += T) io.U0_out[(size_t)i * B + b] = w.x[i];
     if (tid == 0) {
         io.valid[b] = (st == ST_SOLVED || st == ST_INEXACT) ? 1 : 0;
+        if (io.flops) io.flops[b] = (io.accumulate ? io.flops[b] : 0.0) + sys.flops;
         io.st_tick[b] = st;
         io.path[b] = path;
         if (io.accumulate) {

@@ -67,13 +67,14 @@ struct Work {
     // QP data
     double *g, *lo, *hi;               // [n] [m] [m]
     // solver vectors
-    double *x, *xt, *rhs, *tmp, *xp, *sc, *dinv;   // [n] each
+    double *x, *tmp, *xp;                          // [n] each
+    double *xt, *rhs, *sc, *dinv;                  // [8N] each (compact systems: variables + active rows)
     double *mv[kNumMVec];                          // [m] each (roles differ per solver)
     double *red;                                   // [160] reduction scratch
     int *fixed;                        // [n]  1: variable eliminated a priori (lo == hi == 0)
     int *pin;                          // [n]  polish: variable pinned (fixed or at a bound)
     int *idx;                          // [n]  compact list of the variables in the current system
-    int *grow;                         // [n]  polish: active general rows in the current system
+    int *grow;                         // [8N] polish: active general rows in the current system
     int *code;                         // [m]  +1 upper active, -1 lower active, 0 inactive
     int *side;                         // [m]  IPM: bit0 finite upper side, bit1 finite lower side
     int *stance;                       // [N]
@@ -83,20 +84,22 @@ struct Work {
     int ld;
 };
 
-__host__ __device__ inline int factor_ld(int N) { return (6 * N) | 1; }   // odd -> conflict-free both ways
+// The polish system holds the unpinned variables plus the active friction / height rows: up to 8N unknowns.
+__host__ __device__ inline int kkt_max(int N) { return 8 * N; }
+__host__ __device__ inline int factor_ld(int N) { return kkt_max(N) | 1; }   // odd -> conflict-free both ways
 __host__ __device__ inline size_t mat_doubles(int N) {
     const size_t n = 6 * (size_t)N;
-    return n * n + n * (size_t)factor_ld(N);
+    return n * n + (size_t)kkt_max(N) * (size_t)factor_ld(N);
 }
 __host__ __device__ inline size_t work_vec_doubles(int N) {
     const int n = 6 * N, m = 11 * N;
     size_t d = 0;
     d += 4 * N + 2 * N + 2 * (N + 1) + 9 * N + 18 * N + 3 * N + 12 + 2 * 12 * (N + 1) + 12 + 6 + N;
     d += n + 2 * m;           // g lo hi
-    d += 7 * n;               // x xt rhs tmp xp sc dinv
+    d += 3 * n + 4 * kkt_max(N);   // x tmp xp | xt rhs sc dinv
     d += kNumMVec * m;
     d += 160;                 // red
-    d += (4 * n + 2 * m + N + 4 + 1) / 2 + 1;   // ints
+    d += (3 * n + kkt_max(N) + 2 * m + N + 4 + 1) / 2 + 1;   // ints
     return d;
 }
 
@@ -109,15 +112,16 @@ __device__ inline void carve(Work& w, double* base, int N) {
     w.cfree = take(12 * (N + 1)); w.err = take(12 * (N + 1)); w.Qd = take(12); w.Rd = take(6);
     w.hinv = take(N);
     w.g = take(n); w.lo = take(m); w.hi = take(m);
-    w.x = take(n); w.xt = take(n); w.rhs = take(n); w.tmp = take(n); w.xp = take(n); w.sc = take(n);
-    w.dinv = take(n);
+    const int kk = kkt_max(N);
+    w.x = take(n); w.tmp = take(n); w.xp = take(n);
+    w.xt = take(kk); w.rhs = take(kk); w.sc = take(kk); w.dinv = take(kk);
     for (int i = 0; i < kNumMVec; ++i) w.mv[i] = take(m);
     w.red = take(160);
     w.fixed = reinterpret_cast<int*>(p);
     w.pin = w.fixed + n;
     w.idx = w.pin + n;
     w.grow = w.idx + n;
-    w.code = w.grow + n;
+    w.code = w.grow + kk;
     w.side = w.code + m;
     w.stance = w.side + m;
     w.cnt = w.stance + N;
@@ -454,6 +458,18 @@ __device__ inline int condense(const QpConst& c, Work& w, const double* xref, si
     return infeasible;
 }
 
+// algorithmic FLOP counts (FMA = 2) of the dense kernels, accumulated per hopper for the roofline report
+__host__ __device__ inline double flops_factor(int nk) { return (double)nk * ((double)nk * nk - 1.0) / 3.0; }
+__host__ __device__ inline double flops_solve(int nk) { return 2.0 * (double)nk * ((double)nk - 1.0); }
+__host__ __device__ inline double flops_matvec(int n) { return 2.0 * (double)n * n; }
+// linearise (330 per stage) + closed-form Hessian blocks (~430 per 6x6 block plus 14 per term of
+// its stage sums) + gradient (30 per term, 70 per stage)
+__host__ __device__ inline double flops_condense(int N) {
+    double f = 330.0 * N + 70.0 * N;
+    for (int a = 0; a < N; ++a) f += (a + 1) * (430.0 + 14.0 * (N - a)) + 30.0 * (N - a);
+    return f;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Signed Cholesky  K = L S L'  (S = diag(+1 ... +1, -1 ... -1)) of the compact system, nk = nF + ng:
 //   variables  idx[0..nF)   full variable indices kept in the system
@@ -469,6 +485,7 @@ struct LinSys {
     double *Lm, *dinv;
     const double* H;
     const int *idx, *grow;
+    double flops = 0.0;   // algorithmic FLOPs of factor/solve since the last reset (same value in all threads)
 
     __device__ inline double entry(const AOp& A, const double* wts, double dadd, double eps, int i, int j) const {
         if (i < nF) {   // i >= j
@@ -486,6 +503,7 @@ struct LinSys {
     __device__ inline int factor(const AOp& A, const double* wts, double dadd, double eps, double* red) {
         const int tid = threadIdx.x, T = blockDim.x, nk = nF + ng;
         int bad = 0;
+        flops += flops_factor(nk);
         for (int j = 0; j < nk; ++j) {
             const int kpos = j < nF ? j : nF;   // columns k < kpos carry S = +1, columns kpos..j-1 carry -1
             for (int i = j + tid; i < nk; i += T) {
@@ -515,8 +533,9 @@ struct LinSys {
 
     // Solves K out = b for compact vectors of length nk.  b is destroyed, sc is scratch; out may alias b.
     // Ends with a __syncthreads().
-    __device__ inline void solve(double* b, double* out, double* sc) const {
+    __device__ inline void solve(double* b, double* out, double* sc) {
         const int tid = threadIdx.x, T = blockDim.x, nk = nF + ng;
+        flops += flops_solve(nk);
         __syncthreads();
         for (int j = 0; j < nk; ++j) {            // L y = b
             const double yj = b[j] * dinv[j];
@@ -535,7 +554,8 @@ struct LinSys {
     }
 };
 
-__device__ inline void sym_matvec(const double* H, int n, const double* x, double* out) {
+__device__ inline void sym_matvec(const double* H, int n, const double* x, double* out, LinSys* acct = nullptr) {
+    if (acct) acct->flops += flops_matvec(n);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         double acc = 0.0;
         for (int j = 0; j < n; ++j) acc += H[(size_t)j * n + i] * x[j];
@@ -544,6 +564,7 @@ __device__ inline void sym_matvec(const double* H, int n, const double* x, doubl
 }
 
 struct SolveInfo { int status, iters, nfac, path; double rho; };
+
 
 // ------------------------------------------------------------------------------------------------
 // Verified primal-dual active-set refinement (numpy statement: oracle/device_port.py polish_verified).
@@ -586,18 +607,19 @@ __device__ inline int polish_verified(const QpConst& c, Work& w, LinSys& sys, co
         if (tid == 0) {
             int nF = 0, ng = 0;
             for (int i = 0; i < n; ++i) if (!w.pin[i]) w.idx[nF++] = i;
-            for (int r = n; r < m; ++r) if (w.code[r] != 0) { if (ng < n) w.grow[ng] = r; ++ng; }
+            for (int r = n; r < m; ++r) if (w.code[r] != 0) { if (ng < kkt_max(N)) w.grow[ng] = r; ++ng; }
             w.cnt[0] = nF; w.cnt[1] = ng;
         }
         __syncthreads();
         const int nF = w.cnt[0], ng = w.cnt[1], nk = nF + ng;
-        if (nk > n) return 0;
+        if (nk > kkt_max(N)) return 0;
         sys.nF = nF; sys.ng = ng;
         ++info.nfac;
         if (sys.factor(A, nullptr, 0.0, c.kkt_eps, w.red)) return 0;
         double prev = 1e300;
         for (int k = 0; k < 6; ++k) {
-            sym_matvec(w.H, n, w.xp, w.tmp);
+            sym_matvec(w.H, n, w.xp, w.tmp, &sys);
+            __syncthreads();   // tmp is read through the compact index below (another thread's entry)
             double v[1] = {0.0};
             for (int i = tid; i < nk; i += T) {
                 double r_;
@@ -618,7 +640,7 @@ __device__ inline int polish_verified(const QpConst& c, Work& w, LinSys& sys, co
             __syncthreads();
         }
         // ---- pass 1: multipliers of pinned variables, scales ----
-        sym_matvec(w.H, n, w.xp, w.tmp);
+        sym_matvec(w.H, n, w.xp, w.tmp, &sys);
         double v[3] = {0, 0, 0};   // stat, scale, |mult|
         for (int i = tid; i < n; i += T) {
             const double aty = A.colT(i, mul);   // mul[i] == 0 on box rows at this point
@@ -745,7 +767,7 @@ __device__ inline int ipm_solve(const QpConst& c, Work& w, LinSys& sys, const AO
     int conv = 0;
     for (int it = 0; it <= c.ipm_max_iter; ++it) {
         // ---- residuals ----
-        sym_matvec(w.H, n, w.x, w.tmp);
+        sym_matvec(w.H, n, w.x, w.tmp, &sys);
         for (int r = tid; r < m; r += T) tv[r] = lu[r] - ll[r];
         __syncthreads();
         double v[2] = {0.0, 0.0};
@@ -964,7 +986,7 @@ __device__ inline SolveInfo admm_solve(const QpConst& c, Work& w, LinSys& sys, c
         if (it != next_check && it != last_it) continue;
         next_check = it + c.check;
         // ---- residuals of the unscaled problem (OSQP termination test) ----
-        sym_matvec(w.H, n, w.x, w.tmp);
+        sym_matvec(w.H, n, w.x, w.tmp, &sys);
         double v[6] = {0, 0, 0, 0, 0, 0};   // pri, npri, dua, |Hx|, |A'y|, |g|
         for (int r = tid; r < m; r += T) {
             const double ax = A.row(r, w.x);

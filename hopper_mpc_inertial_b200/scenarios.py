@@ -54,7 +54,7 @@ def make_batch(B, idx0=0, seed=1234, N=10, n_ticks=100, N_run=None, mpc_factor=2
         phase_ticks = max(1, int(round(t_p / mpc_dt)))
     if N_run is None:
         N_run = (n_ticks + phase_ticks + 20) * mpc_factor
-    u = _uniforms(seed, idx0, B, 40)
+    u = _uniforms(seed, idx0, B, 41)
     c = 0
 
     def take(n):
@@ -121,6 +121,6 @@ def make_batch(B, idx0=0, seed=1234, N=10, n_ticks=100, N_run=None, mpc_factor=2
     v_b = np.einsum("bji,bj->bi", R, v_w)
     X0 = np.concatenate([pos, q, v_b, w_b], axis=1)
     out = dict(X0=np.ascontiguousarray(X0.T), Qdiag=np.ascontiguousarray((Q_REF[None] * gq).T),
-               Rdiag=np.ascontiguousarray((R_REF[None] * gr).T), curve=curve, tick_offset=off, t_p=t_p)
+               Rdiag=np.ascontiguousarray((R_REF[None] * gr).T), curve=curve, tick_offset=off, t_p=t_p, _x0p=x0p, _xfp=xfp)
     out.update(tabs)
     return out

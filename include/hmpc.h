@@ -180,8 +180,15 @@ int hmpc_rollout(hmpc_handle* h, double* X, const double* xref_tab, const double
 
 /* Per-hopper statistics of the most recent hmpc_solve (or accumulated over the most recent
  * hmpc_rollout): nfac [B] = matrix factorisations, path [B] = HMPC_PATH_* of the last solve,
- * n_infeasible [B] = ticks flagged HMPC_PRIMAL_INFEASIBLE.  Device int32 arrays, each may be NULL. */
-int hmpc_solve_stats(hmpc_handle* h, int32_t* nfac, int32_t* path, int32_t* n_infeasible);
+ * n_infeasible [B] = ticks flagged HMPC_PRIMAL_INFEASIBLE (device int32 arrays), flops [B] = algorithmic
+ * floating-point operations of the solver kernel (device double array; FMA = 2).  Each may be NULL. */
+int hmpc_solve_stats(hmpc_handle* h, int32_t* nfac, int32_t* path, int32_t* n_infeasible, double* flops);
+
+/* Per-kernel device timing of hmpc_rollout: when enabled, CUDA events are recorded on the handle's stream
+ * around every launch.  hmpc_kernel_times synchronises the stream and returns the summed durations (ms)
+ * of the solver kernel and of the simulator kernel over the most recent hmpc_rollout and its tick count. */
+int hmpc_set_timing(hmpc_handle* h, int enable);
+int hmpc_kernel_times(hmpc_handle* h, double* mpc_ms, double* sim_ms, int* n_ticks);
 
 /* Counters since handle creation: kernels launched by this library (for bench gpu_launches). */
 int hmpc_launch_count(hmpc_handle* h, int64_t* n_launches);

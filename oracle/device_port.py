@@ -80,7 +80,7 @@ def polish_verified(H, g, A, lo, hi, x, code, eps=1e-9, tol=1e-9, retries=8, max
         ga[:n] = False
         rows = np.where(ga)[0]
         nF, ng = int((~pin).sum()), len(rows)
-        if nF + ng > n:
+        if nF + ng > (8 * n) // 6:      # device capacity: 8N unknowns
             return None, nfac
         lu, F = _kkt_factor(H, A, pin, rows, eps)
         nfac += 1

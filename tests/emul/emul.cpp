@@ -50,7 +50,7 @@ int emul_solve(const hmpc_config* cfg, const double* Qd, const double* Rd, const
     io.Xsol = Xsol_state; io.Usol = Usol_state; io.code = code_state; io.valid = valid_state;
     io.U_out = U; io.X_out = Xsol; io.U0_out = nullptr;
     io.status = status; io.iters = iters; io.st_tick = st_tick.data(); io.nfac = nfac; io.path = path;
-    io.ninf = ninf.data(); io.init = init; io.accumulate = 0; io.respawn = 0;
+    io.ninf = ninf.data(); io.flops = nullptr; io.init = init; io.accumulate = 0; io.respawn = 0;
     for (int b = 0; b < B; ++b) mpc_hopper(c, w, sys, A, b, B, io);
     return 0;
 }

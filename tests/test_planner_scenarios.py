@@ -1,0 +1,93 @@
+"""Host-side callers of the hot path: planner / gait tables and synthetic scenarios."""
+import numpy as np
+import pytest
+
+from hopper_mpc_inertial_b200 import planner, scenarios, sharding
+from hopper_mpc_inertial_b200.batch import cbits_from_C
+from oracle import hopper_oracle as ho
+from tests.conftest import golden
+
+
+@pytest.mark.parametrize("curve", [False, True])
+def test_planner_matches_reference_golden(curve):
+    g = golden("planner.npz")
+    tag = "curve" if curve else "straight"
+    x0 = np.zeros(12); x0[2] = 0.27
+    xf = x0.copy(); xf[0] = 0.4 * 400 * 1e-3
+    x_ref, pf_ref = planner.path_plan_init(x0, xf, 400, 60, 20, 1e-3, curve, 0.5 * 0.8 * 0.5)
+    np.testing.assert_allclose(x_ref, g[f"x_ref_{tag}"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(pf_ref, g[f"pf_ref_{tag}"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(planner.path_plan_grab(x_ref, 40, 60, 20), g[f"grab_{tag}"], rtol=0, atol=1e-12)
+
+
+def test_gait_map_bit_exact():
+    g = golden("gait.npz")
+    assert np.array_equal(planner.gait_scheduler(g["ts"]), g["sched"])
+    assert np.array_equal(planner.gait_map(60, 0.02, g["map_ts"]), g["maps"])
+
+
+def test_mpc_tables_reproduce_full_rate_tables():
+    x0 = np.zeros(12); x0[2] = 0.27
+    xf = x0.copy(); xf[0] = 0.8
+    N, n_ticks = 10, 100
+    x_ref, pf_ref = planner.path_plan_init(x0, xf, 2000, N, 20, 1e-3, False, 0.2)
+    xt, pt, C, sw = planner.mpc_tables(x_ref, pf_ref, n_ticks, N, 20, 1e-3, 0.02, 0.2)
+    t = 0.2
+    for j in range(n_ticks):
+        np.testing.assert_array_equal(xt[j:j + N], planner.path_plan_grab(x_ref, 20 * j, N, 20))
+        np.testing.assert_array_equal(pt[j:j + N], planner.path_plan_grab(pf_ref, 20 * j, N, 20))
+        for i in range(20):
+            t = t + 1e-3
+            if i == 0:
+                np.testing.assert_array_equal(C[j], ho.gait_map(N, 0.02, t, 0, ho.Params()))
+            want = pf_ref[20 * j + i]
+            got = pt[j] if i < sw[j] else pt[j + 1]
+            np.testing.assert_array_equal(got, want)
+
+
+def test_batch_tables_match_per_hopper_planner():
+    """The vectorised planner used for synthetic batches follows the reference planner's formulas."""
+    B, N, n_ticks = 5, 10, 30
+    sc = scenarios.make_batch(B, N=N, n_ticks=n_ticks, seed=9, t_p=0.8, phase_ticks=40)
+    N_run = (n_ticks + 40 + 20) * 20
+    for b in range(B):
+        x0 = np.zeros(12); xf = np.zeros(12)
+        # recover the planner end points from the tables: row 0 of hopper's reference at offset
+        off = int(sc["tick_offset"][b])
+        curve = bool(sc["curve"][b])
+        # rebuild end points exactly as make_batch does
+        u = scenarios._uniforms(9, b, 1, 41)[0]
+        # compare against the full-rate planner run with the same end points
+        x0 = sc["_x0p"][b]; xf = sc["_xfp"][b]
+        x_ref, pf_ref = planner.path_plan_init(x0, xf, N_run, N, 20, 1e-3, curve, 0.2)
+        xt, pt, C, sw = planner.mpc_tables(x_ref, pf_ref, off + n_ticks, N, 20, 1e-3, 0.02, 0.2)
+        np.testing.assert_allclose(sc["xref_tab"][:, :, b], xt[off:off + n_ticks + N], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(sc["pf_tab"][:, :, b], pt[off:off + n_ticks + N + 1], rtol=0, atol=1e-9)
+        np.testing.assert_array_equal(sc["C"][:, b], C[off:off + n_ticks])
+        np.testing.assert_array_equal(sc["C_tab"][:, b], cbits_from_C(C[off:off + n_ticks]))
+        # switch steps agree wherever the footstep actually changes inside the tick
+        for j in range(n_ticks):
+            for i in range(20):
+                got = sc["pf_tab"][j, :, b] if i < sc["pf_switch"][j, b] else sc["pf_tab"][j + 1, :, b]
+                np.testing.assert_allclose(got, pf_ref[20 * (off + j) + i], rtol=0, atol=1e-9)
+
+
+def test_scenarios_do_not_depend_on_sharding():
+    full = scenarios.make_batch(10, N=10, n_ticks=6, seed=77)
+    for world in (2, 3):
+        parts = []
+        for r in range(world):
+            lo, hi = sharding.shard_range(10, r, world)
+            parts.append(scenarios.make_batch(hi - lo, idx0=lo, N=10, n_ticks=6, seed=77))
+        for key in ("X0", "Qdiag", "Rdiag", "xref_tab", "pf_tab", "C_tab", "pf_switch"):
+            np.testing.assert_array_equal(np.concatenate([p[key] for p in parts], axis=-1), full[key])
+
+
+def test_shard_ranges_partition_the_batch():
+    for B in (1, 7, 4096, 1048576):
+        for world in (1, 2, 3, 4, 8):
+            rs = [sharding.shard_range(B, r, world) for r in range(world)]
+            assert rs[0][0] == 0 and rs[-1][1] == B
+            assert all(rs[i][1] == rs[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in rs]
+            assert max(sizes) - min(sizes) <= 1

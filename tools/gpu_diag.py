@@ -17,7 +17,7 @@ def T(a, dev):
 
 def stage_checks(dyn, N, B=16, seed=0):
     print(f"=== {dyn} N={N} B={B}")
-    sc = scenarios.make_batch(B, N=N, n_ticks=4, seed=seed)
+    sc = scenarios.make_batch(B, N=N, n_ticks=4, seed=seed, dyn=dyn)
     bm = BatchMpc(B, dyn=dyn, N=N)
     dev = bm.device
     bm.set_gains(T(sc["Qdiag"], dev), T(sc["Rdiag"], dev))
@@ -46,7 +46,7 @@ def stage_checks(dyn, N, B=16, seed=0):
     Ad, Bd = bm.linearize(T(x_guess, dev), T(pfw, dev))
     Ad, Bd = Ad.cpu().numpy(), Bd.cpu().numpy()
     cb = sc["C_tab"][0]
-    H, g, lo, hi = [a.cpu().numpy() for a in bm.condense(T(x_in, dev), T(x_guess, dev), T(xref, dev), T(pfw, dev), T(cb.view(np.int64), dev))]
+    H, g, lo, hi, inf = [a.cpu().numpy() for a in bm.condense(T(x_in, dev), T(x_guess, dev), T(xref, dev), T(pfw, dev), T(cb.view(np.int64), dev))]
     eA = eB = eH = eg = el = 0
     for b in range(B):
         p = ho.Params(dyn=dyn, N=N, Qdiag=sc["Qdiag"][:, b].copy(), Rdiag=sc["Rdiag"][:, b].copy())
@@ -55,7 +55,11 @@ def stage_checks(dyn, N, B=16, seed=0):
         qp = ho.build_qp_condensed(x_in[:, b], xref[:, :, b], Ao, Bo, Gd, sc["C"][0, b], p)
         eH = max(eH, np.abs(qp["H"] - H[..., b]).max() / np.abs(qp["H"]).max())
         eg = max(eg, np.abs(qp["g"] - g[..., b]).max() / np.abs(qp["g"]).max())
-        el = max(el, np.abs(np.clip(qp["l"], -1e30, 1e30) - lo[:, b]).max(), np.abs(np.clip(qp["u"], -1e30, 1e30) - hi[:, b]).max())
+        lq = np.clip(qp["l"], -1e30, 1e30); n_ = 6 * N
+        for k in range(2, N):
+            if lq[n_ + 4 * N + k] > -1e26:
+                lq[n_ + 4 * N + k] /= p.mpc_dt ** 2 * (k - 1) / p.m
+        el = max(el, (np.abs(lq - lo[:, b]) / (1 + np.abs(lq))).max(), np.abs(np.clip(qp["u"], -1e30, 1e30) - hi[:, b]).max())
     print("linearize err Ad", eA, "Bd", eB, "| condense rel err H", eH, "g", eg, "bounds", el)
     # solve (init) vs oracle mpcontrol
     t0 = time.time()
@@ -80,7 +84,7 @@ def stage_checks(dyn, N, B=16, seed=0):
 
 
 def loop_check(dyn, N, B=8, n_ticks=10):
-    sc = scenarios.make_batch(B, N=N, n_ticks=n_ticks, seed=7)
+    sc = scenarios.make_batch(B, N=N, n_ticks=n_ticks, seed=7, dyn=dyn)
     bm = BatchMpc(B, dyn=dyn, N=N)
     dev = bm.device
     bm.set_gains(T(sc["Qdiag"], dev), T(sc["Rdiag"], dev))
@@ -99,27 +103,38 @@ def loop_check(dyn, N, B=8, n_ticks=10):
         print(f"  hopper {b}: max|dU| {np.abs(Uo-Ug[:,:,b]).max():.2e} max|dX| {np.abs(Xo-Xg[:,:,b]).max():.2e}")
 
 
-if __name__ == "__main__":
-    for dyn in ("3f", "2f"):
-        stage_checks(dyn, 10)
-    stage_checks("3f", 20, B=4)
-    stage_checks("3f", 60, B=2)
-    loop_check("3f", 10)
-    loop_check("2f", 10)
-    # throughput first look
-    B, N, nt = 4096, 10, 10
-    sc = scenarios.make_batch(B, N=N, n_ticks=nt)
-    bm = BatchMpc(B, dyn="3f", N=N)
+def throughput(dyn, N, B, nt, **kw):
+    sc = scenarios.make_batch(B, N=N, n_ticks=nt, dyn=dyn)
+    bm = BatchMpc(B, dyn=dyn, N=N, **kw)
     dev = bm.device
     bm.set_gains(T(sc["Qdiag"], dev), T(sc["Rdiag"], dev))
     args = (T(sc["xref_tab"], dev), T(sc["pf_tab"], dev), T(sc["C_tab"].view(np.int64), dev), T(sc["pf_switch"], dev))
     X = T(sc["X0"], dev).clone()
-    out = bm.rollout(X, *args, 0, 1, True)
+    out = bm.rollout(X, *args, 0, 2, True)
     torch.cuda.synchronize()
-    t0 = time.time()
-    out = bm.rollout(X, *args, 1, nt - 1, False)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = bm.rollout(X, *args, 2, nt - 2, False)
+    e1.record()
     torch.cuda.synchronize()
-    dt = time.time() - t0
+    dt = e0.elapsed_time(e1) * 1e-3
     st = out["status"].cpu().numpy(); it = out["iters"].cpu().numpy()
-    print(f"B={B} {nt-1} ticks: {dt:.3f}s -> {B*(nt-1)/dt:.0f} steps/s; status counts", np.bincount(st, minlength=5), "mean iters/tick", it.mean() / (nt - 1))
+    nf, pa, ni = [a.cpu().numpy() for a in bm.solve_stats()]
+    print(f"{dyn} N={N} B={B} {kw} {nt-2} ticks: {dt:.3f}s -> {B*(nt-2)/dt:.0f} steps/s; status counts", np.bincount(st, minlength=5),
+          "iters/tick", it.mean() / (nt - 2), "nfac/tick", nf.mean() / (nt - 2), "infeasible ticks", ni.sum(), "paths", np.bincount(pa, minlength=5))
+
+
+if __name__ == "__main__":
+    for dyn in ("3f", "2f"):
+        stage_checks(dyn, 10)
+    stage_checks("3f", 20, B=4)
+    loop_check("3f", 10, n_ticks=30)
+    loop_check("2f", 10, n_ticks=30)
+    throughput("3f", 10, 4096, 42)
+    throughput("3f", 10, 4096, 42, warm_start=0)
+    throughput("3f", 10, 32768, 22)
+    throughput("2f", 10, 4096, 42)
+    throughput("3f", 10, 4096, 22, solver="admm", mode="fixed_iter", max_iter=50, polish=0)
+    throughput("3f", 20, 1024, 12)
+    bm = BatchMpc(1, dyn="3f", N=10)
     print("fp64 peak TFLOP/s", bm.measure_fp64_peak())
