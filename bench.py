@@ -63,10 +63,10 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self._stop = index, [], threading.Event()
+        self.index, self.samples, self._halt = index, [], threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
                                       "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
@@ -75,10 +75,10 @@ class ClockSampler(threading.Thread):
                     self.samples.append(parts)
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=6)
         sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
         mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
