@@ -149,14 +149,15 @@ __global__ void convert_kernel(int B, const double* __restrict__ X, double* __re
 // ------------------------------------------------------------------------------------------------
 // K1+K2: mpcontrol for a batch (mpc_cvx_euler_3f.py:41-69).  Persistent CTAs, one hopper at a time.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+template <int THREADS, int MIN_CTAS>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS)
 mpc_kernel(QpConst c, int B, int mats_in_smem, double* __restrict__ ws, MpcIo io) {
     extern __shared__ double smem[];
     Work w;
     setup_work(w, c, smem, ws, mats_in_smem != 0);
     const int N = c.N, n = 6 * N;
     AOp A{N, n, c.dyn == 3 ? 1 : 0, c.mu, w.stance, w.hinv};
-    LinSys sys{n, w.ld, 0, 0, w.Lm, w.dinv, w.H, w.idx, w.grow};
+    LinSys sys{n, 0, 0, w.Lm, w.dinv, w.H, w.idx, w.grow};
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         __syncthreads();
         mpc_hopper(c, w, sys, A, b, B, io);
@@ -222,7 +223,7 @@ __global__ void condense_kernel(QpConst c, int B, int mats_in_smem, double* __re
         __syncthreads();
         const int inf = condense(c, w, x_ref + b, (size_t)B);
         if (infeasible && tid == 0) infeasible[b] = inf;
-        for (int e = tid; e < n * n; e += T) H[(size_t)e * B + b] = w.H[e];
+        for (int e = tid; e < n * n; e += T) H[(size_t)e * B + b] = sym_at(w.H, n, e / n, e % n);
         for (int i = tid; i < n; i += T) g[(size_t)i * B + b] = w.g[i];
         for (int r = tid; r < m; r += T) { lo[(size_t)r * B + b] = w.lo[r]; hi[(size_t)r * B + b] = w.hi[r]; }
     }
@@ -265,6 +266,7 @@ hmpc::QpConst make_qp_const(const hmpc_config& cfg) {
     c.fz_max = cfg.fz_max; c.z_min = cfg.z_min; c.kf = cfg.kf;
     c.eps_abs = cfg.eps_abs; c.eps_rel = cfg.eps_rel; c.rho0 = cfg.rho0; c.sigma = cfg.sigma;
     c.alpha = cfg.alpha; c.kkt_eps = cfg.kkt_eps; c.polish_tol = cfg.polish_tol; c.ipm_tol = cfg.ipm_tol;
+    c.condense_flops = hmpc::flops_condense(cfg.N);
     return c;
 }
 
@@ -397,7 +399,8 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
             return fail(HMPC_ERR_ALLOC, std::string("cudaMalloc workspace: ") + cudaGetErrorString(e));
         }
     }
-    if ((e = cudaFuncSetAttribute(hmpc::mpc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mpc_smem)) != cudaSuccess ||
+    if ((e = cudaFuncSetAttribute(hmpc::mpc_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mpc_smem)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(hmpc::mpc_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mpc_smem)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(hmpc::condense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mpc_smem)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(hmpc::linearize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vec_bytes)) != cudaSuccess) {
         hmpc_destroy(h);
@@ -489,6 +492,14 @@ int hmpc_condense(hmpc_handle* h, const double* x_in, const double* x_guess, con
 }
 
 namespace {
+// small horizons: 128 threads, registers capped so that three CTAs share an SM; large: 256 threads
+void launch_mpc(hmpc_handle* h, const hmpc::QpConst& qc, const hmpc::MpcIo& io) {
+    if (h->mpc_threads == 128)
+        hmpc::mpc_kernel<128, 3><<<h->mpc_grid, 128, h->mpc_smem, h->stream>>>(qc, h->cfg.batch, h->mats_in_smem ? 1 : 0, h->ws, io);
+    else
+        hmpc::mpc_kernel<256, 1><<<h->mpc_grid, 256, h->mpc_smem, h->stream>>>(qc, h->cfg.batch, h->mats_in_smem ? 1 : 0, h->ws, io);
+}
+
 hmpc::MpcIo make_io(hmpc_handle* h, const double* x_in, const double* x_ref, const double* pf,
                     const uint64_t* Cbits, int init, int accumulate, double* U, double* Xsol, double* U0,
                     int32_t* status, int32_t* iters) {
@@ -510,8 +521,7 @@ int hmpc_solve(hmpc_handle* h, const double* x_in, const double* x_ref, const do
     if (!x_in || !x_ref || !pf || !Cbits) return fail(HMPC_ERR_BAD_ARG, "null input array");
     hmpc::MpcIo io = make_io(h, x_in, x_ref, pf, Cbits, init ? 1 : 0, 0, U, Xsol, nullptr, status, iters);
     io.respawn = 0;   // per-hopper re-initialisation only exists inside hmpc_rollout
-    hmpc::mpc_kernel<<<h->mpc_grid, h->mpc_threads, h->mpc_smem, h->stream>>>(
-        make_qp_const(h->cfg), h->cfg.batch, h->mats_in_smem ? 1 : 0, h->ws, io);
+    launch_mpc(h, make_qp_const(h->cfg), io);
     ++h->launches;
     HMPC_CUDA(cudaGetLastError());
     return HMPC_OK;
@@ -553,8 +563,7 @@ int hmpc_rollout(hmpc_handle* h, double* X, const double* xref_tab, const double
         hmpc::MpcIo io = make_io(h, h->xin, xref_tab + row * 12 * B, pf_tab + row * 3 * B, C_tab + row * B,
                                  (init && t == 0) ? 1 : 0, 1, nullptr, nullptr, h->U0, st, it);
         if (h->timing) cudaEventRecord(h->ev[3 * t], h->stream);
-        hmpc::mpc_kernel<<<h->mpc_grid, h->mpc_threads, h->mpc_smem, h->stream>>>(
-            qc, Bi, h->mats_in_smem ? 1 : 0, h->ws, io);
+        launch_mpc(h, qc, io);
         if (h->timing) cudaEventRecord(h->ev[3 * t + 1], h->stream);
         hmpc::sim_kernel<<<sim_grid, 128, 0, h->stream>>>(
             sc, Bi, X, h->U0, pf_tab + row * 3 * B, pf_tab + (row + 1) * 3 * B,

@@ -15,7 +15,7 @@ __device__ inline void setup_work(Work& w, const QpConst& c, double* smem, doubl
     const size_t n = 6 * (size_t)c.N;
     double* mat = mats_in_smem ? smem + ((work_vec_doubles(c.N) + 1) & ~(size_t)1)
                                : ws + (size_t)blockIdx.x * mat_doubles(c.N);
-    w.H = mat; w.Lm = mat + n * n;
+    w.H = mat; w.Lm = mat + n * (n + 1) / 2;
 }
 
 __device__ inline void load_hopper(const QpConst& c, Work& w, int b, int B, const double* x_in,
@@ -112,7 +112,7 @@ __device__ inline void mpc_hopper(const QpConst& c, Work& w, LinSys& sys, const 
         }
         __syncthreads();
         const int infeasible = condense(c, w, io.x_ref + b, (size_t)B);
-        sys.flops += flops_condense(N);
+        sys.flops += c.condense_flops;
         // warm start: second init pass re-uses pass 0's solution as is; later ticks shift the
         // previous tick's solution and active set by one stage (last stage repeated)
         int warm = 0;

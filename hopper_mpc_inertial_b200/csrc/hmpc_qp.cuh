@@ -34,7 +34,7 @@ namespace hmpc {
 constexpr double kInf = 1e30;
 constexpr double kInfThresh = 1e26;   // OSQP: OSQP_INFTY * MIN_SCALING
 constexpr double kRhoMin = 1e-6, kRhoMax = 1e6;
-constexpr int kNumMVec = 13;          // m-sized scratch vectors shared by the solvers
+constexpr int kNumMVec = 11;          // m-sized scratch vectors shared by the solvers
 
 enum { ST_SOLVED = 0, ST_MAX_ITER = 1, ST_INFEASIBLE = 2, ST_NON_FINITE = 3, ST_INEXACT = 4 };
 enum { PATH_NONE = 0, PATH_WARM = 1, PATH_IPM_POLISH = 2, PATH_IPM = 3, PATH_ADMM = 4 };
@@ -46,6 +46,7 @@ struct QpConst {
     double Jinv[9], rh[3], tau_max[3];
     double fz_max, z_min, kf;
     double eps_abs, eps_rel, rho0, sigma, alpha, kkt_eps, polish_tol, ipm_tol;
+    double condense_flops;   // flops_condense(N), precomputed on the host
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -70,7 +71,7 @@ struct Work {
     double *x, *tmp, *xp;                          // [n] each
     double *xt, *rhs, *sc, *dinv;                  // [8N] each (compact systems: variables + active rows)
     double *mv[kNumMVec];                          // [m] each (roles differ per solver)
-    double *red;                                   // [160] reduction scratch
+    double *red;                                   // [64] reduction scratch
     int *fixed;                        // [n]  1: variable eliminated a priori (lo == hi == 0)
     int *pin;                          // [n]  polish: variable pinned (fixed or at a bound)
     int *idx;                          // [n]  compact list of the variables in the current system
@@ -79,17 +80,18 @@ struct Work {
     int *side;                         // [m]  IPM: bit0 finite upper side, bit1 finite lower side
     int *stance;                       // [N]
     int *cnt;                          // [4]  nF, ng, ...
-    // matrices (shared or global): H n x n row-major (symmetric, full); Lm n x ld column-major factor
+    // matrices (shared or global), packed lower triangles: H of order n, the LDL' factor of order <= 8N
     double *H, *Lm;
-    int ld;
 };
 
 // The polish system holds the unpinned variables plus the active friction / height rows: up to 8N unknowns.
 __host__ __device__ inline int kkt_max(int N) { return 8 * N; }
-__host__ __device__ inline int factor_ld(int N) { return kkt_max(N) | 1; }   // odd -> conflict-free both ways
+// Symmetric / triangular matrices are stored packed, column by column (lower triangle): element (i, j),
+// i >= j, of an order-k matrix sits at tri_off(j, k) + (i - j).
+__host__ __device__ inline int tri_off(int j, int k) { return j * k - (j * (j - 1)) / 2; }
 __host__ __device__ inline size_t mat_doubles(int N) {
-    const size_t n = 6 * (size_t)N;
-    return n * n + (size_t)kkt_max(N) * (size_t)factor_ld(N);
+    const size_t n = 6 * (size_t)N, kk = (size_t)kkt_max(N);
+    return n * (n + 1) / 2 + kk * (kk + 1) / 2;
 }
 __host__ __device__ inline size_t work_vec_doubles(int N) {
     const int n = 6 * N, m = 11 * N;
@@ -98,7 +100,7 @@ __host__ __device__ inline size_t work_vec_doubles(int N) {
     d += n + 2 * m;           // g lo hi
     d += 3 * n + 4 * kkt_max(N);   // x tmp xp | xt rhs sc dinv
     d += kNumMVec * m;
-    d += 160;                 // red
+    d += 64;                  // red
     d += (3 * n + kkt_max(N) + 2 * m + N + 4 + 1) / 2 + 1;   // ints
     return d;
 }
@@ -116,7 +118,7 @@ __device__ inline void carve(Work& w, double* base, int N) {
     w.x = take(n); w.tmp = take(n); w.xp = take(n);
     w.xt = take(kk); w.rhs = take(kk); w.sc = take(kk); w.dinv = take(kk);
     for (int i = 0; i < kNumMVec; ++i) w.mv[i] = take(m);
-    w.red = take(160);
+    w.red = take(64);
     w.fixed = reinterpret_cast<int*>(p);
     w.pin = w.fixed + n;
     w.idx = w.pin + n;
@@ -125,7 +127,6 @@ __device__ inline void carve(Work& w, double* base, int N) {
     w.side = w.code + m;
     w.stance = w.side + m;
     w.cnt = w.stance + N;
-    w.ld = factor_ld(N);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -418,8 +419,8 @@ __device__ inline int condense(const QpConst& c, Work& w, const double* xref, si
                     v += Bva[r] * dv[0] * Bvb[cc] + Bva[3 + r] * dv[1] * Bvb[3 + cc] + Bva[6 + r] * dv[2] * Bvb[6 + cc];
                 v *= 2.0;
                 if (a == b && r == cc && a != N - 1) v += 2.0 * w.Rd[r];
-                w.H[(size_t)(6 * a + r) * n + 6 * b + cc] = v;
-                w.H[(size_t)(6 * b + cc) * n + 6 * a + r] = v;
+                const int hi_ = 6 * a + r, hj_ = 6 * b + cc;          // a >= b: only the diagonal blocks hold
+                if (hi_ >= hj_) w.H[tri_off(hj_, n) + (hi_ - hj_)] = v;   // entries above the diagonal
             }
     }
     // gradient
@@ -471,17 +472,52 @@ __host__ __device__ inline double flops_condense(int N) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Signed Cholesky  K = L S L'  (S = diag(+1 ... +1, -1 ... -1)) of the compact system, nk = nF + ng:
+// Ordered compaction: list[0..count) = { first + i : pred(first + i), 0 <= i < len }, count returned in
+// *cnt (shared).  Warp 0 walks the range 32 entries at a time with ballots; at most `cap` entries are
+// stored but all are counted.  Callers __syncthreads() afterwards.
+// ------------------------------------------------------------------------------------------------
+template <class Pred>
+__device__ inline void compact_indices(int first, int len, int cap, int* list, int* cnt, Pred pred) {
+#ifdef HMPC_HOST_EMUL
+    int c = 0;
+    for (int i = 0; i < len; ++i) if (pred(first + i)) { if (c < cap) list[c] = first + i; ++c; }
+    *cnt = c;
+#else
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int c = 0;
+        for (int base = 0; base < len; base += 32) {
+            const int i = base + lane;
+            const bool p = (i < len) && pred(first + i);
+            const unsigned mask = __ballot_sync(0xffffffffu, p);
+            const int pos = c + __popc(mask & ((1u << lane) - 1u));
+            if (p && pos < cap) list[pos] = first + i;
+            c += __popc(mask);
+        }
+        if (lane == 0) *cnt = c;
+    }
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// LDL' factorisation  K = L' D L'^T  (L' unit lower triangular, D diagonal) of the compact system,
+// nk = nF + ng:
 //   variables  idx[0..nF)   full variable indices kept in the system
 //   rows       grow[0..ng)  active general rows (polish only); they follow the variables
 //   K_vv = H[idx_i][idx_j] + (wts ? (A' diag(wts) A)_ij : 0) + dadd [i==j];  K_rv = A.coef;  K_rr = -eps I
-// With ng = 0 this is the plain Cholesky of the positive definite IPM / ADMM operator; with ng > 0 the
-// matrix is quasi-definite and the signed factorisation exists for every ordering (no pivoting).
-// L is stored column-major with an odd leading dimension so that column (forward substitution) and
-// row (backward substitution) accesses are both free of shared-memory bank conflicts.
+// With ng = 0 this is the positive definite IPM / ADMM operator (all pivots > 0); with ng > 0 the matrix
+// is quasi-definite: the LDL' exists for every ordering and the last ng pivots are negative.
+//
+// Right-looking: K is first assembled into shared memory by all threads, then column j's rank-1 update
+// of the trailing matrix is spread over the CTA (warp per trailing column, lane per row) with ONE
+// barrier per column; the columns are kept unscaled (U = L' D) next to dinv = 1/D.
+// Substitutions run warp-synchronously in warp 0 (the dependency chain is serial anyway and a
+// __syncwarp() is far cheaper than a CTA barrier).
+// U is stored packed (lower triangle, column by column): the forward sweep reads contiguous columns, the
+// backward sweep reads a row with the slowly varying stride nk - i.
 // ------------------------------------------------------------------------------------------------
 struct LinSys {
-    int n, ld, nF, ng;
+    int n, nF, ng;
     double *Lm, *dinv;
     const double* H;
     const int *idx, *grow;
@@ -490,7 +526,7 @@ struct LinSys {
     __device__ inline double entry(const AOp& A, const double* wts, double dadd, double eps, int i, int j) const {
         if (i < nF) {   // i >= j
             const int vi = idx[i], vj = idx[j];
-            double s = H[(size_t)vj * n + vi];
+            double s = vi >= vj ? H[tri_off(vj, n) + (vi - vj)] : H[tri_off(vi, n) + (vj - vi)];
             if (wts) { s += A.gram(vi, vj, wts); if (i == j) s += wts[vi]; }
             if (i == j) s += dadd;
             return s;
@@ -502,29 +538,26 @@ struct LinSys {
     // Returns nonzero (same value in all threads) when a pivot has the wrong sign or is not finite.
     __device__ inline int factor(const AOp& A, const double* wts, double dadd, double eps, double* red) {
         const int tid = threadIdx.x, T = blockDim.x, nk = nF + ng;
-        int bad = 0;
+        const int LS = T < 32 ? T : 32, lane = tid % LS, wid = tid / LS, nw = T / LS;
         flops += flops_factor(nk);
+        // ---- assemble the lower triangle (column-major) ----
+        for (int e = tid; e < nk * nk; e += T) {
+            const int jj = e / nk, ii = e - jj * nk;
+            if (ii >= jj) Lm[tri_off(jj, nk) + (ii - jj)] = entry(A, wts, dadd, eps, ii, jj);
+        }
+        __syncthreads();
+        int bad = 0;
         for (int j = 0; j < nk; ++j) {
-            const int kpos = j < nF ? j : nF;   // columns k < kpos carry S = +1, columns kpos..j-1 carry -1
-            for (int i = j + tid; i < nk; i += T) {
-                const double* li = Lm + i;
-                const double* lj = Lm + j;
-                double acc = 0.0, acn = 0.0;
-                for (int k = 0; k < kpos; ++k) acc += li[(size_t)k * ld] * lj[(size_t)k * ld];
-                for (int k = kpos; k < j; ++k) acn += li[(size_t)k * ld] * lj[(size_t)k * ld];
-                const double s = entry(A, wts, dadd, eps, i, j) - acc + acn;
-                Lm[(size_t)j * ld + i] = s;
-                if (i == j) red[0] = s;
-            }
-            __syncthreads();
-            const double sg = (j < nF) ? 1.0 : -1.0;
-            const double ap = red[0] * sg;
+            const double* colj = Lm + tri_off(j, nk) - j;      // colj[i] = U(i, j), i >= j
+            const double piv = colj[j];
+            const double ap = (j < nF) ? piv : -piv;
             if (!(ap > 0.0) || !(ap < 1e300)) bad = 1;
-            const double inv = rsqrt((ap > 0.0 && ap < 1e300) ? ap : 1.0);
-            for (int i = j + tid; i < nk; i += T) {
-                const double s = Lm[(size_t)j * ld + i];
-                Lm[(size_t)j * ld + i] = (i == j) ? ap * inv : s * sg * inv;
-                if (i == j) dinv[j] = inv;
+            const double rinv = 1.0 / ((ap > 0.0 && ap < 1e300) ? piv : 1.0);
+            if (tid == 0) dinv[j] = rinv;
+            for (int k = j + 1 + wid; k < nk; k += nw) {
+                const double f = colj[k] * rinv;
+                double* colk = Lm + tri_off(k, nk) - k;
+                for (int i = k + lane; i < nk; i += LS) colk[i] -= colj[i] * f;
             }
             __syncthreads();
         }
@@ -535,31 +568,54 @@ struct LinSys {
     // Ends with a __syncthreads().
     __device__ inline void solve(double* b, double* out, double* sc) {
         const int tid = threadIdx.x, T = blockDim.x, nk = nF + ng;
+        const int LS = T < 32 ? T : 32;
         flops += flops_solve(nk);
         __syncthreads();
-        for (int j = 0; j < nk; ++j) {            // L y = b
-            const double yj = b[j] * dinv[j];
-            const double* col = Lm + (size_t)j * ld;
-            for (int i = j + 1 + tid; i < nk; i += T) b[i] -= col[i] * yj;
-            if (tid == 0) sc[j] = (j < nF) ? yj : -yj;   // z = S y
-            __syncthreads();
+        if (tid < LS) {
+            const int lane = tid;
+            for (int j = 0; j < nk; ++j) {            // L' y = b, z = D^-1 y
+                const double t = b[j] * dinv[j];
+                const double* col = Lm + tri_off(j, nk) - j;
+                for (int i = j + 1 + lane; i < nk; i += LS) b[i] -= col[i] * t;
+                if (lane == 0) sc[j] = t;
+                __syncwarp();
+            }
+            for (int j = nk - 1; j >= 0; --j) {       // L'^T x = z
+                const double xj = sc[j];
+                for (int i = lane; i < j; i += LS) sc[i] -= Lm[tri_off(i, nk) + (j - i)] * dinv[i] * xj;
+                if (lane == 0) out[j] = xj;
+                __syncwarp();
+            }
         }
-        for (int j = nk - 1; j >= 0; --j) {       // L' x = z
-            const double xj = sc[j] * dinv[j];
-            const double* rowj = Lm + j;
-            for (int i = tid; i < j; i += T) sc[i] -= rowj[(size_t)i * ld] * xj;
-            if (tid == 0) out[j] = xj;
-            __syncthreads();
-        }
+        __syncthreads();
     }
 };
 
+// out = H x for the symmetric H of order n (packed lower triangle); every row is split into two halves
+// handled by two adjacent threads when the CTA is wide enough.  Callers must __syncthreads() before reading out.
+__device__ __forceinline__ double sym_at(const double* H, int n, int i, int j) {
+    return i >= j ? H[tri_off(j, n) + (i - j)] : H[tri_off(i, n) + (j - i)];
+}
 __device__ inline void sym_matvec(const double* H, int n, const double* x, double* out, LinSys* acct = nullptr) {
     if (acct) acct->flops += flops_matvec(n);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int tid = threadIdx.x, T = blockDim.x;
+    if (T >= 2 * n) {
+        const int i = tid >> 1, h = tid & 1;
         double acc = 0.0;
-        for (int j = 0; j < n; ++j) acc += H[(size_t)j * n + i] * x[j];
-        out[i] = acc;
+        if (i < n) {
+            const int j0 = h ? (n >> 1) : 0, j1 = h ? n : (n >> 1);
+            for (int j = j0; j < j1; ++j) acc += sym_at(H, n, i, j) * x[j];
+        }
+#ifndef HMPC_HOST_EMUL
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+#endif
+        if (i < n && h == 0) out[i] = acc;
+    } else {
+        for (int i = tid; i < n; i += T) {
+            double acc = 0.0;
+            for (int j = 0; j < n; ++j) acc += sym_at(H, n, i, j) * x[j];
+            out[i] = acc;
+        }
     }
 }
 
@@ -604,12 +660,8 @@ __device__ inline int polish_verified(const QpConst& c, Work& w, LinSys& sys, co
             }
         }
         __syncthreads();
-        if (tid == 0) {
-            int nF = 0, ng = 0;
-            for (int i = 0; i < n; ++i) if (!w.pin[i]) w.idx[nF++] = i;
-            for (int r = n; r < m; ++r) if (w.code[r] != 0) { if (ng < kkt_max(N)) w.grow[ng] = r; ++ng; }
-            w.cnt[0] = nF; w.cnt[1] = ng;
-        }
+        compact_indices(0, n, n, w.idx, w.cnt + 0, [&](int i) { return w.pin[i] == 0; });
+        compact_indices(n, m - n, kkt_max(N), w.grow, w.cnt + 1, [&](int r) { return w.code[r] != 0; });
         __syncthreads();
         const int nF = w.cnt[0], ng = w.cnt[1], nk = nF + ng;
         if (nk > kkt_max(N)) return 0;
@@ -641,6 +693,7 @@ __device__ inline int polish_verified(const QpConst& c, Work& w, LinSys& sys, co
         }
         // ---- pass 1: multipliers of pinned variables, scales ----
         sym_matvec(w.H, n, w.xp, w.tmp, &sys);
+        __syncthreads();
         double v[3] = {0, 0, 0};   // stat, scale, |mult|
         for (int i = tid; i < n; i += T) {
             const double aty = A.colT(i, mul);   // mul[i] == 0 on box rows at this point
@@ -718,11 +771,7 @@ __device__ inline int ipm_solve(const QpConst& c, Work& w, LinSys& sys, const AO
     }
     block_reduce<1, 2>(cntv, w.red);
     const double ni = cntv[0];
-    if (tid == 0) {
-        int nF = 0;
-        for (int i = 0; i < n; ++i) if (!w.fixed[i]) w.idx[nF++] = i;
-        w.cnt[0] = nF; w.cnt[1] = 0;
-    }
+    compact_indices(0, n, n, w.idx, w.cnt + 0, [&](int i) { return w.fixed[i] == 0; });
     for (int i = tid; i < n; i += T) { w.x[i] = 0.0; w.xt[i] = 0.0; }
     __syncthreads();
     const int nF = w.cnt[0];
@@ -946,11 +995,7 @@ __device__ inline SolveInfo admm_solve(const QpConst& c, Work& w, LinSys& sys, c
         __syncthreads();
     };
     set_rho(rho);
-    if (tid == 0) {
-        int nF = 0;
-        for (int i = 0; i < n; ++i) if (!w.fixed[i]) w.idx[nF++] = i;
-        w.cnt[0] = nF; w.cnt[1] = 0;
-    }
+    compact_indices(0, n, n, w.idx, w.cnt + 0, [&](int i) { return w.fixed[i] == 0; });
     for (int i = tid; i < n; i += T) {
         const double v = w.fixed[i] ? 0.0 : w.x[i];
         w.x[i] = fmin(fmax(v, w.lo[i]), w.hi[i]);
@@ -987,6 +1032,7 @@ __device__ inline SolveInfo admm_solve(const QpConst& c, Work& w, LinSys& sys, c
         next_check = it + c.check;
         // ---- residuals of the unscaled problem (OSQP termination test) ----
         sym_matvec(w.H, n, w.x, w.tmp, &sys);
+        __syncthreads();
         double v[6] = {0, 0, 0, 0, 0, 0};   // pri, npri, dua, |Hx|, |A'y|, |g|
         for (int r = tid; r < m; r += T) {
             const double ax = A.row(r, w.x);

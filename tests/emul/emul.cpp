@@ -26,6 +26,7 @@ static QpConst qp_const(const hmpc_config& cfg) {
     c.fz_max = cfg.fz_max; c.z_min = cfg.z_min; c.kf = cfg.kf;
     c.eps_abs = cfg.eps_abs; c.eps_rel = cfg.eps_rel; c.rho0 = cfg.rho0; c.sigma = cfg.sigma;
     c.alpha = cfg.alpha; c.kkt_eps = cfg.kkt_eps; c.polish_tol = cfg.polish_tol; c.ipm_tol = cfg.ipm_tol;
+    c.condense_flops = hmpc::flops_condense(cfg.N);
     return c;
 }
 
@@ -44,7 +45,7 @@ int emul_solve(const hmpc_config* cfg, const double* Qd, const double* Rd, const
     Work w;
     setup_work(w, c, smem.data(), nullptr, true);
     AOp A{N, n, c.dyn == 3 ? 1 : 0, c.mu, w.stance, w.hinv};
-    LinSys sys{n, w.ld, 0, 0, w.Lm, w.dinv, w.H, w.idx, w.grow};
+    LinSys sys{n, 0, 0, w.Lm, w.dinv, w.H, w.idx, w.grow};
     MpcIo io;
     io.x_in = x_in; io.x_ref = x_ref; io.pf = pf; io.Cbits = Cbits; io.Qd = Qd; io.Rd = Rd;
     io.Xsol = Xsol_state; io.Usol = Usol_state; io.code = code_state; io.valid = valid_state;
@@ -72,7 +73,7 @@ int emul_condense(const hmpc_config* cfg, const double* Qd, const double* Rd, co
             w.gp[4 * k + 2] = x_guess[(o + 2) * B + b]; w.gp[4 * k + 3] = x_guess[(o + 5) * B + b];
         }
         infeasible[b] = condense(c, w, x_ref + b, (size_t)B);
-        for (int e = 0; e < n * n; ++e) H[(size_t)e * B + b] = w.H[e];
+        for (int e = 0; e < n * n; ++e) H[(size_t)e * B + b] = sym_at(w.H, n, e / n, e % n);
         for (int i = 0; i < n; ++i) g[(size_t)i * B + b] = w.g[i];
         for (int r = 0; r < m; ++r) { lo[(size_t)r * B + b] = w.lo[r]; hi[(size_t)r * B + b] = w.hi[r]; }
     }

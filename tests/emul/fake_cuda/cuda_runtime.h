@@ -15,5 +15,6 @@ struct hmpc_emul_dim { int x; };
 static const hmpc_emul_dim threadIdx{0}, blockDim{1}, blockIdx{0}, gridDim{1};
 static inline void __syncthreads() {}
 static inline int __syncthreads_or(int v) { return v; }
+static inline void __syncwarp() {}
 static inline double rsqrt(double x) { return 1.0 / sqrt(x); }
 static inline int min(int a, int b) { return a < b ? a : b; }
