@@ -59,6 +59,7 @@ struct hmpc_handle {
     int32_t* path = nullptr;      // [B]
     int32_t* ninf = nullptr;      // [B]
     double* flops = nullptr;      // [B] algorithmic FLOPs of the solver kernel
+    int* work_ctr = nullptr;      // next hopper index handed out to the persistent CTAs
     // optional per-kernel device timing of hmpc_rollout (hmpc_set_timing)
     int timing = 0;
     std::vector<cudaEvent_t> ev;
@@ -151,15 +152,22 @@ __global__ void convert_kernel(int B, const double* __restrict__ X, double* __re
 // ------------------------------------------------------------------------------------------------
 template <int THREADS, int MIN_CTAS>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
-mpc_kernel(QpConst c, int B, int mats_in_smem, double* __restrict__ ws, MpcIo io) {
+mpc_kernel(QpConst c, int B, int mats_in_smem, double* __restrict__ ws, int* __restrict__ work_ctr, MpcIo io) {
     extern __shared__ double smem[];
+    __shared__ int s_next;
     Work w;
     setup_work(w, c, smem, ws, mats_in_smem != 0);
     const int N = c.N, n = 6 * N;
     AOp A{N, n, c.dyn == 3 ? 1 : 0, c.mu, w.stance, w.hinv};
     LinSys sys{n, 0, 0, w.Lm, w.dinv, w.H, w.idx, w.grow};
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    // dynamic distribution of hoppers over the persistent CTAs (solve times differ: warm active-set path
+    // vs interior-point path); results do not depend on the order
+    for (;;) {
         __syncthreads();
+        if (threadIdx.x == 0) s_next = atomicAdd(work_ctr, 1);
+        __syncthreads();
+        const int b = s_next;
+        if (b >= B) break;
         mpc_hopper(c, w, sys, A, b, B, io);
     }
 }
@@ -360,7 +368,7 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
         (e = dalloc((void**)&h->st_tick, B * 4)) != cudaSuccess || (e = dalloc((void**)&h->nfac, B * 4)) != cudaSuccess ||
         (e = dalloc((void**)&h->path, B * 4)) != cudaSuccess || (e = dalloc((void**)&h->ninf, B * 4)) != cudaSuccess ||
         (e = dalloc((void**)&h->code, 11 * N * B)) != cudaSuccess || (e = dalloc((void**)&h->valid, B)) != cudaSuccess ||
-        (e = dalloc((void**)&h->flops, B * 8)) != cudaSuccess) {
+        (e = dalloc((void**)&h->flops, B * 8)) != cudaSuccess || (e = dalloc((void**)&h->work_ctr, 64)) != cudaSuccess) {
         hmpc_destroy(h);
         return fail(HMPC_ERR_ALLOC, std::string("cudaMalloc: ") + cudaGetErrorString(e));
     }
@@ -399,7 +407,7 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
             return fail(HMPC_ERR_ALLOC, std::string("cudaMalloc workspace: ") + cudaGetErrorString(e));
         }
     }
-    if ((e = cudaFuncSetAttribute(hmpc::mpc_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mpc_smem)) != cudaSuccess ||
+    if ((e = cudaFuncSetAttribute(hmpc::mpc_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mpc_smem)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(hmpc::mpc_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mpc_smem)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(hmpc::condense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mpc_smem)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(hmpc::linearize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vec_bytes)) != cudaSuccess) {
@@ -419,7 +427,7 @@ int hmpc_destroy(hmpc_handle* h) {
     cudaSetDevice(h->cfg.device);
     cudaFree(h->Qd); cudaFree(h->Rd); cudaFree(h->Xsol); cudaFree(h->Usol); cudaFree(h->xin);
     cudaFree(h->U0); cudaFree(h->st_tmp); cudaFree(h->it_tmp); cudaFree(h->ws);
-    cudaFree(h->code); cudaFree(h->valid); cudaFree(h->st_tick); cudaFree(h->nfac); cudaFree(h->path); cudaFree(h->ninf); cudaFree(h->flops);
+    cudaFree(h->code); cudaFree(h->valid); cudaFree(h->st_tick); cudaFree(h->nfac); cudaFree(h->path); cudaFree(h->ninf); cudaFree(h->flops); cudaFree(h->work_ctr);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     delete h;
     return HMPC_OK;
@@ -492,12 +500,13 @@ int hmpc_condense(hmpc_handle* h, const double* x_in, const double* x_guess, con
 }
 
 namespace {
-// small horizons: 128 threads, registers capped so that three CTAs share an SM; large: 256 threads
+// small horizons: 128 threads, registers capped so that four CTAs share an SM; large: 256 threads
 void launch_mpc(hmpc_handle* h, const hmpc::QpConst& qc, const hmpc::MpcIo& io) {
+    cudaMemsetAsync(h->work_ctr, 0, sizeof(int), h->stream);
     if (h->mpc_threads == 128)
-        hmpc::mpc_kernel<128, 3><<<h->mpc_grid, 128, h->mpc_smem, h->stream>>>(qc, h->cfg.batch, h->mats_in_smem ? 1 : 0, h->ws, io);
+        hmpc::mpc_kernel<128, 4><<<h->mpc_grid, 128, h->mpc_smem, h->stream>>>(qc, h->cfg.batch, h->mats_in_smem ? 1 : 0, h->ws, h->work_ctr, io);
     else
-        hmpc::mpc_kernel<256, 1><<<h->mpc_grid, 256, h->mpc_smem, h->stream>>>(qc, h->cfg.batch, h->mats_in_smem ? 1 : 0, h->ws, io);
+        hmpc::mpc_kernel<256, 1><<<h->mpc_grid, 256, h->mpc_smem, h->stream>>>(qc, h->cfg.batch, h->mats_in_smem ? 1 : 0, h->ws, h->work_ctr, io);
 }
 
 hmpc::MpcIo make_io(hmpc_handle* h, const double* x_in, const double* x_ref, const double* pf,

@@ -26,7 +26,7 @@ __device__ inline void load_hopper(const QpConst& c, Work& w, int b, int B, cons
     for (int i = tid; i < 6; i += T) w.Rd[i] = Rd[(size_t)i * B + b];
     for (int i = tid; i < 3 * N; i += T) w.pfw[i] = pf[(size_t)i * B + b];
     const uint64_t bits = Cbits[b];
-    for (int k = tid; k < N; k += T) w.stance[k] = (int)((bits >> k) & 1ull);
+    for (int k = tid; k < N; k += T) w.stance[k] = (int8_t)((bits >> k) & 1ull);
 }
 
 // linear rollout of the solution (mpc_cvx_euler_3f.py:133,140 dynamics rows): xs [(N+1)][12] in shared
@@ -110,6 +110,8 @@ __device__ inline void mpc_hopper(const QpConst& c, Work& w, LinSys& sys, const 
                 gp[2] = io.Xsol[(o + 2) * B + b]; gp[3] = io.Xsol[(o + 5) * B + b];
             }
         }
+        // the footstep window shares storage with solver scratch (carve()): reload it after a solve
+        if (pass > 0) for (int i = tid; i < 3 * N; i += T) w.pfw[i] = io.pf[(size_t)i * B + b];
         __syncthreads();
         const int infeasible = condense(c, w, io.x_ref + b, (size_t)B);
         sys.flops += c.condense_flops;
@@ -131,7 +133,7 @@ __device__ inline void mpc_hopper(const QpConst& c, Work& w, LinSys& sys, const 
                     if (r < n) src = (r + 6 < n) ? r + 6 : r;
                     else if (r < n + 4 * N) src = (r + 4 < n + 4 * N) ? r + 4 : r;
                     else src = (r + 1 < m) ? r + 1 : r;
-                    w.code[r] = (int)io.code[(size_t)src * B + b];
+                    w.code[r] = io.code[(size_t)src * B + b];
                 }
             }
         }

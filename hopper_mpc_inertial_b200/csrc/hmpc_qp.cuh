@@ -69,23 +69,24 @@ struct Work {
     double *g, *lo, *hi;               // [n] [m] [m]
     // solver vectors
     double *x, *tmp, *xp;                          // [n] each
-    double *xt, *rhs, *sc, *dinv;                  // [8N] each (compact systems: variables + active rows)
+    double *xt, *rhs, *sc, *dinv;                  // [kkt_max] each (compact systems: variables + active rows)
     double *mv[kNumMVec];                          // [m] each (roles differ per solver)
     double *red;                                   // [64] reduction scratch
-    int *fixed;                        // [n]  1: variable eliminated a priori (lo == hi == 0)
-    int *pin;                          // [n]  polish: variable pinned (fixed or at a bound)
     int *idx;                          // [n]  compact list of the variables in the current system
-    int *grow;                         // [8N] polish: active general rows in the current system
-    int *code;                         // [m]  +1 upper active, -1 lower active, 0 inactive
-    int *side;                         // [m]  IPM: bit0 finite upper side, bit1 finite lower side
-    int *stance;                       // [N]
+    int *grow;                         // [kkt_max] polish: active general rows in the current system
     int *cnt;                          // [4]  nF, ng, ...
+    int8_t *fixed;                     // [n]  1: variable eliminated a priori (lo == hi == 0)
+    int8_t *pin;                       // [n]  polish: variable pinned (fixed or at a bound)
+    int8_t *code;                      // [m]  +1 upper active, -1 lower active, 0 inactive
+    int8_t *side;                      // [m]  IPM: bit0 finite upper side, bit1 finite lower side
+    int8_t *stance;                    // [N]
     // matrices (shared or global), packed lower triangles: H of order n, the LDL' factor of order <= 8N
     double *H, *Lm;
 };
 
-// The polish system holds the unpinned variables plus the active friction / height rows: up to 8N unknowns.
-__host__ __device__ inline int kkt_max(int N) { return 8 * N; }
+// The polish system holds the unpinned variables plus the active friction / height rows: up to 7N+2
+// unknowns (a larger active set makes the polish give up and the interior point take over).
+__host__ __device__ inline int kkt_max(int N) { return 7 * N + 2; }
 // Symmetric / triangular matrices are stored packed, column by column (lower triangle): element (i, j),
 // i >= j, of an order-k matrix sits at tri_off(j, k) + (i - j).
 __host__ __device__ inline int tri_off(int j, int k) { return j * k - (j * (j - 1)) / 2; }
@@ -96,37 +97,41 @@ __host__ __device__ inline size_t mat_doubles(int N) {
 __host__ __device__ inline size_t work_vec_doubles(int N) {
     const int n = 6 * N, m = 11 * N;
     size_t d = 0;
-    d += 4 * N + 2 * N + 2 * (N + 1) + 9 * N + 18 * N + 3 * N + 12 + 2 * 12 * (N + 1) + 12 + 6 + N;
+    // linearisation (cfree, gp, pfw alias the last two m-vectors: they are dead once condense() returns)
+    d += 2 * N + 2 * (N + 1) + 9 * N + 18 * N + 12 + 12 * (N + 1) + 12 + 6 + N;
     d += n + 2 * m;           // g lo hi
-    d += 3 * n + 4 * kkt_max(N);   // x tmp xp | xt rhs sc dinv
+    d += 3 * n + N + 4 * kkt_max(N);   // x xp tmp(+N) | xt rhs sc dinv
     d += kNumMVec * m;
     d += 64;                  // red
-    d += (3 * n + kkt_max(N) + 2 * m + N + 4 + 1) / 2 + 1;   // ints
+    d += (n + kkt_max(N) + 4 + 1) / 2;          // int32: idx grow cnt
+    d += (2 * n + 2 * m + N + 7) / 8;           // int8: fixed pin code side stance
     return d;
 }
 
 __device__ inline void carve(Work& w, double* base, int N) {
-    const int n = 6 * N, m = 11 * N;
+    const int n = 6 * N, m = 11 * N, kk = kkt_max(N);
     double* p = base;
     auto take = [&](size_t k) { double* r = p; p += k; return r; };
-    w.gp = take(4 * N); w.cz = take(N); w.sz = take(N); w.PC = take(N + 1); w.PS = take(N + 1);
-    w.Bv = take(9 * N); w.Bw = take(18 * N); w.pfw = take(3 * N); w.xin = take(12);
-    w.cfree = take(12 * (N + 1)); w.err = take(12 * (N + 1)); w.Qd = take(12); w.Rd = take(6);
+    w.cz = take(N); w.sz = take(N); w.PC = take(N + 1); w.PS = take(N + 1);
+    w.Bv = take(9 * N); w.Bw = take(18 * N); w.xin = take(12);
+    w.err = take(12 * (N + 1)); w.Qd = take(12); w.Rd = take(6);
     w.hinv = take(N);
     w.g = take(n); w.lo = take(m); w.hi = take(m);
-    const int kk = kkt_max(N);
-    w.x = take(n); w.tmp = take(n); w.xp = take(n);
+    // tmp | xt | rhs | sc are contiguous: together they are the 4-column panel scratch of LinSys::factor
+    w.x = take(n); w.xp = take(n); w.tmp = take(n + N);
     w.xt = take(kk); w.rhs = take(kk); w.sc = take(kk); w.dinv = take(kk);
     for (int i = 0; i < kNumMVec; ++i) w.mv[i] = take(m);
+    // condense-only scratch on top of the solvers' last two m-vectors: 12(N+1) + 4N + 3N <= 2 * 11N
+    w.cfree = w.mv[kNumMVec - 2]; w.gp = w.cfree + 12 * (N + 1); w.pfw = w.gp + 4 * N;
     w.red = take(64);
-    w.fixed = reinterpret_cast<int*>(p);
-    w.pin = w.fixed + n;
-    w.idx = w.pin + n;
+    w.idx = reinterpret_cast<int*>(p);
     w.grow = w.idx + n;
-    w.code = w.grow + kk;
+    w.cnt = w.grow + kk;
+    w.fixed = reinterpret_cast<int8_t*>(w.cnt + 4);
+    w.pin = w.fixed + n;
+    w.code = w.pin + n;
     w.side = w.code + m;
     w.stance = w.side + m;
-    w.cnt = w.stance + N;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -170,7 +175,7 @@ __device__ inline void block_reduce(double (&v)[K], double* red) {
 struct AOp {
     int N, n, fy_rows;   // fy_rows: 1 for 3f
     double mu;
-    const int* stance;
+    const int8_t* stance;
     const double* hinv;  // [N] 1/(k-1)
     __device__ __forceinline__ bool fr_on(int k, int s) const { return stance[k] && (s < 2 || fy_rows); }
     __device__ inline double row(int r, const double* x) const {
@@ -362,7 +367,7 @@ __device__ inline int condense(const QpConst& c, Work& w, const double* xref, si
             else if (!w.stance[k]) { lo = 0.0; hi = 0.0; }
             else if (cc == 2) { lo = 0.0; hi = c.fz_max; }
             if (cc == 1 && c.dyn == 2) { lo = 0.0; hi = 0.0; }
-            w.fixed[r] = (hi - lo) < 1e-12;
+            w.fixed[r] = (hi - lo) < 1e-12 ? 1 : 0;
         } else if (r < n + 4 * N) {
             const int k = (r - n) >> 2, s = (r - n) & 3;
             if (w.stance[k] && (s < 2 || c.dyn == 3)) hi = 0.0;
@@ -536,30 +541,62 @@ struct LinSys {
     }
 
     // Returns nonzero (same value in all threads) when a pivot has the wrong sign or is not finite.
-    __device__ inline int factor(const AOp& A, const double* wts, double dadd, double eps, double* red) {
+    // P: scratch of at least 4 (nk - 4) doubles (the pre-scaled panel, see below).
+    __device__ inline int factor(const AOp& A, const double* wts, double dadd, double eps, double* P) {
         const int tid = threadIdx.x, T = blockDim.x, nk = nF + ng;
         const int LS = T < 32 ? T : 32, lane = tid % LS, wid = tid / LS, nw = T / LS;
         flops += flops_factor(nk);
-        // ---- assemble the lower triangle (column-major) ----
+        // ---- assemble the lower triangle (packed, column by column) ----
         for (int e = tid; e < nk * nk; e += T) {
             const int jj = e / nk, ii = e - jj * nk;
             if (ii >= jj) Lm[tri_off(jj, nk) + (ii - jj)] = entry(A, wts, dadd, eps, ii, jj);
         }
         __syncthreads();
         int bad = 0;
-        for (int j = 0; j < nk; ++j) {
-            const double* colj = Lm + tri_off(j, nk) - j;      // colj[i] = U(i, j), i >= j
-            const double piv = colj[j];
-            const double ap = (j < nF) ? piv : -piv;
-            if (!(ap > 0.0) || !(ap < 1e300)) bad = 1;
-            const double rinv = 1.0 / ((ap > 0.0 && ap < 1e300) ? piv : 1.0);
-            if (tid == 0) dinv[j] = rinv;
-            for (int k = j + 1 + wid; k < nk; k += nw) {
-                const double f = colj[k] * rinv;
-                double* colk = Lm + tri_off(k, nk) - k;
-                for (int i = k + lane; i < nk; i += LS) colk[i] -= colj[i] * f;
+        // ---- blocked right-looking elimination, 4 pivot columns per block ----
+        for (int j0 = 0; j0 < nk; j0 += 4) {
+            const int bs = (nk - j0) < 4 ? (nk - j0) : 4, t0 = j0 + bs;
+            // panel: eliminate column j inside the panel only; keep P[i - t0][p] = U(i, j) / d_j for the rows below
+            for (int p = 0; p < bs; ++p) {
+                const int j = j0 + p;
+                const double* colj = Lm + tri_off(j, nk) - j;      // colj[i] = U(i, j), i >= j
+                const double piv = colj[j];
+                const double ap = (j < nF) ? piv : -piv;
+                const bool ok = (ap > 0.0) && (ap < 1e300);
+                if (!ok) bad = 1;
+                const double rinv = 1.0 / (ok ? piv : 1.0);
+                if (tid == 0) dinv[j] = rinv;
+                for (int i = j + 1 + tid; i < nk; i += T) {
+                    const double uij = colj[i];
+                    if (i >= t0) P[4 * (i - t0) + p] = uij * rinv;
+                    for (int k = j + 1; k < t0 && k <= i; ++k)
+                        Lm[tri_off(k, nk) + (i - k)] -= uij * (colj[k] * rinv);
+                }
+                __syncthreads();
             }
-            __syncthreads();
+            // trailing matrix: rank-4 update.  Lanes own row pairs (short row t0+q, long row nk-1-q: equal
+            // work per lane, consecutive addresses across lanes), warps own the columns k = t0 + wid (mod nw).
+            const int t = nk - t0;
+            if (t > 0) {       // bs == 4 here
+                const double* c0 = Lm + tri_off(j0, nk) - j0;
+                const double* c1 = Lm + tri_off(j0 + 1, nk) - (j0 + 1);
+                const double* c2 = Lm + tri_off(j0 + 2, nk) - (j0 + 2);
+                const double* c3 = Lm + tri_off(j0 + 3, nk) - (j0 + 3);
+                const int npairs = (t + 1) >> 1;
+                for (int q = lane; q < npairs; q += LS) {
+                    for (int side = 0; side < 2; ++side) {
+                        const int r = side ? (nk - 1 - q) : (t0 + q);
+                        if (side && r == t0 + q) break;
+                        const double a0 = c0[r], a1 = c1[r], a2 = c2[r], a3 = c3[r];
+                        for (int k = t0 + wid; k <= r; k += nw) {
+                            const double* pk = P + 4 * (k - t0);
+                            double* e = Lm + tri_off(k, nk) + (r - k);
+                            *e -= a0 * pk[0] + a1 * pk[1] + a2 * pk[2] + a3 * pk[3];
+                        }
+                    }
+                }
+                __syncthreads();
+            }
         }
         return bad;
     }
@@ -645,7 +682,7 @@ __device__ inline int polish_verified(const QpConst& c, Work& w, LinSys& sys, co
         if (cd > 0 && w.hi[r] > kInfThresh) cd = 0;
         if (cd < 0 && w.lo[r] < -kInfThresh) cd = 0;
         if (r < n && w.fixed[r]) cd = 0;
-        w.code[r] = cd;
+        w.code[r] = (int8_t)cd;
     }
     __syncthreads();
     for (int trial = 0; trial <= c.retries; ++trial) {
@@ -655,7 +692,7 @@ __device__ inline int polish_verified(const QpConst& c, Work& w, LinSys& sys, co
             mul[r] = 0.0;
             if (r < n) {
                 const int pin = (w.fixed[r] || cd != 0) ? 1 : 0;
-                w.pin[r] = pin;
+                w.pin[r] = (int8_t)pin;
                 if (pin) w.xp[r] = w.fixed[r] ? 0.0 : bnd[r];
             }
         }
@@ -667,7 +704,7 @@ __device__ inline int polish_verified(const QpConst& c, Work& w, LinSys& sys, co
         if (nk > kkt_max(N)) return 0;
         sys.nF = nF; sys.ng = ng;
         ++info.nfac;
-        if (sys.factor(A, nullptr, 0.0, c.kkt_eps, w.red)) return 0;
+        if (sys.factor(A, nullptr, 0.0, c.kkt_eps, w.tmp)) return 0;
         double prev = 1e300;
         for (int k = 0; k < 6; ++k) {
             sym_matvec(w.H, n, w.xp, w.tmp, &sys);
@@ -724,7 +761,7 @@ __device__ inline int polish_verified(const QpConst& c, Work& w, LinSys& sys, co
                 if (lo - ax > tol * (1.0 + fabs(lo))) { ncode = -1; bad |= 1; }
                 else if (ax - hi > tol * (1.0 + fabs(hi))) { ncode = 1; bad |= 1; }
             }
-            if (ncode != cd) { changed = 1; w.code[r] = ncode; }
+            if (ncode != cd) { changed = 1; w.code[r] = (int8_t)ncode; }
         }
         bad = __syncthreads_or(bad);
         changed = __syncthreads_or(changed);
@@ -766,7 +803,7 @@ __device__ inline int ipm_solve(const QpConst& c, Work& w, LinSys& sys, const AO
             if (w.hi[r] < kInfThresh) s |= 1;
             if (w.lo[r] > -kInfThresh) s |= 2;
         }
-        w.side[r] = s;
+        w.side[r] = (int8_t)s;
         cntv[0] += (double)((s & 1) + ((s >> 1) & 1));
     }
     block_reduce<1, 2>(cntv, w.red);
@@ -787,7 +824,7 @@ __device__ inline int ipm_solve(const QpConst& c, Work& w, LinSys& sys, const AO
     }
     __syncthreads();
     ++info.nfac;
-    if (sys.factor(A, ni > 0.0 ? wts : nullptr, 0.0, 0.0, w.red)) return 0;
+    if (sys.factor(A, ni > 0.0 ? wts : nullptr, 0.0, 0.0, w.tmp)) return 0;
     for (int i = tid; i < nF; i += T) { const int vi = w.idx[i]; w.rhs[i] = -w.g[vi] - (ni > 0.0 ? A.colT(vi, tv) : 0.0); }
     sys.solve(w.rhs, w.rhs, w.sc);
     for (int i = tid; i < nF; i += T) w.x[w.idx[i]] = w.rhs[i];
@@ -851,7 +888,7 @@ __device__ inline int ipm_solve(const QpConst& c, Work& w, LinSys& sys, const AO
         }
         __syncthreads();
         ++info.nfac;
-        if (sys.factor(A, wts, 0.0, 0.0, w.red)) break;
+        if (sys.factor(A, wts, 0.0, 0.0, w.tmp)) break;
         double alpha = 1.0, sigmu = 0.0;
         for (int phase = 0; phase < 2; ++phase) {
             // complementarity targets: predictor rc = s*lam ; corrector rc = s*lam + ds*dlam - sigma*mu
@@ -866,6 +903,7 @@ __device__ inline int ipm_solve(const QpConst& c, Work& w, LinSys& sys, const AO
             for (int i = tid; i < nF; i += T) { const int vi = w.idx[i]; w.rhs[i] = -w.xp[vi] - A.colT(vi, tv); }
             sys.solve(w.rhs, w.rhs, w.sc);
             for (int i = tid; i < nF; i += T) w.xt[w.idx[i]] = w.rhs[i];
+            for (int i = tid; i < n; i += T) if (w.fixed[i]) w.xt[i] = 0.0;   // xt doubles as factor scratch
             __syncthreads();
             double rmin[1] = {1.0};
             for (int r = tid; r < m; r += T) {
@@ -1007,7 +1045,7 @@ __device__ inline SolveInfo admm_solve(const QpConst& c, Work& w, LinSys& sys, c
     for (int r = tid; r < m; r += T) z[r] = fmin(fmax(A.row(r, w.x), w.lo[r]), w.hi[r]);
     __syncthreads();
     info.nfac = 1;
-    if (sys.factor(A, rv, sigma, 0.0, w.red)) { info.status = ST_NON_FINITE; return info; }
+    if (sys.factor(A, rv, sigma, 0.0, w.tmp)) { info.status = ST_NON_FINITE; return info; }
     const int last_it = c.max_iter;
     int next_check = (c.mode == 1) ? last_it : min(c.first_check, last_it);
     for (int it = 1; it <= last_it; ++it) {
@@ -1016,6 +1054,7 @@ __device__ inline SolveInfo admm_solve(const QpConst& c, Work& w, LinSys& sys, c
         for (int i = tid; i < nF; i += T) { const int vi = w.idx[i]; w.rhs[i] = sigma * w.x[vi] - w.g[vi] + A.colT(vi, wv); }
         sys.solve(w.rhs, w.rhs, w.sc);
         for (int i = tid; i < nF; i += T) w.xt[w.idx[i]] = w.rhs[i];
+        for (int i = tid; i < n; i += T) if (w.fixed[i]) w.xt[i] = 0.0;       // xt doubles as factor scratch
         __syncthreads();
         for (int r = tid; r < m; r += T) {
             const double zt = A.row(r, w.xt);
@@ -1060,7 +1099,7 @@ __device__ inline SolveInfo admm_solve(const QpConst& c, Work& w, LinSys& sys, c
                 rho = rn;
                 set_rho(rho);
                 ++info.nfac;
-                if (sys.factor(A, rv, sigma, 0.0, w.red)) { info.status = ST_NON_FINITE; break; }
+                if (sys.factor(A, rv, sigma, 0.0, w.tmp)) { info.status = ST_NON_FINITE; break; }
             }
         }
     }
