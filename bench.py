@@ -298,7 +298,9 @@ def run_b200(args):
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "mpc_kernel", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": ach_gbs / hbm_peak, "traffic": prof.get("mpc_kernel_dram_bytes_per_launch"),
+                "frac": ach_gbs / hbm_peak,
+                "traffic": (prof["mpc_kernel_dram_bytes_per_hopper"] * B) if "mpc_kernel_dram_bytes_per_hopper" in prof else None,
+                "traffic_source": ("ncu dram__bytes_read+write per hopper at batch %d (profiles/%s) x this batch" % (prof.get("capture_batch", 0), prof.get("source", "?"))) if prof else None,
                 "peak_source": hbm_src, "algorithmic_bytes_per_launch": bytes_tick * B,
                 "avg_launch_ms": mpc_s * 1e3, "share_of_step": mpc_ms / ms,
                 "note": "not HBM-bound (arithmetic intensity >> machine balance); the binding resource is FP64 "

@@ -152,7 +152,7 @@ __global__ void convert_kernel(int B, const double* __restrict__ X, double* __re
 // ------------------------------------------------------------------------------------------------
 template <int THREADS, int MIN_CTAS>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
-mpc_kernel(QpConst c, int B, int mats_in_smem, double* __restrict__ ws, int* __restrict__ work_ctr, MpcIo io) {
+mpc_kernel(QpConst c, int B, int mats_in_smem, int sm_count, double* __restrict__ ws, int* __restrict__ work_ctr, MpcIo io) {
     extern __shared__ double smem[];
     __shared__ int s_next;
     Work w;
@@ -160,6 +160,8 @@ mpc_kernel(QpConst c, int B, int mats_in_smem, double* __restrict__ ws, int* __r
     const int N = c.N, n = 6 * N;
     AOp A{N, n, c.dyn == 3 ? 1 : 0, c.mu, w.stance, w.hinv};
     LinSys sys{n, 0, 0, w.Lm, w.dinv, w.H, w.idx, w.grow};
+    // CTAs are dealt to the SMs round-robin, so the CTAs sharing an SM differ in blockIdx.x / #SMs
+    sys.solver_warp = blockIdx.x / sm_count;
     // dynamic distribution of hoppers over the persistent CTAs (solve times differ: warm active-set path
     // vs interior-point path); results do not depend on the order
     for (;;) {
@@ -504,9 +506,9 @@ namespace {
 void launch_mpc(hmpc_handle* h, const hmpc::QpConst& qc, const hmpc::MpcIo& io) {
     cudaMemsetAsync(h->work_ctr, 0, sizeof(int), h->stream);
     if (h->mpc_threads == 128)
-        hmpc::mpc_kernel<128, 4><<<h->mpc_grid, 128, h->mpc_smem, h->stream>>>(qc, h->cfg.batch, h->mats_in_smem ? 1 : 0, h->ws, h->work_ctr, io);
+        hmpc::mpc_kernel<128, 4><<<h->mpc_grid, 128, h->mpc_smem, h->stream>>>(qc, h->cfg.batch, h->mats_in_smem ? 1 : 0, h->sm_count, h->ws, h->work_ctr, io);
     else
-        hmpc::mpc_kernel<256, 1><<<h->mpc_grid, 256, h->mpc_smem, h->stream>>>(qc, h->cfg.batch, h->mats_in_smem ? 1 : 0, h->ws, h->work_ctr, io);
+        hmpc::mpc_kernel<256, 1><<<h->mpc_grid, 256, h->mpc_smem, h->stream>>>(qc, h->cfg.batch, h->mats_in_smem ? 1 : 0, h->sm_count, h->ws, h->work_ctr, io);
 }
 
 hmpc::MpcIo make_io(hmpc_handle* h, const double* x_in, const double* x_ref, const double* pf,

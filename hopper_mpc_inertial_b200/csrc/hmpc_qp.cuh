@@ -527,6 +527,7 @@ struct LinSys {
     const double* H;
     const int *idx, *grow;
     double flops = 0.0;   // algorithmic FLOPs of factor/solve since the last reset (same value in all threads)
+    int solver_warp = 0;  // which warp of the CTA runs the substitutions
 
     __device__ inline double entry(const AOp& A, const double* wts, double dadd, double eps, int i, int j) const {
         if (i < nF) {   // i >= j
@@ -588,10 +589,13 @@ struct LinSys {
                         const int r = side ? (nk - 1 - q) : (t0 + q);
                         if (side && r == t0 + q) break;
                         const double a0 = c0[r], a1 = c1[r], a2 = c2[r], a3 = c3[r];
-                        for (int k = t0 + wid; k <= r; k += nw) {
-                            const double* pk = P + 4 * (k - t0);
-                            double* e = Lm + tri_off(k, nk) + (r - k);
-                            *e -= a0 * pk[0] + a1 * pk[1] + a2 * pk[2] + a3 * pk[3];
+                        int k = t0 + wid;
+                        int off = tri_off(k, nk) - k;                 // column k starts at Lm + off + k
+                        const double* pk = P + 4 * (k - t0);
+                        for (; k <= r; k += nw) {
+                            Lm[off + r] -= a0 * pk[0] + a1 * pk[1] + a2 * pk[2] + a3 * pk[3];
+                            off += nw * (nk - 1 - k) - (nw * (nw - 1)) / 2;
+                            pk += 4 * nw;
                         }
                     }
                 }
@@ -608,8 +612,11 @@ struct LinSys {
         const int LS = T < 32 ? T : 32;
         flops += flops_solve(nk);
         __syncthreads();
-        if (tid < LS) {
-            const int lane = tid;
+        // one warp runs the substitution; co-resident CTAs use different warp slots so that their
+        // substitutions land on different SM sub-partitions (warp w lives on scheduler w % 4)
+        const int w0 = (T / LS > 1) ? (solver_warp % (T / LS)) * LS : 0;
+        if (tid >= w0 && tid < w0 + LS) {
+            const int lane = tid - w0;
             for (int j = 0; j < nk; ++j) {            // L' y = b, z = D^-1 y
                 const double t = b[j] * dinv[j];
                 const double* col = Lm + tri_off(j, nk) - j;
@@ -626,6 +633,7 @@ struct LinSys {
         }
         __syncthreads();
     }
+
 };
 
 // out = H x for the symmetric H of order n (packed lower triangle); every row is split into two halves
@@ -633,26 +641,30 @@ struct LinSys {
 __device__ __forceinline__ double sym_at(const double* H, int n, int i, int j) {
     return i >= j ? H[tri_off(j, n) + (i - j)] : H[tri_off(i, n) + (j - i)];
 }
+// row i of H times x over the column range [j0, j1): the part left of the diagonal walks the packed columns
+// (stride n-1-j), the part right of it is contiguous
+__device__ __forceinline__ double sym_row_dot(const double* H, int n, int i, int j0, int j1, const double* x) {
+    double acc = 0.0;
+    const int je = j1 < i + 1 ? j1 : i + 1;
+    int off = tri_off(j0, n) - j0;
+    for (int j = j0; j < je; ++j) { acc += H[off + i] * x[j]; off += n - 1 - j; }
+    const double* row = H + tri_off(i, n) - i;
+    for (int j = (j0 > i + 1 ? j0 : i + 1); j < j1; ++j) acc += row[j] * x[j];
+    return acc;
+}
 __device__ inline void sym_matvec(const double* H, int n, const double* x, double* out, LinSys* acct = nullptr) {
     if (acct) acct->flops += flops_matvec(n);
     const int tid = threadIdx.x, T = blockDim.x;
     if (T >= 2 * n) {
         const int i = tid >> 1, h = tid & 1;
         double acc = 0.0;
-        if (i < n) {
-            const int j0 = h ? (n >> 1) : 0, j1 = h ? n : (n >> 1);
-            for (int j = j0; j < j1; ++j) acc += sym_at(H, n, i, j) * x[j];
-        }
+        if (i < n) acc = sym_row_dot(H, n, i, h ? (n >> 1) : 0, h ? n : (n >> 1), x);
 #ifndef HMPC_HOST_EMUL
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
 #endif
         if (i < n && h == 0) out[i] = acc;
     } else {
-        for (int i = tid; i < n; i += T) {
-            double acc = 0.0;
-            for (int j = 0; j < n; ++j) acc += sym_at(H, n, i, j) * x[j];
-            out[i] = acc;
-        }
+        for (int i = tid; i < n; i += T) out[i] = sym_row_dot(H, n, i, 0, n, x);
     }
 }
 
@@ -709,17 +721,27 @@ __device__ inline int polish_verified(const QpConst& c, Work& w, LinSys& sys, co
         for (int k = 0; k < 6; ++k) {
             sym_matvec(w.H, n, w.xp, w.tmp, &sys);
             __syncthreads();   // tmp is read through the compact index below (another thread's entry)
-            double v[1] = {0.0};
+            double v[2] = {0.0, 0.0};   // residual, magnitude of the terms it is the difference of
             for (int i = tid; i < nk; i += T) {
                 double r_;
-                if (i < nF) { const int vi = w.idx[i]; r_ = -(w.tmp[vi] + w.g[vi] + A.colT(vi, mul)); }
-                else { const int rr = w.grow[i - nF]; r_ = bnd[rr] - A.row(rr, w.xp); }
+                if (i < nF) {
+                    const int vi = w.idx[i];
+                    const double aty = A.colT(vi, mul);
+                    r_ = -(w.tmp[vi] + w.g[vi] + aty);
+                    v[1] = fmax(v[1], fabs(w.tmp[vi]) + fabs(w.g[vi]) + fabs(aty));
+                } else {
+                    const int rr = w.grow[i - nF];
+                    const double ax = A.row(rr, w.xp);
+                    r_ = bnd[rr] - ax;
+                    v[1] = fmax(v[1], fabs(bnd[rr]) + fabs(ax));
+                }
                 w.rhs[i] = r_;
                 v[0] = fmax(v[0], fabs(r_));
             }
-            block_reduce<1, 0>(v, w.red);
+            block_reduce<2, 0>(v, w.red);
             if (!(v[0] == v[0])) return 0;
-            if (k >= 2 && v[0] > 0.25 * prev) break;
+            // stop when the residual sits at its rounding level or has stopped contracting
+            if (k >= 1 && (v[0] <= 1e-13 * v[1] || (k >= 2 && v[0] > 0.25 * prev))) break;
             prev = v[0];
             sys.solve(w.rhs, w.xt, w.sc);
             for (int i = tid; i < nk; i += T) {

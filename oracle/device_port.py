@@ -87,10 +87,14 @@ def polish_verified(H, g, A, lo, hi, x, code, eps=1e-9, tol=1e-9, retries=8, max
         mul = np.zeros(m)
         prev = np.inf
         for k in range(max_refine):
-            rd = -(H @ xp + g + A.T @ mul)[F]
-            rp = (bnd - A @ xp)[rows]
+            Hx_, Aty_, Ax_ = H @ xp, A.T @ mul, A @ xp
+            rd = -(Hx_ + g + Aty_)[F]
+            rp = (bnd - Ax_)[rows]
             res = max(np.abs(rd).max(initial=0.0), np.abs(rp).max(initial=0.0))
-            if k >= 2 and res > 0.25 * prev:
+            mag = max((np.abs(Hx_) + np.abs(g) + np.abs(Aty_))[F].max(initial=0.0),
+                      (np.abs(bnd) + np.abs(Ax_))[rows].max(initial=0.0))
+            # stop when the residual sits at its rounding level or has stopped contracting
+            if k >= 1 and (res <= 1e-13 * mag or (k >= 2 and res > 0.25 * prev)):
                 break
             prev = res
             sol = sla.lu_solve(lu, np.concatenate((rd, rp)))

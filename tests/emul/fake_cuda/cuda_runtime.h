@@ -9,6 +9,7 @@
 #define __host__
 #define __global__
 #define __forceinline__ inline
+#define __noinline__
 #define __restrict__
 #define __launch_bounds__(x)
 struct hmpc_emul_dim { int x; };
