@@ -721,27 +721,28 @@ __device__ inline int polish_verified(const QpConst& c, Work& w, LinSys& sys, co
         for (int k = 0; k < 6; ++k) {
             sym_matvec(w.H, n, w.xp, w.tmp, &sys);
             __syncthreads();   // tmp is read through the compact index below (another thread's entry)
-            double v[2] = {0.0, 0.0};   // residual, magnitude of the terms it is the difference of
+            double v[2] = {0.0, 0.0};   // residual; largest residual relative to the terms it is the difference of
             for (int i = tid; i < nk; i += T) {
-                double r_;
+                double r_, mag;
                 if (i < nF) {
                     const int vi = w.idx[i];
                     const double aty = A.colT(vi, mul);
                     r_ = -(w.tmp[vi] + w.g[vi] + aty);
-                    v[1] = fmax(v[1], fabs(w.tmp[vi]) + fabs(w.g[vi]) + fabs(aty));
+                    mag = fabs(w.tmp[vi]) + fabs(w.g[vi]) + fabs(aty);
                 } else {
                     const int rr = w.grow[i - nF];
                     const double ax = A.row(rr, w.xp);
                     r_ = bnd[rr] - ax;
-                    v[1] = fmax(v[1], fabs(bnd[rr]) + fabs(ax));
+                    mag = fabs(bnd[rr]) + fabs(ax);
                 }
                 w.rhs[i] = r_;
                 v[0] = fmax(v[0], fabs(r_));
+                v[1] = fmax(v[1], fabs(r_) / (mag + 1e-300));
             }
             block_reduce<2, 0>(v, w.red);
             if (!(v[0] == v[0])) return 0;
-            // stop when the residual sits at its rounding level or has stopped contracting
-            if (k >= 1 && (v[0] <= 1e-13 * v[1] || (k >= 2 && v[0] > 0.25 * prev))) break;
+            // stop when every row's residual sits at its rounding level or the residual has stopped contracting
+            if (k >= 1 && (v[1] <= 1e-12 || (k >= 2 && v[0] > 0.25 * prev))) break;
             prev = v[0];
             sys.solve(w.rhs, w.xt, w.sc);
             for (int i = tid; i < nk; i += T) {

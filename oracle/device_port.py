@@ -91,10 +91,10 @@ def polish_verified(H, g, A, lo, hi, x, code, eps=1e-9, tol=1e-9, retries=8, max
             rd = -(Hx_ + g + Aty_)[F]
             rp = (bnd - Ax_)[rows]
             res = max(np.abs(rd).max(initial=0.0), np.abs(rp).max(initial=0.0))
-            mag = max((np.abs(Hx_) + np.abs(g) + np.abs(Aty_))[F].max(initial=0.0),
-                      (np.abs(bnd) + np.abs(Ax_))[rows].max(initial=0.0))
-            # stop when the residual sits at its rounding level or has stopped contracting
-            if k >= 1 and (res <= 1e-13 * mag or (k >= 2 and res > 0.25 * prev)):
+            rel = max((np.abs(rd) / ((np.abs(Hx_) + np.abs(g) + np.abs(Aty_))[F] + 1e-300)).max(initial=0.0),
+                      (np.abs(rp) / ((np.abs(bnd) + np.abs(Ax_))[rows] + 1e-300)).max(initial=0.0))
+            # stop when every row's residual sits at its rounding level or the residual has stopped contracting
+            if k >= 1 and (rel <= 1e-12 or (k >= 2 and res > 0.25 * prev)):
                 break
             prev = res
             sol = sla.lu_solve(lu, np.concatenate((rd, rp)))

@@ -313,3 +313,34 @@ def test_runner_and_cli_dropin():
     np.testing.assert_allclose(r.f_hist[0:200:20], U_log, rtol=0, atol=1e-7)
     r3 = cli.main(["2f", "--runtime", "100", "--horizon", "10"])       # README spelling
     assert r3.X_traj.shape == (101, 13)
+
+
+def test_sharded_run_equals_unsharded():
+    """Sharding by hopper: two shards -- on two GPUs when the box has them, else two handles on one
+    GPU -- reproduce the unsharded batch bit for bit (scenarios are keyed by the global hopper index)."""
+    from hopper_mpc_inertial_b200 import sharding
+    from hopper_mpc_inertial_b200.batch import BatchMpc
+    B, N, n_ticks = 301, 10, 6
+    full = scenarios.make_batch(B, N=N, n_ticks=n_ticks, seed=31)
+
+    def run(sc, device):
+        dev = f"cuda:{device}"
+        bm = BatchMpc(sc["X0"].shape[1], dyn="3f", N=N, device=device)
+        bm.set_gains(T(sc["Qdiag"], dev), T(sc["Rdiag"], dev))
+        X = T(sc["X0"], dev).clone()
+        with torch.cuda.device(device):
+            bm.use_current_stream()
+            out = bm.rollout(X, T(sc["xref_tab"], dev), T(sc["pf_tab"], dev), T(sc["C_tab"].view(np.int64), dev),
+                             T(sc["pf_switch"], dev), 0, n_ticks, True, log=True)
+            torch.cuda.synchronize(device)
+        return X.cpu().numpy(), out["U_log"].cpu().numpy()
+
+    X_full, U_full = run(full, 0)
+    ndev = torch.cuda.device_count()
+    parts = []
+    for r in range(2):
+        lo, hi = sharding.shard_range(B, r, 2)
+        sc = scenarios.make_batch(hi - lo, idx0=lo, N=N, n_ticks=n_ticks, seed=31)
+        parts.append(run(sc, r if ndev >= 2 else 0))
+    assert np.array_equal(np.concatenate([p[0] for p in parts], axis=-1), X_full)
+    assert np.array_equal(np.concatenate([p[1] for p in parts], axis=-1), U_full)
