@@ -150,13 +150,13 @@ __global__ void convert_kernel(int B, const double* __restrict__ X, double* __re
 // ------------------------------------------------------------------------------------------------
 // K1+K2: mpcontrol for a batch (mpc_cvx_euler_3f.py:41-69).  Persistent CTAs, one hopper at a time.
 // ------------------------------------------------------------------------------------------------
-template <int THREADS, int MIN_CTAS>
+template <int THREADS, int MIN_CTAS, bool SMEM_MATS>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
-mpc_kernel(QpConst c, int B, int mats_in_smem, int sm_count, double* __restrict__ ws, int* __restrict__ work_ctr, MpcIo io) {
+mpc_kernel(QpConst c, int B, int sm_count, double* __restrict__ ws, int* __restrict__ work_ctr, MpcIo io) {
     extern __shared__ double smem[];
     __shared__ int s_next;
     Work w;
-    setup_work(w, c, smem, ws, mats_in_smem != 0);
+    setup_work<SMEM_MATS>(w, c, smem, ws);
     const int N = c.N, n = 6 * N;
     AOp A{N, n, c.dyn == 3 ? 1 : 0, c.mu, w.stance, w.hinv};
     LinSys sys{n, 0, 0, w.Lm, w.dinv, w.H, w.idx, w.grow};
@@ -220,7 +220,7 @@ __global__ void condense_kernel(QpConst c, int B, int mats_in_smem, double* __re
                                 int32_t* __restrict__ infeasible) {
     extern __shared__ double smem[];
     Work w;
-    setup_work(w, c, smem, ws, mats_in_smem != 0);
+    if (mats_in_smem) setup_work<true>(w, c, smem, ws); else setup_work<false>(w, c, smem, ws);
     const int N = c.N, n = 6 * N, m = 11 * N, tid = threadIdx.x, T = blockDim.x;
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         __syncthreads();
@@ -409,8 +409,10 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
             return fail(HMPC_ERR_ALLOC, std::string("cudaMalloc workspace: ") + cudaGetErrorString(e));
         }
     }
-    if ((e = cudaFuncSetAttribute(hmpc::mpc_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mpc_smem)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(hmpc::mpc_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mpc_smem)) != cudaSuccess ||
+    if ((e = cudaFuncSetAttribute(hmpc::mpc_kernel<128, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mpc_smem)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(hmpc::mpc_kernel<128, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mpc_smem)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(hmpc::mpc_kernel<256, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mpc_smem)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(hmpc::mpc_kernel<256, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mpc_smem)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(hmpc::condense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mpc_smem)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(hmpc::linearize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vec_bytes)) != cudaSuccess) {
         hmpc_destroy(h);
@@ -505,10 +507,15 @@ namespace {
 // small horizons: 128 threads, registers capped so that four CTAs share an SM; large: 256 threads
 void launch_mpc(hmpc_handle* h, const hmpc::QpConst& qc, const hmpc::MpcIo& io) {
     cudaMemsetAsync(h->work_ctr, 0, sizeof(int), h->stream);
-    if (h->mpc_threads == 128)
-        hmpc::mpc_kernel<128, 4><<<h->mpc_grid, 128, h->mpc_smem, h->stream>>>(qc, h->cfg.batch, h->mats_in_smem ? 1 : 0, h->sm_count, h->ws, h->work_ctr, io);
+    const int B = h->cfg.batch;
+    if (h->mpc_threads == 128 && h->mats_in_smem)
+        hmpc::mpc_kernel<128, 4, true><<<h->mpc_grid, 128, h->mpc_smem, h->stream>>>(qc, B, h->sm_count, h->ws, h->work_ctr, io);
+    else if (h->mpc_threads == 128)
+        hmpc::mpc_kernel<128, 1, false><<<h->mpc_grid, 128, h->mpc_smem, h->stream>>>(qc, B, h->sm_count, h->ws, h->work_ctr, io);
+    else if (h->mats_in_smem)
+        hmpc::mpc_kernel<256, 1, true><<<h->mpc_grid, 256, h->mpc_smem, h->stream>>>(qc, B, h->sm_count, h->ws, h->work_ctr, io);
     else
-        hmpc::mpc_kernel<256, 1><<<h->mpc_grid, 256, h->mpc_smem, h->stream>>>(qc, h->cfg.batch, h->mats_in_smem ? 1 : 0, h->sm_count, h->ws, h->work_ctr, io);
+        hmpc::mpc_kernel<256, 1, false><<<h->mpc_grid, 256, h->mpc_smem, h->stream>>>(qc, B, h->sm_count, h->ws, h->work_ctr, io);
 }
 
 hmpc::MpcIo make_io(hmpc_handle* h, const double* x_in, const double* x_ref, const double* pf,

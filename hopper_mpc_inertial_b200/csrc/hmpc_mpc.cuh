@@ -10,11 +10,15 @@ namespace hmpc {
 // ------------------------------------------------------------------------------------------------
 // shared set-up of one hopper's Work: carve shared memory, point the matrices
 // ------------------------------------------------------------------------------------------------
-__device__ inline void setup_work(Work& w, const QpConst& c, double* smem, double* ws, bool mats_in_smem) {
+// SMEM_MATS is a compile-time switch so that, in the shared-memory configuration, every access to H and to
+// the factor is provably a shared-memory access (LDS/STS instead of generic loads).
+template <bool SMEM_MATS>
+__device__ inline void setup_work(Work& w, const QpConst& c, double* smem, double* ws) {
     carve(w, smem, c.N);
     const size_t n = 6 * (size_t)c.N;
-    double* mat = mats_in_smem ? smem + ((work_vec_doubles(c.N) + 1) & ~(size_t)1)
-                               : ws + (size_t)blockIdx.x * mat_doubles(c.N);
+    double* mat;
+    if (SMEM_MATS) mat = smem + ((work_vec_doubles(c.N) + 1) & ~(size_t)1);
+    else mat = ws + (size_t)blockIdx.x * mat_doubles(c.N);
     w.H = mat; w.Lm = mat + n * (n + 1) / 2;
 }
 

@@ -43,7 +43,7 @@ int emul_solve(const hmpc_config* cfg, const double* Qd, const double* Rd, const
     std::vector<double> smem(((work_vec_doubles(N) + 1) & ~(size_t)1) + mat_doubles(N) + 8);
     std::vector<int32_t> st_tick(B), ninf(B);
     Work w;
-    setup_work(w, c, smem.data(), nullptr, true);
+    setup_work<true>(w, c, smem.data(), nullptr);
     AOp A{N, n, c.dyn == 3 ? 1 : 0, c.mu, w.stance, w.hinv};
     LinSys sys{n, 0, 0, w.Lm, w.dinv, w.H, w.idx, w.grow};
     MpcIo io;
@@ -64,7 +64,7 @@ int emul_condense(const hmpc_config* cfg, const double* Qd, const double* Rd, co
     const int B = cfg->batch, N = cfg->N, n = 6 * N, m = 11 * N;
     std::vector<double> smem(((work_vec_doubles(N) + 1) & ~(size_t)1) + mat_doubles(N) + 8);
     Work w;
-    setup_work(w, c, smem.data(), nullptr, true);
+    setup_work<true>(w, c, smem.data(), nullptr);
     for (int b = 0; b < B; ++b) {
         load_hopper(c, w, b, B, x_in, pf, Cbits, Qd, Rd);
         for (int k = 0; k < N; ++k) {
