@@ -398,7 +398,7 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
     h->mats_in_smem = (vec_bytes + mat_bytes + 1024 <= smem_cap);
     h->mpc_smem = vec_bytes + (h->mats_in_smem ? mat_bytes : 0);
     if (h->mpc_smem > smem_cap) { hmpc_destroy(h); return fail(HMPC_ERR_UNSUPPORTED, "horizon too large for shared memory"); }
-    h->mpc_threads = (n <= 128) ? 128 : 256;
+    h->mpc_threads = (n <= 64) ? 128 : 256;   // one CTA per SM beyond N = 10: use the wider CTA
     int per_sm = 1;
     if (h->mats_in_smem) per_sm = std::max<int>(1, (int)((size_t)prop.sharedMemPerMultiprocessor / (h->mpc_smem + 1024)));
     else per_sm = std::max<int>(1, std::min<int>(8, (int)((size_t)prop.sharedMemPerMultiprocessor / (h->mpc_smem + 1024))));
