@@ -19,6 +19,7 @@ PATH_NONE, PATH_WARM, PATH_IPM_POLISH, PATH_IPM, PATH_ADMM = 0, 1, 2, 3, 4
 SOLVER = {"exact": 0, "admm": 1}
 MODE = {"early_exit": 0, "fixed_iter": 1}
 ON_INFEASIBLE = {"hold": 0, "respawn": 1}
+PRECISION = {"fp64": 0, "fp32": 1}
 
 # every symbol include/hmpc.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = [

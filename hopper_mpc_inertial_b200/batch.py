@@ -54,6 +54,8 @@ class BatchMpc:
                 v = _lib.MODE[v]
             if k == "on_infeasible" and isinstance(v, str):
                 v = _lib.ON_INFEASIBLE[v]
+            if k == "precision" and isinstance(v, str):
+                v = _lib.PRECISION[v]
             cur = getattr(cfg, k)
             if hasattr(cur, "__len__"):
                 arr = np.asarray(v, dtype=float).reshape(-1)

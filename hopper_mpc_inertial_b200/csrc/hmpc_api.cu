@@ -150,16 +150,18 @@ __global__ void convert_kernel(int B, const double* __restrict__ X, double* __re
 // ------------------------------------------------------------------------------------------------
 // K1+K2: mpcontrol for a batch (mpc_cvx_euler_3f.py:41-69).  Persistent CTAs, one hopper at a time.
 // ------------------------------------------------------------------------------------------------
-template <int THREADS, int MIN_CTAS, bool SMEM_MATS>
+// F: precision of the factorisation and of the substitutions (double, or float = mixed precision: QP data,
+// iterates and residuals stay FP64 and the refinement loops recover FP64-level accuracy)
+template <int THREADS, int MIN_CTAS, bool SMEM_MATS, typename F>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 mpc_kernel(QpConst c, int B, int sm_count, double* __restrict__ ws, int* __restrict__ work_ctr, MpcIo io) {
     extern __shared__ double smem[];
     __shared__ int s_next;
     Work w;
-    setup_work<SMEM_MATS>(w, c, smem, ws);
+    setup_work<SMEM_MATS>(w, c, smem, ws, (int)sizeof(F));
     const int N = c.N, n = 6 * N;
     AOp A{N, n, c.dyn == 3 ? 1 : 0, c.mu, w.stance, w.hinv};
-    LinSys sys{n, 0, 0, w.Lm, w.dinv, w.H, w.idx, w.grow};
+    LinSys<F> sys{n, 0, 0, reinterpret_cast<F*>(w.Lm), reinterpret_cast<F*>(w.dinv), w.H, w.idx, w.grow};
     // CTAs are dealt to the SMs round-robin, so the CTAs sharing an SM differ in blockIdx.x / #SMs
     sys.solver_warp = blockIdx.x / sm_count;
     // dynamic distribution of hoppers over the persistent CTAs (solve times differ: warm active-set path
@@ -277,6 +279,14 @@ hmpc::QpConst make_qp_const(const hmpc_config& cfg) {
     c.eps_abs = cfg.eps_abs; c.eps_rel = cfg.eps_rel; c.rho0 = cfg.rho0; c.sigma = cfg.sigma;
     c.alpha = cfg.alpha; c.kkt_eps = cfg.kkt_eps; c.polish_tol = cfg.polish_tol; c.ipm_tol = cfg.ipm_tol;
     c.condense_flops = hmpc::flops_condense(cfg.N);
+    c.max_refine = 6;
+    c.stagnation = 0.25;
+    if (cfg.precision == HMPC_FP32) {   // FP32 factor: more refinement sweeps, regularisation / IPM tolerance at FP32 scale
+        c.max_refine = 14;
+        c.stagnation = 0.7;
+        c.kkt_eps = std::max(cfg.kkt_eps, 1e-3);
+        c.ipm_tol = std::max(cfg.ipm_tol, 1e-6);
+    }
     return c;
 }
 
@@ -330,7 +340,7 @@ int hmpc_default_config(hmpc_config* cfg) {
     cfg->tau_max[0] = 7.78; cfg->tau_max[1] = 7.78; cfg->tau_max[2] = 4.0;
     cfg->fz_max = 206.0; cfg->z_min = 0.1; cfg->kf = 100.0;
     cfg->eps_abs = 1e-5; cfg->eps_rel = 1e-5; cfg->rho0 = 0.1; cfg->sigma = 1e-6; cfg->alpha = 1.6;
-    cfg->kkt_eps = 1e-9; cfg->polish_tol = 1e-9; cfg->ipm_tol = 1e-9;
+    cfg->kkt_eps = 1e-9; cfg->polish_tol = 1e-9; cfg->ipm_tol = 1e-6;
     return HMPC_OK;
 }
 
@@ -341,7 +351,7 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
     if (cfg->batch < 1) return fail(HMPC_ERR_BAD_ARG, "batch must be >= 1");
     if (cfg->N < 2 || cfg->N > HMPC_MAX_N) return fail(HMPC_ERR_BAD_ARG, "N must be in [2, 64]");
     if (cfg->dyn != HMPC_DYN_2F && cfg->dyn != HMPC_DYN_3F) return fail(HMPC_ERR_BAD_ARG, "dyn must be 2 or 3");
-    if (cfg->precision != HMPC_FP64) return fail(HMPC_ERR_UNSUPPORTED, "only FP64 precision is implemented");
+    if (cfg->precision != HMPC_FP64 && cfg->precision != HMPC_FP32) return fail(HMPC_ERR_BAD_ARG, "precision must be HMPC_FP64 or HMPC_FP32");
     if (cfg->mpc_factor < 1 || cfg->mpc_factor > 255) return fail(HMPC_ERR_BAD_ARG, "mpc_factor must be in [1,255]");
     if (cfg->max_iter < 1 || cfg->check_interval < 1 || cfg->first_check < 1 || cfg->polish_retries < 0 ||
         cfg->ipm_max_iter < 1)
@@ -393,7 +403,8 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
     }
     // solver geometry
     const size_t vec_bytes = ((hmpc::work_vec_doubles((int)N) + 1) & ~(size_t)1) * 8;
-    const size_t mat_bytes = hmpc::mat_doubles((int)N) * 8;
+    const int fsize = cfg->precision == HMPC_FP32 ? 4 : 8;
+    const size_t mat_bytes = hmpc::mat_doubles((int)N, fsize) * 8;
     const size_t smem_cap = (size_t)prop.sharedMemPerBlockOptin;
     h->mats_in_smem = (vec_bytes + mat_bytes + 1024 <= smem_cap);
     h->mpc_smem = vec_bytes + (h->mats_in_smem ? mat_bytes : 0);
@@ -409,10 +420,16 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
             return fail(HMPC_ERR_ALLOC, std::string("cudaMalloc workspace: ") + cudaGetErrorString(e));
         }
     }
-    if ((e = cudaFuncSetAttribute(hmpc::mpc_kernel<128, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mpc_smem)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(hmpc::mpc_kernel<128, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mpc_smem)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(hmpc::mpc_kernel<256, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mpc_smem)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(hmpc::mpc_kernel<256, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mpc_smem)) != cudaSuccess ||
+    const int smem_i = (int)h->mpc_smem;
+    const cudaFuncAttribute dyn_attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    if ((e = cudaFuncSetAttribute(hmpc::mpc_kernel<128, 4, true, double>, dyn_attr, smem_i)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(hmpc::mpc_kernel<128, 1, false, double>, dyn_attr, smem_i)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(hmpc::mpc_kernel<256, 1, true, double>, dyn_attr, smem_i)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(hmpc::mpc_kernel<256, 1, false, double>, dyn_attr, smem_i)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(hmpc::mpc_kernel<128, 5, true, float>, dyn_attr, smem_i)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(hmpc::mpc_kernel<128, 1, false, float>, dyn_attr, smem_i)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(hmpc::mpc_kernel<256, 1, true, float>, dyn_attr, smem_i)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(hmpc::mpc_kernel<256, 1, false, float>, dyn_attr, smem_i)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(hmpc::condense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mpc_smem)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(hmpc::linearize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vec_bytes)) != cudaSuccess) {
         hmpc_destroy(h);
@@ -508,14 +525,14 @@ namespace {
 void launch_mpc(hmpc_handle* h, const hmpc::QpConst& qc, const hmpc::MpcIo& io) {
     cudaMemsetAsync(h->work_ctr, 0, sizeof(int), h->stream);
     const int B = h->cfg.batch;
-    if (h->mpc_threads == 128 && h->mats_in_smem)
-        hmpc::mpc_kernel<128, 4, true><<<h->mpc_grid, 128, h->mpc_smem, h->stream>>>(qc, B, h->sm_count, h->ws, h->work_ctr, io);
-    else if (h->mpc_threads == 128)
-        hmpc::mpc_kernel<128, 1, false><<<h->mpc_grid, 128, h->mpc_smem, h->stream>>>(qc, B, h->sm_count, h->ws, h->work_ctr, io);
-    else if (h->mats_in_smem)
-        hmpc::mpc_kernel<256, 1, true><<<h->mpc_grid, 256, h->mpc_smem, h->stream>>>(qc, B, h->sm_count, h->ws, h->work_ctr, io);
-    else
-        hmpc::mpc_kernel<256, 1, false><<<h->mpc_grid, 256, h->mpc_smem, h->stream>>>(qc, B, h->sm_count, h->ws, h->work_ctr, io);
+    const bool f32 = h->cfg.precision == HMPC_FP32;
+#define HMPC_LAUNCH(TH, MINB, SM, FT) \
+    hmpc::mpc_kernel<TH, MINB, SM, FT><<<h->mpc_grid, TH, h->mpc_smem, h->stream>>>(qc, B, h->sm_count, h->ws, h->work_ctr, io)
+    if (h->mpc_threads == 128 && h->mats_in_smem) { if (f32) HMPC_LAUNCH(128, 5, true, float); else HMPC_LAUNCH(128, 4, true, double); }
+    else if (h->mpc_threads == 128) { if (f32) HMPC_LAUNCH(128, 1, false, float); else HMPC_LAUNCH(128, 1, false, double); }
+    else if (h->mats_in_smem) { if (f32) HMPC_LAUNCH(256, 1, true, float); else HMPC_LAUNCH(256, 1, true, double); }
+    else { if (f32) HMPC_LAUNCH(256, 1, false, float); else HMPC_LAUNCH(256, 1, false, double); }
+#undef HMPC_LAUNCH
 }
 
 hmpc::MpcIo make_io(hmpc_handle* h, const double* x_in, const double* x_ref, const double* pf,

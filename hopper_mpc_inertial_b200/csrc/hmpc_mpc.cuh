@@ -13,12 +13,12 @@ namespace hmpc {
 // SMEM_MATS is a compile-time switch so that, in the shared-memory configuration, every access to H and to
 // the factor is provably a shared-memory access (LDS/STS instead of generic loads).
 template <bool SMEM_MATS>
-__device__ inline void setup_work(Work& w, const QpConst& c, double* smem, double* ws) {
+__device__ inline void setup_work(Work& w, const QpConst& c, double* smem, double* ws, int fsize = 8) {
     carve(w, smem, c.N);
     const size_t n = 6 * (size_t)c.N;
     double* mat;
     if (SMEM_MATS) mat = smem + ((work_vec_doubles(c.N) + 1) & ~(size_t)1);
-    else mat = ws + (size_t)blockIdx.x * mat_doubles(c.N);
+    else mat = ws + (size_t)blockIdx.x * mat_doubles(c.N, fsize);
     w.H = mat; w.Lm = mat + n * (n + 1) / 2;
 }
 
@@ -85,7 +85,8 @@ struct MpcIo {
 };
 
 // One hopper b of a batch of B.  All threads of the CTA call this together.
-__device__ inline void mpc_hopper(const QpConst& c, Work& w, LinSys& sys, const AOp& A, int b, int B, const MpcIo& io) {
+template <class Sys>
+__device__ inline void mpc_hopper(const QpConst& c, Work& w, Sys& sys, const AOp& A, int b, int B, const MpcIo& io) {
     const int N = c.N, n = 6 * N, m = 11 * N, tid = threadIdx.x, T = blockDim.x;
     double* xs = w.err;   // reused after condense: solution trajectory [(N+1)][12]
     __syncthreads();
@@ -114,8 +115,8 @@ __device__ inline void mpc_hopper(const QpConst& c, Work& w, LinSys& sys, const 
                 gp[2] = io.Xsol[(o + 2) * B + b]; gp[3] = io.Xsol[(o + 5) * B + b];
             }
         }
-        // the footstep window shares storage with solver scratch (carve()): reload it after a solve
-        if (pass > 0) for (int i = tid; i < 3 * N; i += T) w.pfw[i] = io.pf[(size_t)i * B + b];
+        // the footstep window and the gains share storage with solver scratch (carve()): reload after a solve
+        if (pass > 0) load_hopper(c, w, b, B, io.x_in, io.pf, io.Cbits, io.Qd, io.Rd);
         __syncthreads();
         const int infeasible = condense(c, w, io.x_ref + b, (size_t)B);
         sys.flops += c.condense_flops;

@@ -41,12 +41,13 @@ enum { PATH_NONE = 0, PATH_WARM = 1, PATH_IPM_POLISH = 2, PATH_IPM = 3, PATH_ADM
 
 struct QpConst {
     int N, dyn, uref_mode, solver, mode, max_iter, check, first_check, retries, adaptive_rho, warm_start;
-    int ipm_max_iter, polish;
+    int ipm_max_iter, polish, max_refine;
     double dt, m, g, mu;
     double Jinv[9], rh[3], tau_max[3];
     double fz_max, z_min, kf;
     double eps_abs, eps_rel, rho0, sigma, alpha, kkt_eps, polish_tol, ipm_tol;
     double condense_flops;   // flops_condense(N), precomputed on the host
+    double stagnation;       // refinement stops when the residual shrinks by less than this factor
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -71,7 +72,7 @@ struct Work {
     double *x, *tmp, *xp;                          // [n] each
     double *xt, *rhs, *sc, *dinv;                  // [kkt_max] each (compact systems: variables + active rows)
     double *mv[kNumMVec];                          // [m] each (roles differ per solver)
-    double *red;                                   // [64] reduction scratch
+    double *red;                                   // [48] reduction scratch
     int *idx;                          // [n]  compact list of the variables in the current system
     int *grow;                         // [kkt_max] polish: active general rows in the current system
     int *cnt;                          // [4]  nF, ng, ...
@@ -81,7 +82,8 @@ struct Work {
     int8_t *side;                      // [m]  IPM: bit0 finite upper side, bit1 finite lower side
     int8_t *stance;                    // [N]
     // matrices (shared or global), packed lower triangles: H of order n, the LDL' factor of order <= 8N
-    double *H, *Lm;
+    double* H;
+    void* Lm;
 };
 
 // The polish system holds the unpinned variables plus the active friction / height rows: up to 7N+2
@@ -90,19 +92,20 @@ __host__ __device__ inline int kkt_max(int N) { return 7 * N + 2; }
 // Symmetric / triangular matrices are stored packed, column by column (lower triangle): element (i, j),
 // i >= j, of an order-k matrix sits at tri_off(j, k) + (i - j).
 __host__ __device__ inline int tri_off(int j, int k) { return j * k - (j * (j - 1)) / 2; }
-__host__ __device__ inline size_t mat_doubles(int N) {
+// fsize: bytes per factor entry (8: FP64 factor, 4: FP32 factor)
+__host__ __device__ inline size_t mat_doubles(int N, int fsize = 8) {
     const size_t n = 6 * (size_t)N, kk = (size_t)kkt_max(N);
-    return n * (n + 1) / 2 + kk * (kk + 1) / 2;
+    return n * (n + 1) / 2 + (kk * (kk + 1) / 2 * (size_t)fsize + 7) / 8;
 }
 __host__ __device__ inline size_t work_vec_doubles(int N) {
     const int n = 6 * N, m = 11 * N;
     size_t d = 0;
-    // linearisation (cfree, gp, pfw alias the last two m-vectors: they are dead once condense() returns)
-    d += 2 * N + 2 * (N + 1) + 9 * N + 18 * N + 12 + 12 * (N + 1) + 12 + 6 + N;
+    // linearisation (cfree, gp, pfw, Qd, Rd, PC, PS alias the last three m-vectors: dead once condense() returns)
+    d += 2 * N + 9 * N + 18 * N + 12 + 12 * (N + 1) + N;
     d += n + 2 * m;           // g lo hi
-    d += 3 * n + N + 4 * kkt_max(N);   // x xp tmp(+N) | xt rhs sc dinv
+    d += 3 * n + (N > 14 ? N - 14 : 0) + 4 * kkt_max(N);   // x xp tmp(+pad) | xt rhs sc dinv
     d += kNumMVec * m;
-    d += 64;                  // red
+    d += 48;                  // red
     d += (n + kkt_max(N) + 4 + 1) / 2;          // int32: idx grow cnt
     d += (2 * n + 2 * m + N + 7) / 8;           // int8: fixed pin code side stance
     return d;
@@ -112,18 +115,19 @@ __device__ inline void carve(Work& w, double* base, int N) {
     const int n = 6 * N, m = 11 * N, kk = kkt_max(N);
     double* p = base;
     auto take = [&](size_t k) { double* r = p; p += k; return r; };
-    w.cz = take(N); w.sz = take(N); w.PC = take(N + 1); w.PS = take(N + 1);
+    w.cz = take(N); w.sz = take(N);
     w.Bv = take(9 * N); w.Bw = take(18 * N); w.xin = take(12);
-    w.err = take(12 * (N + 1)); w.Qd = take(12); w.Rd = take(6);
+    w.err = take(12 * (N + 1));
     w.hinv = take(N);
     w.g = take(n); w.lo = take(m); w.hi = take(m);
     // tmp | xt | rhs | sc are contiguous: together they are the 4-column panel scratch of LinSys::factor
-    w.x = take(n); w.xp = take(n); w.tmp = take(n + N);
+    w.x = take(n); w.xp = take(n); w.tmp = take(n + (N > 14 ? N - 14 : 0));   // pad: 4 (kkt_max - 4) panel entries
     w.xt = take(kk); w.rhs = take(kk); w.sc = take(kk); w.dinv = take(kk);
     for (int i = 0; i < kNumMVec; ++i) w.mv[i] = take(m);
-    // condense-only scratch on top of the solvers' last two m-vectors: 12(N+1) + 4N + 3N <= 2 * 11N
-    w.cfree = w.mv[kNumMVec - 2]; w.gp = w.cfree + 12 * (N + 1); w.pfw = w.gp + 4 * N;
-    w.red = take(64);
+    // condense-only scratch on top of the solvers' last three m-vectors: 12(N+1) + 4N + 3N + 18 + 2(N+1) <= 33N
+    w.cfree = w.mv[kNumMVec - 3]; w.gp = w.cfree + 12 * (N + 1); w.pfw = w.gp + 4 * N;
+    w.Qd = w.pfw + 3 * N; w.Rd = w.Qd + 12; w.PC = w.Rd + 6; w.PS = w.PC + (N + 1);
+    w.red = take(48);
     w.idx = reinterpret_cast<int*>(p);
     w.grow = w.idx + n;
     w.cnt = w.grow + kk;
@@ -509,7 +513,10 @@ __device__ inline void compact_indices(int first, int len, int cap, int* list, i
 // nk = nF + ng:
 //   variables  idx[0..nF)   full variable indices kept in the system
 //   rows       grow[0..ng)  active general rows (polish only); they follow the variables
-//   K_vv = H[idx_i][idx_j] + (wts ? (A' diag(wts) A)_ij : 0) + dadd [i==j];  K_rv = A.coef;  K_rr = -eps I
+//   K_vv = H[idx_i][idx_j] + (wts ? (A' diag(wts) A)_ij : 0) + dadd [i==j];  K_rv = A.coef;
+//   K_rr = 0; after the variables are eliminated the row block holds the Schur complement -G K_vv^-1 G',
+//   whose diagonal is then scaled by (1 + eps): a relative regularisation that keeps exactly dependent rows
+//   at a negative pivot well above the factor's rounding level and is removed again by the refinement
 // With ng = 0 this is the positive definite IPM / ADMM operator (all pivots > 0); with ng > 0 the matrix
 // is quasi-definite: the LDL' exists for every ordering and the last ng pivots are negative.
 //
@@ -521,9 +528,11 @@ __device__ inline void compact_indices(int first, int len, int cap, int* list, i
 // U is stored packed (lower triangle, column by column): the forward sweep reads contiguous columns, the
 // backward sweep reads a row with the slowly varying stride nk - i.
 // ------------------------------------------------------------------------------------------------
+template <typename F>
 struct LinSys {
+    typedef F real;
     int n, nF, ng;
-    double *Lm, *dinv;
+    F *Lm, *dinv;
     const double* H;
     const int *idx, *grow;
     double flops = 0.0;   // algorithmic FLOPs of factor/solve since the last reset (same value in all threads)
@@ -538,38 +547,53 @@ struct LinSys {
             return s;
         }
         if (j < nF) return A.coef(grow[i - nF], idx[j]);
-        return (i == j) ? -eps : 0.0;
+        if (i != j) return 0.0;
+        // the row block starts at zero: its regularisation is applied relative to the Schur complement once
+        // the variables have been eliminated (factor()).  A row without any unpinned variable is decoupled.
+        const int r = grow[i - nF];
+        for (int q = 0; q < nF; ++q) if (A.coef(r, idx[q]) != 0.0) return 0.0;
+        return -1.0;
     }
 
     // Returns nonzero (same value in all threads) when a pivot has the wrong sign or is not finite.
     // P: scratch of at least 4 (nk - 4) doubles (the pre-scaled panel, see below).
-    __device__ inline int factor(const AOp& A, const double* wts, double dadd, double eps, double* P) {
+    __device__ inline int factor(const AOp& A, const double* wts, double dadd, double eps, double* scratch) {
+        F* P = reinterpret_cast<F*>(scratch);
         const int tid = threadIdx.x, T = blockDim.x, nk = nF + ng;
         const int LS = T < 32 ? T : 32, lane = tid % LS, wid = tid / LS, nw = T / LS;
         flops += flops_factor(nk);
-        // ---- assemble the lower triangle (packed, column by column) ----
+        // ---- assemble the lower triangle (packed, column by column); entries are formed in FP64 ----
         for (int e = tid; e < nk * nk; e += T) {
             const int jj = e / nk, ii = e - jj * nk;
-            if (ii >= jj) Lm[tri_off(jj, nk) + (ii - jj)] = entry(A, wts, dadd, eps, ii, jj);
+            if (ii >= jj) Lm[tri_off(jj, nk) + (ii - jj)] = (F)entry(A, wts, dadd, eps, ii, jj);
         }
         __syncthreads();
         int bad = 0;
         // ---- blocked right-looking elimination, 4 pivot columns per block ----
-        for (int j0 = 0; j0 < nk; j0 += 4) {
-            const int bs = (nk - j0) < 4 ? (nk - j0) : 4, t0 = j0 + bs;
+        for (int j0 = 0; j0 < nk;) {
+            // blocks never straddle the variable / row boundary nF
+            const int lim = (j0 < nF ? nF : nk) - j0;
+            const int bs = lim < 4 ? lim : 4, t0 = j0 + bs;
+            if (j0 == nF && ng > 0) {
+                for (int r = tid; r < ng; r += T) Lm[tri_off(nF + r, nk)] *= (F)(1.0 + eps);
+                __syncthreads();
+            }
             // panel: eliminate column j inside the panel only; keep P[i - t0][p] = U(i, j) / d_j for the rows below
             for (int p = 0; p < bs; ++p) {
                 const int j = j0 + p;
-                const double* colj = Lm + tri_off(j, nk) - j;      // colj[i] = U(i, j), i >= j
-                const double piv = colj[j];
-                const double ap = (j < nF) ? piv : -piv;
-                const bool ok = (ap > 0.0) && (ap < 1e300);
+                const F* colj = Lm + tri_off(j, nk) - j;      // colj[i] = U(i, j), i >= j
+                const F piv = colj[j];
+                const F ap = (j < nF) ? piv : -piv;
+                const bool ok = (ap > (F)0) && (ap < (F)1e30);
                 if (!ok) bad = 1;
-                const double rinv = 1.0 / (ok ? piv : 1.0);
+                const F rinv = (F)1 / (ok ? piv : (F)1);
                 if (tid == 0) dinv[j] = rinv;
                 for (int i = j + 1 + tid; i < nk; i += T) {
-                    const double uij = colj[i];
-                    if (i >= t0) P[4 * (i - t0) + p] = uij * rinv;
+                    const F uij = colj[i];
+                    if (i >= t0) {
+                        P[4 * (i - t0) + p] = uij * rinv;
+                        if (p == bs - 1) for (int pp = bs; pp < 4; ++pp) P[4 * (i - t0) + pp] = (F)0;   // short block
+                    }
                     for (int k = j + 1; k < t0 && k <= i; ++k)
                         Lm[tri_off(k, nk) + (i - k)] -= uij * (colj[k] * rinv);
                 }
@@ -578,20 +602,20 @@ struct LinSys {
             // trailing matrix: rank-4 update.  Lanes own row pairs (short row t0+q, long row nk-1-q: equal
             // work per lane, consecutive addresses across lanes), warps own the columns k = t0 + wid (mod nw).
             const int t = nk - t0;
-            if (t > 0) {       // bs == 4 here
-                const double* c0 = Lm + tri_off(j0, nk) - j0;
-                const double* c1 = Lm + tri_off(j0 + 1, nk) - (j0 + 1);
-                const double* c2 = Lm + tri_off(j0 + 2, nk) - (j0 + 2);
-                const double* c3 = Lm + tri_off(j0 + 3, nk) - (j0 + 3);
+            if (t > 0) {
+                const F* c0 = Lm + tri_off(j0, nk) - j0;
+                const F* c1 = bs > 1 ? Lm + tri_off(j0 + 1, nk) - (j0 + 1) : c0;     // short block: the unused
+                const F* c2 = bs > 2 ? Lm + tri_off(j0 + 2, nk) - (j0 + 2) : c0;     // columns alias c0 and meet
+                const F* c3 = bs > 3 ? Lm + tri_off(j0 + 3, nk) - (j0 + 3) : c0;     // zeros in P
                 const int npairs = (t + 1) >> 1;
                 for (int q = lane; q < npairs; q += LS) {
                     for (int side = 0; side < 2; ++side) {
                         const int r = side ? (nk - 1 - q) : (t0 + q);
                         if (side && r == t0 + q) break;
-                        const double a0 = c0[r], a1 = c1[r], a2 = c2[r], a3 = c3[r];
+                        const F a0 = c0[r], a1 = c1[r], a2 = c2[r], a3 = c3[r];
                         int k = t0 + wid;
                         int off = tri_off(k, nk) - k;                 // column k starts at Lm + off + k
-                        const double* pk = P + 4 * (k - t0);
+                        const F* pk = P + 4 * (k - t0);
                         for (; k <= r; k += nw) {
                             Lm[off + r] -= a0 * pk[0] + a1 * pk[1] + a2 * pk[2] + a3 * pk[3];
                             off += nw * (nk - 1 - k) - (nw * (nw - 1)) / 2;
@@ -601,13 +625,15 @@ struct LinSys {
                 }
                 __syncthreads();
             }
+            j0 = t0;
         }
         return bad;
     }
 
-    // Solves K out = b for compact vectors of length nk.  b is destroyed, sc is scratch; out may alias b.
-    // Ends with a __syncthreads().
-    __device__ inline void solve(double* b, double* out, double* sc) {
+    // Solves K out = b for compact FP64 vectors of length nk; the substitutions run in the factor's precision
+    // on a private copy (scratch, nk entries).  b is left untouched, out may alias b.  Ends with a __syncthreads().
+    __device__ inline void solve(const double* b, double* out, double* scratch) {
+        F* sc = reinterpret_cast<F*>(scratch);
         const int tid = threadIdx.x, T = blockDim.x, nk = nF + ng;
         const int LS = T < 32 ? T : 32;
         flops += flops_solve(nk);
@@ -617,23 +643,25 @@ struct LinSys {
         const int w0 = (T / LS > 1) ? (solver_warp % (T / LS)) * LS : 0;
         if (tid >= w0 && tid < w0 + LS) {
             const int lane = tid - w0;
+            for (int i = lane; i < nk; i += LS) sc[i] = (F)b[i];
+            __syncwarp();
             for (int j = 0; j < nk; ++j) {            // L' y = b, z = D^-1 y
-                const double t = b[j] * dinv[j];
-                const double* col = Lm + tri_off(j, nk) - j;
-                for (int i = j + 1 + lane; i < nk; i += LS) b[i] -= col[i] * t;
-                if (lane == 0) sc[j] = t;
+                const F t = sc[j] * dinv[j];
+                const F* col = Lm + tri_off(j, nk) - j;
+                for (int i = j + 1 + lane; i < nk; i += LS) sc[i] -= col[i] * t;
                 __syncwarp();
+                if (lane == 0) sc[j] = t;
             }
+            __syncwarp();
             for (int j = nk - 1; j >= 0; --j) {       // L'^T x = z
-                const double xj = sc[j];
+                const F xj = sc[j];
                 for (int i = lane; i < j; i += LS) sc[i] -= Lm[tri_off(i, nk) + (j - i)] * dinv[i] * xj;
-                if (lane == 0) out[j] = xj;
+                if (lane == 0) out[j] = (double)xj;
                 __syncwarp();
             }
         }
         __syncthreads();
     }
-
 };
 
 // out = H x for the symmetric H of order n (packed lower triangle); every row is split into two halves
@@ -652,7 +680,8 @@ __device__ __forceinline__ double sym_row_dot(const double* H, int n, int i, int
     for (int j = (j0 > i + 1 ? j0 : i + 1); j < j1; ++j) acc += row[j] * x[j];
     return acc;
 }
-__device__ inline void sym_matvec(const double* H, int n, const double* x, double* out, LinSys* acct = nullptr) {
+template <class Sys>
+__device__ inline void sym_matvec(const double* H, int n, const double* x, double* out, Sys* acct) {
     if (acct) acct->flops += flops_matvec(n);
     const int tid = threadIdx.x, T = blockDim.x;
     if (T >= 2 * n) {
@@ -684,7 +713,8 @@ struct SolveInfo { int status, iters, nfac, path; double rho; };
 // repeated, at most c.retries times.
 // On success: w.x <- solution, w.mv[0] <- multipliers, w.code <- active set; returns 1 (all threads).
 // ------------------------------------------------------------------------------------------------
-__device__ inline int polish_verified(const QpConst& c, Work& w, LinSys& sys, const AOp& A, SolveInfo& info) {
+template <class Sys>
+__device__ inline int polish_verified(const QpConst& c, Work& w, Sys& sys, const AOp& A, SolveInfo& info) {
     const int N = c.N, n = 6 * N, m = 11 * N, tid = threadIdx.x, T = blockDim.x;
     const double tol = c.polish_tol;
     double* mul = w.mv[0];
@@ -718,7 +748,8 @@ __device__ inline int polish_verified(const QpConst& c, Work& w, LinSys& sys, co
         ++info.nfac;
         if (sys.factor(A, nullptr, 0.0, c.kkt_eps, w.tmp)) return 0;
         double prev = 1e300;
-        for (int k = 0; k < 6; ++k) {
+        bool hx_current = false;     // w.tmp == H xp for the final xp (the loop left right after a residual)
+        for (int k = 0; k < c.max_refine; ++k) {
             sym_matvec(w.H, n, w.xp, w.tmp, &sys);
             __syncthreads();   // tmp is read through the compact index below (another thread's entry)
             double v[2] = {0.0, 0.0};   // residual; largest residual relative to the terms it is the difference of
@@ -742,7 +773,7 @@ __device__ inline int polish_verified(const QpConst& c, Work& w, LinSys& sys, co
             block_reduce<2, 0>(v, w.red);
             if (!(v[0] == v[0])) return 0;
             // stop when every row's residual sits at its rounding level or the residual has stopped contracting
-            if (k >= 1 && (v[1] <= 1e-12 || (k >= 2 && v[0] > 0.25 * prev))) break;
+            if (k >= 1 && (v[1] <= 1e-12 || (k >= 2 && v[0] > c.stagnation * prev))) { hx_current = true; break; }
             prev = v[0];
             sys.solve(w.rhs, w.xt, w.sc);
             for (int i = tid; i < nk; i += T) {
@@ -752,8 +783,10 @@ __device__ inline int polish_verified(const QpConst& c, Work& w, LinSys& sys, co
             __syncthreads();
         }
         // ---- pass 1: multipliers of pinned variables, scales ----
-        sym_matvec(w.H, n, w.xp, w.tmp, &sys);
-        __syncthreads();
+        if (!hx_current) {
+            sym_matvec(w.H, n, w.xp, w.tmp, &sys);
+            __syncthreads();
+        }
         double v[3] = {0, 0, 0};   // stat, scale, |mult|
         for (int i = tid; i < n; i += T) {
             const double aty = A.colT(i, mul);   // mul[i] == 0 on box rows at this point
@@ -806,7 +839,8 @@ __device__ inline int polish_verified(const QpConst& c, Work& w, LinSys& sys, co
 // Start: one Newton step of the quadratic penalty towards the row mid-points.
 // On exit w.x = iterate, w.code = active-set estimate (lambda > slack).  Returns 1 when converged.
 // ------------------------------------------------------------------------------------------------
-__device__ inline int ipm_solve(const QpConst& c, Work& w, LinSys& sys, const AOp& A, SolveInfo& info) {
+template <class Sys>
+__device__ inline int ipm_solve(const QpConst& c, Work& w, Sys& sys, const AOp& A, SolveInfo& info) {
     const int N = c.N, n = 6 * N, m = 11 * N, tid = threadIdx.x, T = blockDim.x;
     double *su = w.mv[0], *sl = w.mv[1], *lu = w.mv[2], *ll = w.mv[3], *rpu = w.mv[4], *rpl = w.mv[5];
     double *pu = w.mv[6], *pl = w.mv[7], *tv = w.mv[8], *adx = w.mv[9], *wts = w.mv[10];
@@ -1002,7 +1036,8 @@ __device__ inline int ipm_solve(const QpConst& c, Work& w, LinSys& sys, const AO
 // On entry (warm != 0): w.xp = time-shifted previous solution, w.code = time-shifted previous active set.
 // On exit: w.x = solution, w.code = active set (for the next tick's warm start).
 // ------------------------------------------------------------------------------------------------
-__device__ inline SolveInfo solve_exact(const QpConst& c, Work& w, LinSys& sys, const AOp& A, int warm) {
+template <class Sys>
+__device__ inline SolveInfo solve_exact(const QpConst& c, Work& w, Sys& sys, const AOp& A, int warm) {
     const int n = 6 * c.N, tid = threadIdx.x, T = blockDim.x;
     SolveInfo info{ST_MAX_ITER, 0, 0, PATH_NONE, 0.0};
     if (warm) {
@@ -1039,7 +1074,8 @@ __device__ inline SolveInfo solve_exact(const QpConst& c, Work& w, LinSys& sys, 
 // On entry w.x / w.mv[2] hold the warm start (x, y) or zeros.  On exit w.x, w.mv[2] = (x, y) and
 // w.code = OSQP's polish guess of the active set.
 // ------------------------------------------------------------------------------------------------
-__device__ inline SolveInfo admm_solve(const QpConst& c, Work& w, LinSys& sys, const AOp& A) {
+template <class Sys>
+__device__ inline SolveInfo admm_solve(const QpConst& c, Work& w, Sys& sys, const AOp& A) {
     const int N = c.N, n = 6 * N, m = 11 * N, tid = threadIdx.x, T = blockDim.x;
     SolveInfo info{ST_MAX_ITER, 0, 0, PATH_ADMM, c.rho0};
     double *rv = w.mv[0], *z = w.mv[1], *y = w.mv[2], *wv = w.mv[3];

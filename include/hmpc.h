@@ -72,7 +72,9 @@ typedef struct hmpc_config {
     int32_t dyn;           /* HMPC_DYN_2F | HMPC_DYN_3F */
     int32_t N;             /* horizon (robotrunner.py:46 uses 60; benches 10/20/40) */
     int32_t mpc_factor;    /* sim steps per MPC tick (robotrunner.py:48) = 20 */
-    int32_t precision;     /* HMPC_FP64 | HMPC_FP32 (FP32 not implemented yet -> HMPC_ERR_UNSUPPORTED) */
+    int32_t precision;     /* HMPC_FP64 | HMPC_FP32.  FP32 = mixed precision: the factorisations and substitutions
+                              run in FP32 (factor stored as float), QP data / iterates / residuals stay FP64 and the
+                              refinement loops recover the accuracy; same acceptance test on the original QP */
     int32_t uref_mode;     /* HMPC_UREF_ALIASED (reference-faithful) | HMPC_UREF_PER_STAGE */
     int32_t solver;        /* HMPC_SOLVER_EXACT: warm-started verified active-set refinement with an
                               interior-point fallback -> the exact optimum (default);
@@ -101,9 +103,11 @@ typedef struct hmpc_config {
     double kf;             /* terminal state-cost factor, mpc_cvx_euler_3f.py:113 (100); input factor kuf=0 */
     double eps_abs, eps_rel;   /* ADMM residual test (cvxpy: 1e-5 each) */
     double rho0, sigma, alpha; /* OSQP defaults 0.1, 1e-6, 1.6 */
-    double kkt_eps;            /* regularisation of the quasi-definite polish system (removed by refinement) */
+    double kkt_eps;            /* relative regularisation of the row block of the quasi-definite polish system
+                                  (removed by refinement); FP32 mode uses at least 1e-3 */
     double polish_tol;         /* relative KKT acceptance tolerance of the verification, default 1e-9 */
-    double ipm_tol;            /* interior-point residual / complementarity tolerance, default 1e-9 */
+    double ipm_tol;            /* interior-point residual / complementarity tolerance, default 1e-6 (the verified
+                                  polish that follows lands on the exact optimum) */
 } hmpc_config;
 
 typedef struct hmpc_handle hmpc_handle;

@@ -51,7 +51,12 @@ def _kkt_factor(H, A, pin, rows, eps):
     K[:nF, :nF] = H[np.ix_(F, F)]
     K[nF:, :nF] = G
     K[:nF, nF:] = G.T
-    K[nF:, nF:] = -eps * np.eye(ng)
+    # relative regularisation of the row block (device: LinSys::factor): the diagonal of the Schur
+    # complement -G H_FF^-1 G' is scaled by (1 + eps); rows without an unpinned variable are decoupled
+    if ng:
+        S = G @ np.linalg.solve(H[np.ix_(F, F)], G.T) if nF else np.zeros((ng, ng))
+        d = np.where(np.abs(G).sum(axis=1) > 0, eps * np.diag(S), 1.0)
+        K[nF:, nF:] = -np.diag(d)
     return sla.lu_factor(K), F
 
 

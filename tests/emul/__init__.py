@@ -57,7 +57,8 @@ def default_config(**over):
     cfg.fz_max, cfg.z_min, cfg.kf = 206.0, 0.1, 100.0
     cfg.eps_abs = cfg.eps_rel = 1e-5
     cfg.rho0, cfg.sigma, cfg.alpha = 0.1, 1e-6, 1.6
-    cfg.kkt_eps = cfg.polish_tol = cfg.ipm_tol = 1e-9
+    cfg.kkt_eps = cfg.polish_tol = 1e-9
+    cfg.ipm_tol = 1e-6
     for k, v in over.items():
         setattr(cfg, k, v)
     return cfg

@@ -27,6 +27,14 @@ static QpConst qp_const(const hmpc_config& cfg) {
     c.eps_abs = cfg.eps_abs; c.eps_rel = cfg.eps_rel; c.rho0 = cfg.rho0; c.sigma = cfg.sigma;
     c.alpha = cfg.alpha; c.kkt_eps = cfg.kkt_eps; c.polish_tol = cfg.polish_tol; c.ipm_tol = cfg.ipm_tol;
     c.condense_flops = hmpc::flops_condense(cfg.N);
+    c.max_refine = 6;
+    c.stagnation = 0.25;
+    if (cfg.precision == HMPC_FP32) {
+        c.max_refine = 14;
+        c.stagnation = 0.7;
+        c.kkt_eps = cfg.kkt_eps > 1e-3 ? cfg.kkt_eps : 1e-3;
+        c.ipm_tol = cfg.ipm_tol > 1e-6 ? cfg.ipm_tol : 1e-6;
+    }
     return c;
 }
 
@@ -45,14 +53,19 @@ int emul_solve(const hmpc_config* cfg, const double* Qd, const double* Rd, const
     Work w;
     setup_work<true>(w, c, smem.data(), nullptr);
     AOp A{N, n, c.dyn == 3 ? 1 : 0, c.mu, w.stance, w.hinv};
-    LinSys sys{n, 0, 0, w.Lm, w.dinv, w.H, w.idx, w.grow};
     MpcIo io;
     io.x_in = x_in; io.x_ref = x_ref; io.pf = pf; io.Cbits = Cbits; io.Qd = Qd; io.Rd = Rd;
     io.Xsol = Xsol_state; io.Usol = Usol_state; io.code = code_state; io.valid = valid_state;
     io.U_out = U; io.X_out = Xsol; io.U0_out = nullptr;
     io.status = status; io.iters = iters; io.st_tick = st_tick.data(); io.nfac = nfac; io.path = path;
     io.ninf = ninf.data(); io.flops = nullptr; io.init = init; io.accumulate = 0; io.respawn = 0;
-    for (int b = 0; b < B; ++b) mpc_hopper(c, w, sys, A, b, B, io);
+    if (cfg->precision == HMPC_FP32) {
+        LinSys<float> sys{n, 0, 0, reinterpret_cast<float*>(w.Lm), reinterpret_cast<float*>(w.dinv), w.H, w.idx, w.grow};
+        for (int b = 0; b < B; ++b) mpc_hopper(c, w, sys, A, b, B, io);
+    } else {
+        LinSys<double> sys{n, 0, 0, reinterpret_cast<double*>(w.Lm), reinterpret_cast<double*>(w.dinv), w.H, w.idx, w.grow};
+        for (int b = 0; b < B; ++b) mpc_hopper(c, w, sys, A, b, B, io);
+    }
     return 0;
 }
 

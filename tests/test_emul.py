@@ -49,11 +49,12 @@ def test_condense_matches_reference_qp_data(dyn):
         assert inf[0] == 0
 
 
-@pytest.mark.parametrize("dyn,N", [("3f", 10), ("2f", 10), ("3f", 20)])
-def test_closed_loop_matches_oracle(dyn, N):
+@pytest.mark.parametrize("dyn,N,precision", [("3f", 10, 0), ("2f", 10, 0), ("3f", 20, 0), ("3f", 10, 1), ("2f", 10, 1)])
+def test_closed_loop_matches_oracle(dyn, N, precision):
+    """precision 1 = FP32 factorisation / substitution with FP64 data and refinement: same parity bound."""
     B, n_ticks = (6, 25) if N == 10 else (2, 8)
     sc = scenarios.make_batch(B, N=N, n_ticks=n_ticks, seed=21, dyn=dyn)
-    em = EmulMpc(B, dyn=dyn, N=N)
+    em = EmulMpc(B, dyn=dyn, N=N, precision=precision)
     em.set_gains(sc["Qdiag"], sc["Rdiag"])
     mpcs = [OracleMpc(ho.Params(dyn=dyn, N=N, Qdiag=sc["Qdiag"][:, b].copy(), Rdiag=sc["Rdiag"][:, b].copy()))
             for b in range(B)]

@@ -100,17 +100,27 @@ def test_mpcontrol_matches_oracle_optimum(dyn, N, B):
             assert np.sum(pa == _lib.PATH_WARM) > 0
 
 
-@pytest.mark.parametrize("dyn", ["3f", "2f"])
-def test_closed_loop_rollout_matches_oracle(dyn):
+@pytest.mark.parametrize("dyn,precision", [("3f", "fp64"), ("2f", "fp64"), ("3f", "fp32"), ("2f", "fp32")])
+def test_closed_loop_rollout_matches_oracle(dyn, precision):
+    """fp32 = FP32 factorisation / substitution, FP64 data and refinement (mixed precision): the accepted
+    points pass the same KKT test of the original QP, so the FP64 parity bound is kept."""
     B, N, n_ticks = 8, 10, 30
     sc = scenarios.make_batch(B, N=N, n_ticks=n_ticks, seed=7, dyn=dyn)
-    bm = mk(B, dyn, N)
+    bm = mk(B, dyn, N, precision=precision)
     bm.set_gains(T(sc["Qdiag"]), T(sc["Rdiag"]))
     X = T(sc["X0"]).clone()
     out = bm.rollout(X, T(sc["xref_tab"]), T(sc["pf_tab"]), cb64(sc["C_tab"]), T(sc["pf_switch"]), 0, n_ticks, True, log=True)
-    assert np.all(out["status"].cpu().numpy() == 0)
+    st = out["status"].cpu().numpy()
+    if precision == "fp64":
+        assert np.all(st == 0)
+    else:
+        # the FP32 interior point can stall on near-infeasible QPs (status MAX_ITER / INEXACT, never a wrong
+        # SOLVED); parity is asserted on the hoppers whose every tick was verified
+        assert np.sum(st == 0) >= B - 1, st
     Xg, Ug = out["X_log"].cpu().numpy(), out["U_log"].cpu().numpy()
     for b in range(B):
+        if st[b] != 0:
+            continue
         p = ho.Params(dyn=dyn, N=N, Qdiag=sc["Qdiag"][:, b].copy(), Rdiag=sc["Rdiag"][:, b].copy())
         Xo, Uo = closed_loop(p, sc["X0"][:, b], sc["xref_tab"][:, :, b], sc["pf_tab"][:, :, b], sc["C"][:, b],
                              sc["pf_switch"][:, b], n_ticks)
@@ -142,6 +152,26 @@ def _cbits(C):
 
 
 # ---- properties at full batch size ------------------------------------------------------------
+def test_fp32_mode_batch_matches_fp64_mode():
+    """BASELINE configs[3] asks for FP32 and FP64 modes: over a 2048-hopper closed loop the mixed-precision
+    mode solves (almost) every QP to the verified optimum and its trajectories stay within 1e-6 of FP64's."""
+    B, N, n_ticks = 2048, 10, 10
+    sc = scenarios.make_batch(B, N=N, n_ticks=n_ticks, seed=17)
+    res = {}
+    for prec in ("fp64", "fp32"):
+        bm = mk(B, "3f", N, precision=prec)
+        bm.set_gains(T(sc["Qdiag"]), T(sc["Rdiag"]))
+        X = T(sc["X0"]).clone()
+        out = bm.rollout(X, T(sc["xref_tab"]), T(sc["pf_tab"]), cb64(sc["C_tab"]), T(sc["pf_switch"]), 0, n_ticks, True, log=True)
+        res[prec] = (X.cpu().numpy(), out["U_log"].cpu().numpy(), out["status"].cpu().numpy())
+    st64, st32 = res["fp64"][2], res["fp32"][2]
+    assert np.mean(st32 == 0) > 0.995, np.bincount(st32, minlength=5)
+    ok = (st64 == 0) & (st32 == 0)
+    assert np.abs(res["fp64"][0][:, ok] - res["fp32"][0][:, ok]).max() < 1e-6
+    U64, U32 = res["fp64"][1][:, :, ok], res["fp32"][1][:, :, ok]
+    assert np.all(np.abs(U64 - U32) <= 10 * u_tol(U64))
+
+
 def test_batch_4096_properties():
     """BASELINE config 3 (3f, 4096 hoppers, horizon 10): every hopper is either solved exactly or flagged
     infeasible; results are bit-identical between two runs, between a hopper inside the batch and the same
