@@ -522,7 +522,8 @@ __device__ inline void compact_indices(int first, int len, int cap, int* list, i
 //
 // Right-looking: K is first assembled into shared memory by all threads, then column j's rank-1 update
 // of the trailing matrix is spread over the CTA (warp per trailing column, lane per row) with ONE
-// barrier per column; the columns are kept unscaled (U = L' D) next to dinv = 1/D.
+// barrier per column; the columns stay unscaled (U = L' D) during the elimination and are scaled to the unit
+// lower triangular L' at the end, next to dinv = 1/D.
 // Substitutions run warp-synchronously in warp 0 (the dependency chain is serial anyway and a
 // __syncwarp() is far cheaper than a CTA barrier).
 // U is stored packed (lower triangle, column by column): the forward sweep reads contiguous columns, the
@@ -627,37 +628,83 @@ struct LinSys {
             }
             j0 = t0;
         }
+        // scale the columns: L' = U D^-1 (unit lower triangular), so that the substitutions carry no
+        // multiplication by 1/d on their dependency chain
+        for (int e = tid; e < nk * nk; e += T) {
+            const int jj = e / nk, ii = e - jj * nk;
+            if (ii > jj) Lm[tri_off(jj, nk) + (ii - jj)] *= dinv[jj];
+        }
+        __syncthreads();
         return bad;
     }
 
-    // Solves K out = b for compact FP64 vectors of length nk; the substitutions run in the factor's precision
-    // on a private copy (scratch, nk entries).  b is left untouched, out may alias b.  Ends with a __syncthreads().
+    // Solves K out = b for compact FP64 vectors of length nk with K = L' D L'^T; the substitutions run in the
+    // factor's precision.  b is left untouched unless out aliases it.  Ends with a __syncthreads().
+    // One warp runs the (serial) substitution; each lane keeps the right-hand-side entries of its rows
+    // (lane, lane+32, lane+64) in registers and the pivot entry is broadcast with a shuffle, so the dependency
+    // chain per column is one shuffle and one FMA.
     __device__ inline void solve(const double* b, double* out, double* scratch) {
         F* sc = reinterpret_cast<F*>(scratch);
         const int tid = threadIdx.x, T = blockDim.x, nk = nF + ng;
         const int LS = T < 32 ? T : 32;
         flops += flops_solve(nk);
         __syncthreads();
-        // one warp runs the substitution; co-resident CTAs use different warp slots so that their
-        // substitutions land on different SM sub-partitions (warp w lives on scheduler w % 4)
+        // co-resident CTAs use different warp slots so that their substitutions land on different SM
+        // sub-partitions (warp w lives on scheduler w % 4)
         const int w0 = (T / LS > 1) ? (solver_warp % (T / LS)) * LS : 0;
         if (tid >= w0 && tid < w0 + LS) {
             const int lane = tid - w0;
-            for (int i = lane; i < nk; i += LS) sc[i] = (F)b[i];
-            __syncwarp();
-            for (int j = 0; j < nk; ++j) {            // L' y = b, z = D^-1 y
-                const F t = sc[j] * dinv[j];
-                const F* col = Lm + tri_off(j, nk) - j;
-                for (int i = j + 1 + lane; i < nk; i += LS) sc[i] -= col[i] * t;
+#ifndef HMPC_HOST_EMUL
+            if (nk <= 96) {
+                const unsigned FULL = 0xffffffffu;
+                const int i0 = lane, i1 = lane + 32, i2 = lane + 64;
+                F b0 = i0 < nk ? (F)b[i0] : (F)0, b1 = i1 < nk ? (F)b[i1] : (F)0, b2 = i2 < nk ? (F)b[i2] : (F)0;
+                const F* col = Lm;                          // col[i - j] = L'(i, j)
+#pragma unroll 1
+                for (int j = 0; j < nk; ++j) {              // L' y = b
+                    const F src = j < 32 ? b0 : (j < 64 ? b1 : b2);
+                    const F t = __shfl_sync(FULL, src, j & 31);
+                    if (i0 > j && i0 < nk) b0 -= col[i0 - j] * t;
+                    if (i1 > j && i1 < nk) b1 -= col[i1 - j] * t;
+                    if (i2 > j && i2 < nk) b2 -= col[i2 - j] * t;
+                    col += nk - j;
+                }
+                if (i0 < nk) b0 *= dinv[i0];                // z = D^-1 y
+                if (i1 < nk) b1 *= dinv[i1];
+                if (i2 < nk) b2 *= dinv[i2];
+                const F* r0 = Lm + (i0 < nk ? tri_off(i0, nk) - i0 : 0);   // r[j] = L'(j, i), j > i
+                const F* r1 = Lm + (i1 < nk ? tri_off(i1, nk) - i1 : 0);
+                const F* r2 = Lm + (i2 < nk ? tri_off(i2, nk) - i2 : 0);
+#pragma unroll 1
+                for (int j = nk - 1; j > 0; --j) {          // L'^T x = z
+                    const F src = j < 32 ? b0 : (j < 64 ? b1 : b2);
+                    const F xj = __shfl_sync(FULL, src, j & 31);
+                    if (i0 < j) b0 -= r0[j] * xj;
+                    if (i1 < j) b1 -= r1[j] * xj;
+                    if (i2 < j) b2 -= r2[j] * xj;
+                }
+                if (i0 < nk) out[i0] = (double)b0;
+                if (i1 < nk) out[i1] = (double)b1;
+                if (i2 < nk) out[i2] = (double)b2;
+            } else
+#endif
+            {
+                for (int i = lane; i < nk; i += LS) sc[i] = (F)b[i];
                 __syncwarp();
-                if (lane == 0) sc[j] = t;
-            }
-            __syncwarp();
-            for (int j = nk - 1; j >= 0; --j) {       // L'^T x = z
-                const F xj = sc[j];
-                for (int i = lane; i < j; i += LS) sc[i] -= Lm[tri_off(i, nk) + (j - i)] * dinv[i] * xj;
-                if (lane == 0) out[j] = (double)xj;
+                for (int j = 0; j < nk; ++j) {            // L' y = b
+                    const F t = sc[j];
+                    const F* col = Lm + tri_off(j, nk) - j;
+                    for (int i = j + 1 + lane; i < nk; i += LS) sc[i] -= col[i] * t;
+                    __syncwarp();
+                }
+                for (int i = lane; i < nk; i += LS) sc[i] *= dinv[i];     // z = D^-1 y
                 __syncwarp();
+                for (int j = nk - 1; j > 0; --j) {        // L'^T x = z
+                    const F xj = sc[j];
+                    for (int i = lane; i < j; i += LS) sc[i] -= Lm[tri_off(i, nk) + (j - i)] * xj;
+                    __syncwarp();
+                }
+                for (int i = lane; i < nk; i += LS) out[i] = (double)sc[i];
             }
         }
         __syncthreads();
