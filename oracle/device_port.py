@@ -31,13 +31,16 @@ def _factor(H, A, wts, dadd, pin):
 
 
 def shift_warm_start(x_prev, code_prev, N):
-    """Time shift of the previous tick's solution and active-set codes by one stage (last stage repeated)."""
+    """Warm start from the previous tick (device: mpc_hopper): stage k takes the previous stage k+1, except
+    the last two stages, which keep their own previous solution / active-set pattern."""
     n = 6 * N
-    x0 = np.concatenate((x_prev[6:], x_prev[-6:]))
-    c = np.zeros_like(code_prev)
-    c[:n - 6] = code_prev[6:n]; c[n - 6:n] = code_prev[n - 6:n]
-    c[n:n + 4 * (N - 1)] = code_prev[n + 4:n + 4 * N]; c[n + 4 * (N - 1):n + 4 * N] = code_prev[n + 4 * (N - 1):n + 4 * N]
-    c[n + 4 * N:n + 5 * N - 1] = code_prev[n + 4 * N + 1:]; c[n + 5 * N - 1] = code_prev[n + 5 * N - 1]
+    x0 = np.array(x_prev, float)
+    c = np.array(code_prev)
+    for k in range(N - 2):
+        x0[6 * k:6 * k + 6] = x_prev[6 * (k + 1):6 * (k + 1) + 6]
+        c[6 * k:6 * k + 6] = code_prev[6 * (k + 1):6 * (k + 1) + 6]
+        c[n + 4 * k:n + 4 * k + 4] = code_prev[n + 4 * (k + 1):n + 4 * (k + 1) + 4]
+        c[n + 4 * N + k] = code_prev[n + 4 * N + k + 1]
     return x0, c
 
 
