@@ -849,31 +849,41 @@ __device__ inline int polish_verified(const QpConst& c, Work& w, Sys& sys, const
         const double scale = fmax(1.0, v[1]);
         const double stol = tol * fmax(scale, v[2]);
         // ---- pass 2: per-row verdicts and the refined active set ----
-        int bad = (v[0] <= 1e-10 * scale) ? 0 : 1, changed = 0;
+        // Rows whose multiplier has the wrong sign are released first; violated rows are only activated by
+        // a trial that had no wrong-signed row (measured: fewer trials and fewer give-ups than doing both at
+        // once).  w.side (interior-point scratch) holds the proposed change: 1 release, 2 / 3 activate lower / upper.
+        int bad = (v[0] <= 1e-10 * scale) ? 0 : 1, anywrong = 0;
         if (!(v[0] == v[0]) || !(v[2] == v[2])) bad = 2;
         for (int r = tid; r < m; r += T) {
             const double ax = A.row(r, w.xp), lo = w.lo[r], hi = w.hi[r];
             const int cd = w.code[r];
             const bool apriori = (r < n) && w.fixed[r];
-            int ncode = cd;
+            int change = 0;
             if (cd != 0) {
                 const double lam = mul[r];
-                if ((cd > 0 && lam < -stol) || (cd < 0 && lam > stol)) { ncode = 0; bad |= 1; }
+                if ((cd > 0 && lam < -stol) || (cd < 0 && lam > stol)) { change = 1; bad |= 1; anywrong = 1; }
                 if (r >= n && fabs(ax - bnd[r]) > tol * (1.0 + fabs(bnd[r]))) bad |= 1;   // singular / inconsistent set
             } else if (!apriori) {
-                if (lo - ax > tol * (1.0 + fabs(lo))) { ncode = -1; bad |= 1; }
-                else if (ax - hi > tol * (1.0 + fabs(hi))) { ncode = 1; bad |= 1; }
+                if (lo - ax > tol * (1.0 + fabs(lo))) { change = 2; bad |= 1; }
+                else if (ax - hi > tol * (1.0 + fabs(hi))) { change = 3; bad |= 1; }
             }
-            if (ncode != cd) { changed = 1; w.code[r] = (int8_t)ncode; }
+            w.side[r] = (int8_t)change;
         }
         bad = __syncthreads_or(bad);
-        changed = __syncthreads_or(changed);
+        anywrong = __syncthreads_or(anywrong);
         if (!bad) {
             for (int i = tid; i < n; i += T) w.x[i] = w.xp[i];
             for (int r = n + tid; r < m; r += T) if (!w.code[r]) mul[r] = 0.0;
             __syncthreads();
             return 1;
         }
+        int changed = 0;
+        for (int r = tid; r < m; r += T) {
+            const int change = w.side[r];
+            if (change == 1) { w.code[r] = 0; changed = 1; }
+            else if (change >= 2 && !anywrong) { w.code[r] = (int8_t)(change == 2 ? -1 : 1); changed = 1; }
+        }
+        changed = __syncthreads_or(changed);
         if (!changed || (bad & 2)) return 0;
     }
     return 0;

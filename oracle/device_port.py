@@ -128,10 +128,12 @@ def polish_verified(H, g, A, lo, hi, x, code, eps=1e-9, tol=1e-9, retries=8, max
             return (xp, y, code), nfac
         if not np.isfinite(stat):
             return None, nfac
+        # release wrong-signed rows first; violated rows are only activated by a trial without wrong-signed rows
         ncode = code.copy()
         ncode[wrong] = 0
-        ncode[vl] = -1
-        ncode[vu] = 1
+        if not wrong.any():
+            ncode[vl] = -1
+            ncode[vu] = 1
         if (ncode == code).all():
             return None, nfac
         code = ncode
