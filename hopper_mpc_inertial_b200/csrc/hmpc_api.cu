@@ -20,6 +20,7 @@
 #include "hmpc_sim.cuh"
 #include "hmpc_qp.cuh"
 #include "hmpc_mpc.cuh"
+#include "hmpc_kernel.cuh"
 
 namespace {
 
@@ -145,35 +146,6 @@ __global__ void convert_kernel(int B, const double* __restrict__ X, double* __re
     convert_state(Xl, xl);
 #pragma unroll
     for (int i = 0; i < 12; ++i) x[(size_t)i * B + b] = xl[i];
-}
-
-// ------------------------------------------------------------------------------------------------
-// K1+K2: mpcontrol for a batch (mpc_cvx_euler_3f.py:41-69).  Persistent CTAs, one hopper at a time.
-// ------------------------------------------------------------------------------------------------
-// F: precision of the factorisation and of the substitutions (double, or float = mixed precision: QP data,
-// iterates and residuals stay FP64 and the refinement loops recover FP64-level accuracy)
-template <int THREADS, int MIN_CTAS, bool SMEM_MATS, typename F>
-__global__ void __launch_bounds__(THREADS, MIN_CTAS)
-mpc_kernel(QpConst c, int B, int sm_count, double* __restrict__ ws, int* __restrict__ work_ctr, MpcIo io) {
-    extern __shared__ double smem[];
-    __shared__ int s_next;
-    Work w;
-    setup_work<SMEM_MATS>(w, c, smem, ws, (int)sizeof(F));
-    const int N = c.N, n = 6 * N;
-    AOp A{N, n, c.dyn == 3 ? 1 : 0, c.mu, w.stance, w.hinv};
-    LinSys<F> sys{n, 0, 0, reinterpret_cast<F*>(w.Lm), reinterpret_cast<F*>(w.dinv), w.H, w.idx, w.grow};
-    // CTAs are dealt to the SMs round-robin, so the CTAs sharing an SM differ in blockIdx.x / #SMs
-    sys.solver_warp = blockIdx.x / sm_count;
-    // dynamic distribution of hoppers over the persistent CTAs (solve times differ: warm active-set path
-    // vs interior-point path); results do not depend on the order
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_next = atomicAdd(work_ctr, 1);
-        __syncthreads();
-        const int b = s_next;
-        if (b >= B) break;
-        mpc_hopper(c, w, sys, A, b, B, io);
-    }
 }
 
 // parity-test kernels ---------------------------------------------------------------------------
@@ -352,6 +324,7 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
     if (cfg->N < 2 || cfg->N > HMPC_MAX_N) return fail(HMPC_ERR_BAD_ARG, "N must be in [2, 64]");
     if (cfg->dyn != HMPC_DYN_2F && cfg->dyn != HMPC_DYN_3F) return fail(HMPC_ERR_BAD_ARG, "dyn must be 2 or 3");
     if (cfg->precision != HMPC_FP64 && cfg->precision != HMPC_FP32) return fail(HMPC_ERR_BAD_ARG, "precision must be HMPC_FP64 or HMPC_FP32");
+    if (cfg->precision == HMPC_FP32 && cfg->N > 10) return fail(HMPC_ERR_UNSUPPORTED, "FP32 mode is built for horizons N <= 10 only");
     if (cfg->mpc_factor < 1 || cfg->mpc_factor > 255) return fail(HMPC_ERR_BAD_ARG, "mpc_factor must be in [1,255]");
     if (cfg->max_iter < 1 || cfg->check_interval < 1 || cfg->first_check < 1 || cfg->polish_retries < 0 ||
         cfg->ipm_max_iter < 1)
@@ -421,15 +394,9 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
         }
     }
     const int smem_i = (int)h->mpc_smem;
-    const cudaFuncAttribute dyn_attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
-    if ((e = cudaFuncSetAttribute(hmpc::mpc_kernel<128, 4, true, double>, dyn_attr, smem_i)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(hmpc::mpc_kernel<128, 1, false, double>, dyn_attr, smem_i)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(hmpc::mpc_kernel<256, 1, true, double>, dyn_attr, smem_i)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(hmpc::mpc_kernel<256, 1, false, double>, dyn_attr, smem_i)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(hmpc::mpc_kernel<128, 5, true, float>, dyn_attr, smem_i)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(hmpc::mpc_kernel<128, 1, false, float>, dyn_attr, smem_i)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(hmpc::mpc_kernel<256, 1, true, float>, dyn_attr, smem_i)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(hmpc::mpc_kernel<256, 1, false, float>, dyn_attr, smem_i)) != cudaSuccess ||
+    if (h->mpc_threads == 128) e = (cfg->precision == HMPC_FP32) ? hmpc::mpc_set_smem_n10_f32(smem_i) : hmpc::mpc_set_smem_n10_f64(smem_i);
+    else e = h->mats_in_smem ? hmpc::mpc_set_smem_wide_smem(smem_i) : hmpc::mpc_set_smem_wide_gmem(smem_i);
+    if (e != cudaSuccess ||
         (e = cudaFuncSetAttribute(hmpc::condense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mpc_smem)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(hmpc::linearize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vec_bytes)) != cudaSuccess) {
         hmpc_destroy(h);
@@ -524,15 +491,12 @@ namespace {
 // small horizons: 128 threads, registers capped so that four CTAs share an SM; large: 256 threads
 void launch_mpc(hmpc_handle* h, const hmpc::QpConst& qc, const hmpc::MpcIo& io) {
     cudaMemsetAsync(h->work_ctr, 0, sizeof(int), h->stream);
-    const int B = h->cfg.batch;
-    const bool f32 = h->cfg.precision == HMPC_FP32;
-#define HMPC_LAUNCH(TH, MINB, SM, FT) \
-    hmpc::mpc_kernel<TH, MINB, SM, FT><<<h->mpc_grid, TH, h->mpc_smem, h->stream>>>(qc, B, h->sm_count, h->ws, h->work_ctr, io)
-    if (h->mpc_threads == 128 && h->mats_in_smem) { if (f32) HMPC_LAUNCH(128, 5, true, float); else HMPC_LAUNCH(128, 4, true, double); }
-    else if (h->mpc_threads == 128) { if (f32) HMPC_LAUNCH(128, 1, false, float); else HMPC_LAUNCH(128, 1, false, double); }
-    else if (h->mats_in_smem) { if (f32) HMPC_LAUNCH(256, 1, true, float); else HMPC_LAUNCH(256, 1, true, double); }
-    else { if (f32) HMPC_LAUNCH(256, 1, false, float); else HMPC_LAUNCH(256, 1, false, double); }
-#undef HMPC_LAUNCH
+    const hmpc::MpcLaunch l{h->mpc_grid, h->mpc_threads, h->mpc_smem, h->stream, h->cfg.batch, h->sm_count, h->ws, h->work_ctr};
+    if (h->mpc_threads == 128) {
+        if (h->cfg.precision == HMPC_FP32) hmpc::mpc_launch_n10_f32(l, qc, io);
+        else hmpc::mpc_launch_n10_f64(l, qc, io);
+    } else if (h->mats_in_smem) hmpc::mpc_launch_wide_smem(l, qc, io);
+    else hmpc::mpc_launch_wide_gmem(l, qc, io);
 }
 
 hmpc::MpcIo make_io(hmpc_handle* h, const double* x_in, const double* x_ref, const double* pf,

@@ -1,0 +1,70 @@
+// hmpc_kernel.cuh -- the persistent solver kernel (K1+K2) as a template, plus the per-instantiation host
+// entry points.  Every instantiation lives in its own translation unit (csrc/inst_*.cu) so that the library
+// builds in parallel: one instantiation of this kernel is ~30 k SASS instructions.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "hmpc_sim.cuh"
+#include "hmpc_mpc.cuh"
+
+namespace hmpc {
+
+// ------------------------------------------------------------------------------------------------
+// K1+K2: mpcontrol for a batch (mpc_cvx_euler_3f.py:41-69).  Persistent CTAs, one hopper at a time.
+// ------------------------------------------------------------------------------------------------
+// F: precision of the factorisation and of the substitutions (double, or float = mixed precision: QP data,
+// iterates and residuals stay FP64 and the refinement loops recover FP64-level accuracy)
+template <int THREADS, int MIN_CTAS, bool SMEM_MATS, typename F>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS)
+mpc_kernel(QpConst c, int B, int sm_count, double* __restrict__ ws, int* __restrict__ work_ctr, MpcIo io) {
+    extern __shared__ double smem[];
+    __shared__ int s_next;
+    Work w;
+    setup_work<SMEM_MATS>(w, c, smem, ws, (int)sizeof(F));
+    const int N = c.N, n = 6 * N;
+    AOp A{N, n, c.dyn == 3 ? 1 : 0, c.mu, w.stance, w.hinv};
+    LinSys<F> sys{n, 0, 0, reinterpret_cast<F*>(w.Lm), reinterpret_cast<F*>(w.dinv), w.H, w.idx, w.grow};
+    // CTAs are dealt to the SMs round-robin, so the CTAs sharing an SM differ in blockIdx.x / #SMs
+    sys.solver_warp = blockIdx.x / sm_count;
+    // dynamic distribution of hoppers over the persistent CTAs (solve times differ: warm active-set path
+    // vs interior-point path); results do not depend on the order
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_next = atomicAdd(work_ctr, 1);
+        __syncthreads();
+        const int b = s_next;
+        if (b >= B) break;
+        mpc_hopper(c, w, sys, A, b, B, io);
+    }
+}
+
+// host entry points of one instantiation
+struct MpcLaunch {
+    int grid, threads;
+    size_t smem;
+    cudaStream_t stream;
+    int B, sm_count;
+    double* ws;
+    int* work_ctr;
+};
+
+template <int THREADS, int MIN_CTAS, bool SMEM_MATS, typename F>
+inline cudaError_t mpc_set_smem(int bytes) {
+    return cudaFuncSetAttribute(mpc_kernel<THREADS, MIN_CTAS, SMEM_MATS, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+template <int THREADS, int MIN_CTAS, bool SMEM_MATS, typename F>
+inline void mpc_launch(const MpcLaunch& l, const QpConst& qc, const MpcIo& io) {
+    mpc_kernel<THREADS, MIN_CTAS, SMEM_MATS, F><<<l.grid, THREADS, l.smem, l.stream>>>(qc, l.B, l.sm_count, l.ws, l.work_ctr, io);
+}
+
+// the instantiations the library ships (defined in csrc/inst_*.cu)
+cudaError_t mpc_set_smem_n10_f64(int bytes);      // 128 threads, 4 CTAs/SM, shared-memory matrices, FP64 factor
+void mpc_launch_n10_f64(const MpcLaunch&, const QpConst&, const MpcIo&);
+cudaError_t mpc_set_smem_n10_f32(int bytes);      // 128 threads, 5 CTAs/SM, shared-memory matrices, FP32 factor
+void mpc_launch_n10_f32(const MpcLaunch&, const QpConst&, const MpcIo&);
+cudaError_t mpc_set_smem_wide_smem(int bytes);    // 256 threads, 1 CTA/SM, shared-memory matrices, FP64 factor
+void mpc_launch_wide_smem(const MpcLaunch&, const QpConst&, const MpcIo&);
+cudaError_t mpc_set_smem_wide_gmem(int bytes);    // 256 threads, matrices in the L2-resident workspace, FP64 factor
+void mpc_launch_wide_gmem(const MpcLaunch&, const QpConst&, const MpcIo&);
+
+}  // namespace hmpc

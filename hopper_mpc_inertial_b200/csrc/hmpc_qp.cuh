@@ -29,6 +29,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "hmpc_sim.cuh"   // mat3_vec / mat3T_vec
+
 namespace hmpc {
 
 constexpr double kInf = 1e30;
