@@ -102,6 +102,8 @@ def polish_verified(H, g, A, lo, hi, x, code, eps=1e-9, tol=1e-9, retries=8, max
             rel = max((np.abs(rd) / ((np.abs(Hx_) + np.abs(g) + np.abs(Aty_))[F] + 1e-300)).max(initial=0.0),
                       (np.abs(rp) / ((np.abs(bnd) + np.abs(Ax_))[rows] + 1e-300)).max(initial=0.0))
             # stop when every row's residual sits at its rounding level or the residual has stopped contracting
+            if k == 1 and ng == 0 and res <= 1e-7 * prev:      # exact system, already at working accuracy
+                break
             if k >= 1 and (rel <= 1e-12 or (k >= 2 and res > 0.25 * prev)):
                 break
             prev = res
