@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -381,6 +382,8 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
     const size_t smem_cap = (size_t)prop.sharedMemPerBlockOptin;
     h->mats_in_smem = (vec_bytes + mat_bytes + 1024 <= smem_cap);
     h->mpc_smem = vec_bytes + (h->mats_in_smem ? mat_bytes : 0);
+    // occupancy experiments (profiles/README.md): HMPC_SMEM_PAD=<bytes> pads the dynamic shared memory request
+    if (const char* pad = getenv("HMPC_SMEM_PAD")) h->mpc_smem += (size_t)atol(pad);
     if (h->mpc_smem > smem_cap) { hmpc_destroy(h); return fail(HMPC_ERR_UNSUPPORTED, "horizon too large for shared memory"); }
     h->mpc_threads = (n <= 64) ? 128 : 256;   // one CTA per SM beyond N = 10: use the wider CTA
     int per_sm = 1;
