@@ -2,7 +2,8 @@
 //
 // Kernels
 //   sim_kernel        K3: mpc_factor x RK4 (ZOH control) + convert, one thread per hopper, SoA I/O
-//   mpc_kernel        K1+K2: time shift, linearise, condense, ADMM + verified polish, solution rollout;
+//   mpc_kernel        K1+K2 (hmpc_kernel.cuh, instantiated in inst_*.cu): time shift, linearise, condense,
+//                     solve (warm active-set refinement / interior point / ADMM), solution rollout;
 //                     one CTA per hopper (persistent grid-stride loop)
 //   convert_kernel / linearize_kernel / condense_kernel   parity-test entry points
 //   dfma_peak_kernel  FP64 FMA roofline microbenchmark

@@ -22,8 +22,9 @@
 //                 the cold start / fallback; every accepted point passes the KKT test of the ORIGINAL QP
 //   admm_solve    OSQP iteration in the dense condensed form, fixed-iteration or
 //                 early-exit, residual-balancing rho adaptation
-// Linear algebra: one signed Cholesky  K = L S L'  (S = diag(+-1)) of the compacted operator -- the
-// positive definite  H + A'WA  (IPM, ADMM) or the quasi-definite  [[H_FF, G'],[G, -eps I]]  (polish).
+// Linear algebra: one LDL' factorisation  K = L' D L'^T  of the compacted operator -- the positive definite
+// H + A'WA  (IPM, ADMM) or the quasi-definite  [[H_FF, G'],[G, -E]]  (polish; negative pivots for the rows),
+// in FP64 or, in the mixed-precision mode, in FP32 (struct LinSys).
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
