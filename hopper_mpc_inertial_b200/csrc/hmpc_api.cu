@@ -398,7 +398,10 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
         }
     }
     const int smem_i = (int)h->mpc_smem;
-    if (h->mpc_threads == 128) e = (cfg->precision == HMPC_FP32) ? hmpc::mpc_set_smem_n10_f32(smem_i) : hmpc::mpc_set_smem_n10_f64(smem_i);
+    if (h->mpc_threads == 128) {
+        if (cfg->precision == HMPC_FP32) e = hmpc::mpc_set_smem_n10_f32(smem_i);
+        else e = (cfg->solver == HMPC_SOLVER_ADMM) ? hmpc::mpc_set_smem_n10_f64_admm(smem_i) : hmpc::mpc_set_smem_n10_f64(smem_i);
+    }
     else e = h->mats_in_smem ? hmpc::mpc_set_smem_wide_smem(smem_i) : hmpc::mpc_set_smem_wide_gmem(smem_i);
     if (e != cudaSuccess ||
         (e = cudaFuncSetAttribute(hmpc::condense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mpc_smem)) != cudaSuccess ||
@@ -498,6 +501,7 @@ void launch_mpc(hmpc_handle* h, const hmpc::QpConst& qc, const hmpc::MpcIo& io) 
     const hmpc::MpcLaunch l{h->mpc_grid, h->mpc_threads, h->mpc_smem, h->stream, h->cfg.batch, h->sm_count, h->ws, h->work_ctr};
     if (h->mpc_threads == 128) {
         if (h->cfg.precision == HMPC_FP32) hmpc::mpc_launch_n10_f32(l, qc, io);
+        else if (h->cfg.solver == HMPC_SOLVER_ADMM) hmpc::mpc_launch_n10_f64_admm(l, qc, io);
         else hmpc::mpc_launch_n10_f64(l, qc, io);
     } else if (h->mats_in_smem) hmpc::mpc_launch_wide_smem(l, qc, io);
     else hmpc::mpc_launch_wide_gmem(l, qc, io);

@@ -14,7 +14,7 @@ namespace hmpc {
 // ------------------------------------------------------------------------------------------------
 // F: precision of the factorisation and of the substitutions (double, or float = mixed precision: QP data,
 // iterates and residuals stay FP64 and the refinement loops recover FP64-level accuracy)
-template <int THREADS, int MIN_CTAS, bool SMEM_MATS, typename F>
+template <int THREADS, int MIN_CTAS, bool SMEM_MATS, typename F, bool WITH_ADMM>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 mpc_kernel(QpConst c, int B, int sm_count, double* __restrict__ ws, int* __restrict__ work_ctr, MpcIo io) {
     extern __shared__ double smem[];
@@ -34,7 +34,7 @@ mpc_kernel(QpConst c, int B, int sm_count, double* __restrict__ ws, int* __restr
         __syncthreads();
         const int b = s_next;
         if (b >= B) break;
-        mpc_hopper(c, w, sys, A, b, B, io);
+        mpc_hopper<WITH_ADMM>(c, w, sys, A, b, B, io);
     }
 }
 
@@ -48,18 +48,20 @@ struct MpcLaunch {
     int* work_ctr;
 };
 
-template <int THREADS, int MIN_CTAS, bool SMEM_MATS, typename F>
+template <int THREADS, int MIN_CTAS, bool SMEM_MATS, typename F, bool WITH_ADMM>
 inline cudaError_t mpc_set_smem(int bytes) {
-    return cudaFuncSetAttribute(mpc_kernel<THREADS, MIN_CTAS, SMEM_MATS, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    return cudaFuncSetAttribute(mpc_kernel<THREADS, MIN_CTAS, SMEM_MATS, F, WITH_ADMM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
-template <int THREADS, int MIN_CTAS, bool SMEM_MATS, typename F>
+template <int THREADS, int MIN_CTAS, bool SMEM_MATS, typename F, bool WITH_ADMM>
 inline void mpc_launch(const MpcLaunch& l, const QpConst& qc, const MpcIo& io) {
-    mpc_kernel<THREADS, MIN_CTAS, SMEM_MATS, F><<<l.grid, THREADS, l.smem, l.stream>>>(qc, l.B, l.sm_count, l.ws, l.work_ctr, io);
+    mpc_kernel<THREADS, MIN_CTAS, SMEM_MATS, F, WITH_ADMM><<<l.grid, THREADS, l.smem, l.stream>>>(qc, l.B, l.sm_count, l.ws, l.work_ctr, io);
 }
 
 // the instantiations the library ships (defined in csrc/inst_*.cu)
-cudaError_t mpc_set_smem_n10_f64(int bytes);      // 128 threads, 4 CTAs/SM, shared-memory matrices, FP64 factor
+cudaError_t mpc_set_smem_n10_f64(int bytes);      // 128 threads, 4 CTAs/SM, shared-memory matrices, FP64 factor, exact solver only
 void mpc_launch_n10_f64(const MpcLaunch&, const QpConst&, const MpcIo&);
+cudaError_t mpc_set_smem_n10_f64_admm(int bytes); // the same with the ADMM branch compiled in
+void mpc_launch_n10_f64_admm(const MpcLaunch&, const QpConst&, const MpcIo&);
 cudaError_t mpc_set_smem_n10_f32(int bytes);      // 128 threads, 5 CTAs/SM, shared-memory matrices, FP32 factor
 void mpc_launch_n10_f32(const MpcLaunch&, const QpConst&, const MpcIo&);
 cudaError_t mpc_set_smem_wide_smem(int bytes);    // 256 threads, 1 CTA/SM, shared-memory matrices, FP64 factor

@@ -85,7 +85,8 @@ struct MpcIo {
 };
 
 // One hopper b of a batch of B.  All threads of the CTA call this together.
-template <class Sys>
+// WITH_ADMM = false compiles the OSQP-style ADMM branch out (smaller kernel for the default exact solver)
+template <bool WITH_ADMM, class Sys>
 __device__ inline void mpc_hopper(const QpConst& c, Work& w, Sys& sys, const AOp& A, int b, int B, const MpcIo& io) {
     const int N = c.N, n = 6 * N, m = 11 * N, tid = threadIdx.x, T = blockDim.x;
     double* xs = w.err;   // reused after condense: solution trajectory [(N+1)][12]
@@ -146,7 +147,7 @@ __device__ inline void mpc_hopper(const QpConst& c, Work& w, Sys& sys, const AOp
                 }
             }
         }
-        if (!warm || c.solver == HMPC_SOLVER_ADMM) {
+        if (!warm || (WITH_ADMM && c.solver == HMPC_SOLVER_ADMM)) {
             for (int i = tid; i < n; i += T) w.x[i] = warm ? w.xp[i] : 0.0;
             for (int r = tid; r < m; r += T) w.mv[2][r] = 0.0;    // ADMM multipliers start at zero
         }
@@ -158,7 +159,7 @@ __device__ inline void mpc_hopper(const QpConst& c, Work& w, Sys& sys, const AOp
             __syncthreads();
         } else {
             SolveInfo info;
-            if (c.solver == HMPC_SOLVER_ADMM) {
+            if (WITH_ADMM && c.solver == HMPC_SOLVER_ADMM) {
                 info = admm_solve(c, w, sys, A);
                 if (c.polish) {
                     for (int i = tid; i < n; i += T) w.xp[i] = w.x[i];

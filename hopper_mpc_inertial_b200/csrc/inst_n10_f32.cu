@@ -2,6 +2,6 @@
 #include "hmpc_kernel.cuh"
 
 namespace hmpc {
-cudaError_t mpc_set_smem_n10_f32(int bytes) { return mpc_set_smem<128, 5, true, float>(bytes); }
-void mpc_launch_n10_f32(const MpcLaunch& l, const QpConst& qc, const MpcIo& io) { mpc_launch<128, 5, true, float>(l, qc, io); }
+cudaError_t mpc_set_smem_n10_f32(int bytes) { return mpc_set_smem<128, 5, true, float, true>(bytes); }
+void mpc_launch_n10_f32(const MpcLaunch& l, const QpConst& qc, const MpcIo& io) { mpc_launch<128, 5, true, float, true>(l, qc, io); }
 }  // namespace hmpc

@@ -2,6 +2,6 @@
 #include "hmpc_kernel.cuh"
 
 namespace hmpc {
-cudaError_t mpc_set_smem_n10_f64(int bytes) { return mpc_set_smem<128, 4, true, double>(bytes); }
-void mpc_launch_n10_f64(const MpcLaunch& l, const QpConst& qc, const MpcIo& io) { mpc_launch<128, 4, true, double>(l, qc, io); }
+cudaError_t mpc_set_smem_n10_f64(int bytes) { return mpc_set_smem<128, 4, true, double, false>(bytes); }
+void mpc_launch_n10_f64(const MpcLaunch& l, const QpConst& qc, const MpcIo& io) { mpc_launch<128, 4, true, double, false>(l, qc, io); }
 }  // namespace hmpc

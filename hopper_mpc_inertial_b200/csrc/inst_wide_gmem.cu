@@ -2,6 +2,6 @@
 #include "hmpc_kernel.cuh"
 
 namespace hmpc {
-cudaError_t mpc_set_smem_wide_gmem(int bytes) { return mpc_set_smem<256, 1, false, double>(bytes); }
-void mpc_launch_wide_gmem(const MpcLaunch& l, const QpConst& qc, const MpcIo& io) { mpc_launch<256, 1, false, double>(l, qc, io); }
+cudaError_t mpc_set_smem_wide_gmem(int bytes) { return mpc_set_smem<256, 1, false, double, true>(bytes); }
+void mpc_launch_wide_gmem(const MpcLaunch& l, const QpConst& qc, const MpcIo& io) { mpc_launch<256, 1, false, double, true>(l, qc, io); }
 }  // namespace hmpc

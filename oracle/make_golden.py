@@ -16,6 +16,7 @@ inputs; the tests then check the oracle restatement (tests -m "not gpu") and the
 Two more fixtures are ORACLE outputs (exact optimum per tick), not reference outputs -- the reference's
 cvxpy/OSQP back end cannot run here.  They save the GPU box from minutes of numpy closed loop:
   loop_2f.npz / loop_3f_curve.npz   closed loop of run.py 2f / 3f --curve over 2000 ms, N = 60
+  loop_3f_curve_5s.npz              run.py 3f --curve with the default 5 s run time
 """
 from __future__ import annotations
 
@@ -146,8 +147,9 @@ def main():
     # ---- oracle closed loops of the two reference runs (N = 60, 2000 ms) ----
     sys.path.insert(0, ROOT)
     from hopper_mpc_inertial_b200 import planner
-    for tag, dyn, curve in (("loop_2f", "2f", False), ("loop_3f_curve", "3f", True)):
-        N_run, N60 = 2000, 60
+    for tag, dyn, curve, N_run in (("loop_2f", "2f", False, 2000), ("loop_3f_curve", "3f", True, 2000),
+                                   ("loop_3f_curve_5s", "3f", True, 5000)):
+        N60 = 60
         r = ref.robotrunner.Runner(dt=1e-3, dyn=dyn, curve=curve, N_run=N_run)
         x_ref, pf_ref = r.path_plan_init(x_in=ref.robotrunner.convert(r.X_0), xf=ref.robotrunner.convert(r.X_f))
         n_ticks = N_run // 20

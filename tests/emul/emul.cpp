@@ -61,10 +61,10 @@ int emul_solve(const hmpc_config* cfg, const double* Qd, const double* Rd, const
     io.ninf = ninf.data(); io.flops = nullptr; io.init = init; io.accumulate = 0; io.respawn = 0;
     if (cfg->precision == HMPC_FP32) {
         LinSys<float> sys{n, 0, 0, reinterpret_cast<float*>(w.Lm), reinterpret_cast<float*>(w.dinv), w.H, w.idx, w.grow};
-        for (int b = 0; b < B; ++b) mpc_hopper(c, w, sys, A, b, B, io);
+        for (int b = 0; b < B; ++b) mpc_hopper<true>(c, w, sys, A, b, B, io);
     } else {
         LinSys<double> sys{n, 0, 0, reinterpret_cast<double*>(w.Lm), reinterpret_cast<double*>(w.dinv), w.H, w.idx, w.grow};
-        for (int b = 0; b < B; ++b) mpc_hopper(c, w, sys, A, b, B, io);
+        for (int b = 0; b < B; ++b) mpc_hopper<true>(c, w, sys, A, b, B, io);
     }
     return 0;
 }

@@ -129,10 +129,11 @@ def test_closed_loop_rollout_matches_oracle(dyn, precision):
         np.testing.assert_allclose(Xg[:, :, b], Xo, rtol=0, atol=1e-6)
 
 
-@pytest.mark.parametrize("tag,dyn", [("loop_2f", "2f"), ("loop_3f_curve", "3f")])
+@pytest.mark.parametrize("tag,dyn", [("loop_2f", "2f"), ("loop_3f_curve", "3f"), ("loop_3f_curve_5s", "3f")])
 def test_reference_runs_2000ms_N60(tag, dyn):
-    """run.py 2f --N_run 2000 and run.py 3f --curve --N_run 2000 (N = 60, reference constants): closed-loop
-    trajectory against the oracle loop frozen in tests/golden.  State tolerance 1e-5 abs over 100 ticks."""
+    """BASELINE configs[0] and [1]: run.py 2f --N_run 2000, run.py 3f --curve --N_run 2000 and run.py 3f --curve
+    (default 5 s) at the reference's horizon N = 60 and constants: closed-loop trajectory against the oracle
+    loop frozen in tests/golden.  State tolerance 1e-5 abs over 100 / 250 ticks."""
     g = golden(f"{tag}.npz")
     N, n_ticks = int(g["N"]), int(g["n_ticks"])
     bm = mk(1, dyn, N)
