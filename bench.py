@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--solver", choices=["exact", "admm"], default="exact")
     ap.add_argument("--precision", choices=["fp64", "fp32"], default="fp64",
                     help="fp32: FP32 factorisation / substitution with FP64 data and refinement (mixed precision)")
+    ap.add_argument("--sqp-sweeps", type=int, default=1, help="relinearisation sweeps per tick (1 = the reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="wall-clock budget of the CPU baseline sample")
     return ap.parse_args()
@@ -185,7 +186,7 @@ def run_b200(args):
     # ---- synthetic scenario for this shard (host, numpy), tables resident in HBM ----
     sc = scenarios.make_batch(B, idx0=idx0, N=N, n_ticks=n_ticks + 1, dyn=args.dyn)
     bm = BatchMpc(B, dyn=args.dyn, N=N, device=local, solver=args.solver, precision=args.precision,
-                  on_infeasible="respawn")
+                  on_infeasible="respawn", sqp_sweeps=args.sqp_sweeps)
     T = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
     bm.set_gains(T(sc["Qdiag"]), T(sc["Rdiag"]))
     xref_h = torch.from_numpy(np.ascontiguousarray(sc["xref_tab"])).pin_memory()
@@ -291,7 +292,8 @@ def run_b200(args):
     # Same hoppers, same ticks as timed region 1 (the per-tick cost drifts with the tick index): a second
     # handle replays the warm-up from the initial states, then the e2e region covers ticks W .. W+K-1.
     bm_res, X_res = bm, X
-    bm = BatchMpc(B, dyn=args.dyn, N=N, device=local, solver=args.solver, precision=args.precision, on_infeasible="respawn")
+    bm = BatchMpc(B, dyn=args.dyn, N=N, device=local, solver=args.solver, precision=args.precision, on_infeasible="respawn",
+                  sqp_sweeps=args.sqp_sweeps)
     bm.set_gains(T(sc["Qdiag"]), T(sc["Rdiag"]))
     X = T(sc["X0"]).clone()
     bm.rollout(X, xref_d, pf_d, C_d, sw_d, 0, W - 2, True)
@@ -364,7 +366,7 @@ def run_b200(args):
             "dtype": "f64" if args.precision == "fp64" else "f64 data and residuals, f32 factorisation (mixed precision)",
             "data": "synthetic",
             "config": {"workload": workload_name(args, world), "precision": args.precision, "dyn": args.dyn, "horizon": N, "batch_per_gpu": B,
-                       "solver": args.solver, "mpc_factor": 20, "parallelism": f"shard-by-hopper x{world}, no data-path collective",
+                       "solver": args.solver, "sqp_sweeps": args.sqp_sweeps, "mpc_factor": 20, "parallelism": f"shard-by-hopper x{world}, no data-path collective",
                        "cache": "inputs larger than L2 (per-tick working set %.0f MB per GPU > 126 MB L2)"
                                 % (B * (bytes_tick + 13 * 16 + 15 * 8 * 2) / 1e6),
                        "on_infeasible": "respawn"},

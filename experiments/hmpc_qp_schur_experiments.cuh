@@ -44,6 +44,11 @@ static __device__ unsigned long long g_phase[16];
 #define PH_T0(v) do {} while (0)
 #define PH_ADD(id, v) do {} while (0)
 #endif
+// Experimental single-factorisation active-set refinement (polish_schur): 0 off, 1 LDL' + substitutions,
+// 2 explicit inverse by symmetric sweeps.  See DESIGN.md for the measurements behind the default.
+#ifndef HMPC_SCHUR
+#define HMPC_SCHUR 0
+#endif
 constexpr double kInf = 1e30;
 constexpr double kInfThresh = 1e26;   // OSQP: OSQP_INFTY * MIN_SCALING
 constexpr double kRhoMin = 1e-6, kRhoMax = 1e6;
@@ -158,28 +163,44 @@ template <int OP>
 __device__ __forceinline__ double red_op(double a, double b) {
     return OP == 0 ? fmax(a, b) : (OP == 1 ? fmin(a, b) : a + b);
 }
+// The kernel is one large inlined function whose hot code exceeds the instruction cache (ncu: 17 % of the warp
+// stalls are no_inst, 99 % of the executed instructions come from 107 KB of SASS), so the building blocks that
+// are called from many places -- this reduction, LinSys::factor / solve, sym_matvec -- are kept out of line:
+// one copy each.  Values travel by value (registers), never through a reference to a local array.
+template <int K> struct RedVals { double v[K]; };
 template <int K, int OP>
-__device__ inline void block_reduce(double (&v)[K], double* red) {
+__device__ __noinline__ RedVals<K> block_reduce_core(RedVals<K> in, double* red) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
 #ifndef HMPC_HOST_EMUL   // tests/emul runs this source as one serial "thread" on the CPU
 #pragma unroll
     for (int k = 0; k < K; ++k) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v[k] = red_op<OP>(v[k], __shfl_xor_sync(0xffffffffu, v[k], o));
+        for (int o = 16; o > 0; o >>= 1) in.v[k] = red_op<OP>(in.v[k], __shfl_xor_sync(0xffffffffu, in.v[k], o));
     }
 #endif
     __syncthreads();
     if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) red[wid * K + k] = v[k];
+        for (int k = 0; k < K; ++k) red[wid * K + k] = in.v[k];
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         double r = red[k];
+#pragma unroll 1
         for (int q = 1; q < nw; ++q) r = red_op<OP>(r, red[q * K + k]);
-        v[k] = r;
+        in.v[k] = r;
     }
+    return in;
+}
+template <int K, int OP>
+__device__ __forceinline__ void block_reduce(double (&v)[K], double* red) {
+    RedVals<K> t;
+#pragma unroll
+    for (int k = 0; k < K; ++k) t.v[k] = v[k];
+    t = block_reduce_core<K, OP>(t, red);
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = t.v[k];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -571,7 +592,7 @@ struct LinSys {
 
     // Returns nonzero (same value in all threads) when a pivot has the wrong sign or is not finite.
     // P: scratch of at least 4 (nk - 4) doubles (the pre-scaled panel, see below).
-    __device__ inline int factor(const AOp& A, const double* wts, double dadd, double eps, double* scratch) {
+    __device__ __noinline__ int factor(const AOp& A, const double* wts, double dadd, double eps, double* scratch) {
         PH_T0(ph_f);
         F* P = reinterpret_cast<F*>(scratch);
         const int tid = threadIdx.x, T = blockDim.x, nk = nF + ng;
@@ -654,13 +675,160 @@ struct LinSys {
         return bad;
     }
 
-    // Solves K out = b for compact FP64 vectors of length nk with K = L' D L'^T; the substitutions run in the
-    // factor's precision.  b is left untouched unless out aliases it.  Ends with a __syncthreads().
-    // One warp runs the (serial) substitution; each lane keeps the right-hand-side entries of its rows
-    // (lane, lane+32, lane+64) in registers and the pivot entry is broadcast with a shuffle, so the dependency
-    // chain per column is one shuffle and one FMA.
-    __device__ inline void solve(const double* b, double* out, double* scratch) {
-        F* sc = reinterpret_cast<F*>(scratch);
+    // In-place inversion of the positive definite K_vv (ng = 0, no weights) by symmetric sweeps:
+    // Lm <- -K_vv^-1, packed like the factor.  Sweeping pivot k maps  a_kk -> -1/d,  a_ik -> a_ik/d,
+    // a_ij -> a_ij - a_ik a_jk / d  (d = a_kk, a Schur-complement diagonal, > 0); after all nk pivots the
+    // matrix is -K^-1.  Every pivot is one pass over the packed triangle by the whole CTA (warp per column,
+    // lane per row) and ONE barrier: the next pivot's column is written to a second buffer, together with the
+    // reciprocal of its diagonal, by the threads that update those entries.  3x the flops of the LDL' but no
+    // serial chain, and afterwards every solve is a symmetric matrix-vector product.
+    // scratch: 2 (nk + 1) entries.  Returns nonzero (same value in all threads) when a pivot is not positive.
+    __device__ __noinline__ int sweep_invert(const AOp& A, double* scratch) {
+        const int tid = threadIdx.x, T = blockDim.x, nk = nF;
+        const int LS = T < 32 ? T : 32, lane = tid % LS, wid = tid / LS, nw = T / LS;
+        PH_T0(ph_w);
+        F* pc = reinterpret_cast<F*>(scratch);
+        F* pcn = pc + (nk + 1);
+        flops += 3.0 * flops_factor(nk);
+        for (int jj = wid; jj < nk; jj += nw) {
+            F* colp = Lm + tri_off(jj, nk) - jj;
+            for (int ii = jj + lane; ii < nk; ii += LS) {
+                const F val = (F)entry(A, nullptr, 0.0, 0.0, ii, jj);
+                colp[ii] = val;
+                if (jj == 0) { pc[ii] = val; if (ii == 0) pc[nk] = (F)1 / val; }
+            }
+        }
+        __syncthreads();
+        int bad = 0;
+        for (int k = 0; k < nk; ++k) {
+            const F d = pc[k], dinv = pc[nk];
+            if (!(d > (F)0 && d < (F)1e30)) bad = 1;
+            for (int jj = wid; jj < nk; jj += nw) {
+                F* colp = Lm + tri_off(jj, nk) - jj;
+                const F pj = pc[jj] * dinv;
+                for (int ii = jj + lane; ii < nk; ii += LS) {
+                    F val;
+                    if (jj == k) val = (ii == k) ? -dinv : pc[ii] * dinv;
+                    else if (ii == k) val = pj;
+                    else val = colp[ii] - pc[ii] * pj;
+                    colp[ii] = val;
+                    if (jj == k + 1) { pcn[ii] = val; if (ii == k + 1) pcn[nk] = (F)1 / val; }
+                    else if (ii == k + 1) pcn[jj] = val;
+                }
+            }
+            __syncthreads();
+            F* t = pc; pc = pcn; pcn = t;
+        }
+        PH_ADD(10, ph_w);
+        return bad;
+    }
+
+    // Forward / backward substitution over the pivots 32 S .. 32 S + 31 for a system of NS row slots per lane
+    // (see warp_subst).  A single warp issues in order, so the cost per pivot is the instruction count of the
+    // loop body more than the 41-cycle shuffle + FMA chain: the loops carry no address arithmetic and one
+    // predicate.  q_j = Lm + tri_off(j) - j addresses column j by ROW (q_j[i] = L'(i, j)); it stays inside the
+    // packed factor for every row 0 <= i < nk -- also above the diagonal and for the column after the last --
+    // so every lane loads unconditionally (rows >= nk alias row nk - 1; their results are never used) and only
+    // the slot that contains the pivot masks its multiplier.  The entries of the next pivot are loaded before
+    // the current shuffle is consumed.
+    template <int S, int NS>
+    __device__ __forceinline__ void fwd_seg(int lane, int nk, const F*& q, F& b0, F& b1, F& b2) const {
+        const int jend = nk - 32 * S < 32 ? nk - 32 * S : 32;
+        const int e0 = lane < nk ? lane : nk - 1, e1 = lane + 32 < nk ? lane + 32 : nk - 1, e2 = lane + 64 < nk ? lane + 64 : nk - 1;
+        F& bs = S == 0 ? b0 : (S == 1 ? b1 : b2);
+        const int es = S == 0 ? e0 : (S == 1 ? e1 : e2);
+        F ls = q[es], l1 = (S < 1 && NS > 1) ? q[e1] : (F)0, l2 = (S < 2 && NS > 2) ? q[e2] : (F)0;
+#pragma unroll 4
+        for (int jj = 0; jj < jend; ++jj) {
+            q += nk - (32 * S + jj) - 1;                 // -> column j + 1
+            const F lsn = q[es];
+            const F l1n = (S < 1 && NS > 1) ? q[e1] : (F)0, l2n = (S < 2 && NS > 2) ? q[e2] : (F)0;
+            const F t = __shfl_sync(0xffffffffu, bs, jj);
+            bs -= (lane > jj ? ls : (F)0) * t;
+            if (S < 1 && NS > 1) b1 -= l1 * t;
+            if (S < 2 && NS > 2) b2 -= l2 * t;
+            ls = lsn; l1 = l1n; l2 = l2n;
+        }
+    }
+    // r_i = Lm + tri_off(i) - i addresses row i of L'^T by column: r_i[j] = L'(j, i), inside the factor for all j
+    template <int S>
+    __device__ __forceinline__ void bwd_seg(int lane, int nk, const F* r0, const F* r1, const F* r2, F& b0, F& b1, F& b2) const {
+        const int jtop = (nk < 32 * (S + 1) ? nk : 32 * (S + 1)) - 1;
+        const int jlow = S == 0 ? 1 : 32 * S;
+        F& bs = S == 0 ? b0 : (S == 1 ? b1 : b2);
+        const F* rs = S == 0 ? r0 : (S == 1 ? r1 : r2);
+        F ls = rs[jtop], l0 = S >= 1 ? r0[jtop] : (F)0, l1 = S >= 2 ? r1[jtop] : (F)0;
+#pragma unroll 4
+        for (int j = jtop; j >= jlow; --j) {
+            const int jn = j > 0 ? j - 1 : 0;
+            const F lsn = rs[jn];
+            const F l0n = S >= 1 ? r0[jn] : (F)0, l1n = S >= 2 ? r1[jn] : (F)0;
+            const F xj = __shfl_sync(0xffffffffu, bs, j & 31);
+            bs -= (lane < (j & 31) ? ls : (F)0) * xj;
+            if (S >= 1) b0 -= l0 * xj;
+            if (S >= 2) b1 -= l1 * xj;
+            ls = lsn; l0 = l0n; l1 = l1n;
+        }
+    }
+
+    // One warp's substitution  K out = b  (K = L' D L'^T, nk unknowns) in the factor's precision.  With map != null
+    // b and out are addressed through it (b[map[i]], out[map[i]]: full-index vectors of a compact system).
+    // Each lane keeps the right-hand-side entries of its rows (lane, lane+32, lane+64) in registers and the pivot
+    // entry is broadcast with a shuffle, so the dependency chain per column is one shuffle and one FMA.
+    __device__ inline void warp_subst(int lane, int LS, const double* b, double* out, const int* map, F* sc) const {
+        const int nk = nF + ng;
+#ifndef HMPC_HOST_EMUL
+        if (nk <= 96) {
+            const unsigned FULL = 0xffffffffu;
+            const int i0 = lane, i1 = lane + 32, i2 = lane + 64;
+            const int m0 = (map && i0 < nk) ? map[i0] : i0, m1 = (map && i1 < nk) ? map[i1] : i1, m2 = (map && i2 < nk) ? map[i2] : i2;
+            F b0 = i0 < nk ? (F)b[m0] : (F)0, b1 = i1 < nk ? (F)b[m1] : (F)0, b2 = i2 < nk ? (F)b[m2] : (F)0;
+            // The pivots are walked segment by segment (32 at a time): inside segment S the broadcast always comes
+            // from row slot S (no select on the dependency chain), slots below S are finished / untouched and are
+            // skipped, slots above S are fully active.  Inner loops are branch-free: an inactive lane loads a valid
+            // entry and multiplies by zero (a lane-dependent `if` costs a divergence / reconvergence pair per row
+            // and column -- measured 199 cycles per column, against 41 for the bare shuffle + FMA chain).
+            const F* q = Lm;                            // q[i] = L'(i, j), see fwd_seg
+            if (nk <= 32) fwd_seg<0, 1>(lane, nk, q, b0, b1, b2);          // L' y = b
+            else if (nk <= 64) { fwd_seg<0, 2>(lane, nk, q, b0, b1, b2); fwd_seg<1, 2>(lane, nk, q, b0, b1, b2); }
+            else { fwd_seg<0, 3>(lane, nk, q, b0, b1, b2); fwd_seg<1, 3>(lane, nk, q, b0, b1, b2); fwd_seg<2, 3>(lane, nk, q, b0, b1, b2); }
+            if (i0 < nk) b0 *= dinv[i0];                // z = D^-1 y
+            if (i1 < nk) b1 *= dinv[i1];
+            if (i2 < nk) b2 *= dinv[i2];
+            const int e0 = i0 < nk ? i0 : nk - 1, e1 = i1 < nk ? i1 : nk - 1, e2 = i2 < nk ? i2 : nk - 1;
+            const F* r0 = Lm + tri_off(e0, nk) - e0;    // r[j] = L'(j, i), see bwd_seg
+            const F* r1 = Lm + tri_off(e1, nk) - e1;
+            const F* r2 = Lm + tri_off(e2, nk) - e2;
+            if (nk > 64) bwd_seg<2>(lane, nk, r0, r1, r2, b0, b1, b2);   // L'^T x = z
+            if (nk > 32) bwd_seg<1>(lane, nk, r0, r1, r2, b0, b1, b2);
+            bwd_seg<0>(lane, nk, r0, r1, r2, b0, b1, b2);
+            if (i0 < nk) out[m0] = (double)b0;
+            if (i1 < nk) out[m1] = (double)b1;
+            if (i2 < nk) out[m2] = (double)b2;
+            return;
+        }
+#endif
+        for (int i = lane; i < nk; i += LS) sc[i] = (F)b[map ? map[i] : i];
+        __syncwarp();
+        for (int j = 0; j < nk; ++j) {            // L' y = b
+            const F t = sc[j];
+            const F* col = Lm + tri_off(j, nk) - j;
+            for (int i = j + 1 + lane; i < nk; i += LS) sc[i] -= col[i] * t;
+            __syncwarp();
+        }
+        for (int i = lane; i < nk; i += LS) sc[i] *= dinv[i];     // z = D^-1 y
+        __syncwarp();
+        for (int j = nk - 1; j > 0; --j) {        // L'^T x = z
+            const F xj = sc[j];
+            for (int i = lane; i < j; i += LS) sc[i] -= Lm[tri_off(i, nk) + (j - i)] * xj;
+            __syncwarp();
+        }
+        for (int i = lane; i < nk; i += LS) out[map ? map[i] : i] = (double)sc[i];
+    }
+
+    // Solves K out = b for compact FP64 vectors of length nk; b is left untouched unless out aliases it.
+    // One warp runs the (serial) substitution.  Starts and ends with a __syncthreads().
+    __device__ __noinline__ void solve(const double* b, double* out, double* scratch, const int* map = nullptr) {
         const int tid = threadIdx.x, T = blockDim.x, nk = nF + ng;
         const int LS = T < 32 ? T : 32;
         PH_T0(ph_s);
@@ -669,63 +837,34 @@ struct LinSys {
         // co-resident CTAs use different warp slots so that their substitutions land on different SM
         // sub-partitions (warp w lives on scheduler w % 4)
         const int w0 = (T / LS > 1) ? (solver_warp % (T / LS)) * LS : 0;
-        if (tid >= w0 && tid < w0 + LS) {
-            const int lane = tid - w0;
-#ifndef HMPC_HOST_EMUL
-            if (nk <= 96) {
-                const unsigned FULL = 0xffffffffu;
-                const int i0 = lane, i1 = lane + 32, i2 = lane + 64;
-                F b0 = i0 < nk ? (F)b[i0] : (F)0, b1 = i1 < nk ? (F)b[i1] : (F)0, b2 = i2 < nk ? (F)b[i2] : (F)0;
-                const F* col = Lm;                          // col[i - j] = L'(i, j)
-#pragma unroll 1
-                for (int j = 0; j < nk; ++j) {              // L' y = b
-                    const F src = j < 32 ? b0 : (j < 64 ? b1 : b2);
-                    const F t = __shfl_sync(FULL, src, j & 31);
-                    if (i0 > j && i0 < nk) b0 -= col[i0 - j] * t;
-                    if (i1 > j && i1 < nk) b1 -= col[i1 - j] * t;
-                    if (i2 > j && i2 < nk) b2 -= col[i2 - j] * t;
-                    col += nk - j;
-                }
-                if (i0 < nk) b0 *= dinv[i0];                // z = D^-1 y
-                if (i1 < nk) b1 *= dinv[i1];
-                if (i2 < nk) b2 *= dinv[i2];
-                const F* r0 = Lm + (i0 < nk ? tri_off(i0, nk) - i0 : 0);   // r[j] = L'(j, i), j > i
-                const F* r1 = Lm + (i1 < nk ? tri_off(i1, nk) - i1 : 0);
-                const F* r2 = Lm + (i2 < nk ? tri_off(i2, nk) - i2 : 0);
-#pragma unroll 1
-                for (int j = nk - 1; j > 0; --j) {          // L'^T x = z
-                    const F src = j < 32 ? b0 : (j < 64 ? b1 : b2);
-                    const F xj = __shfl_sync(FULL, src, j & 31);
-                    if (i0 < j) b0 -= r0[j] * xj;
-                    if (i1 < j) b1 -= r1[j] * xj;
-                    if (i2 < j) b2 -= r2[j] * xj;
-                }
-                if (i0 < nk) out[i0] = (double)b0;
-                if (i1 < nk) out[i1] = (double)b1;
-                if (i2 < nk) out[i2] = (double)b2;
-            } else
-#endif
-            {
-                for (int i = lane; i < nk; i += LS) sc[i] = (F)b[i];
+        if (tid >= w0 && tid < w0 + LS) warp_subst(tid - w0, LS, b, out, map, reinterpret_cast<F*>(scratch));
+        __syncthreads();
+        PH_ADD(5, ph_s);
+    }
+
+    // nrhs systems at once, in place: column q is the full-index vector cols + slot[q] * ld (addressed through
+    // map, see warp_subst).  The warps of the CTA take the columns round-robin, so up to T/32 substitutions run
+    // concurrently on the same factor.  Needs nk <= 96 unless the CTA has a single warp (no per-warp scratch).
+    __device__ __noinline__ void solve_columns(int nrhs, double* cols, int ld, const int* slot, const int* map, double* scratch) {
+        const int tid = threadIdx.x, T = blockDim.x, nk = nF + ng;
+        const int LS = T < 32 ? T : 32, nw = T / LS, wid = tid / LS, lane = tid % LS;
+        PH_T0(ph_s);
+        flops += nrhs * flops_solve(nk);
+        __syncthreads();
+        if (nk <= 96) {
+            for (int q = (wid + solver_warp) % nw; q < nrhs; q += nw) {
+                double* v = cols + (size_t)slot[q] * ld;
+                warp_subst(lane, LS, v, v, map, reinterpret_cast<F*>(scratch));
+            }
+        } else if (wid == 0) {
+            for (int q = 0; q < nrhs; ++q) {
+                double* v = cols + (size_t)slot[q] * ld;
+                warp_subst(lane, LS, v, v, map, reinterpret_cast<F*>(scratch));
                 __syncwarp();
-                for (int j = 0; j < nk; ++j) {            // L' y = b
-                    const F t = sc[j];
-                    const F* col = Lm + tri_off(j, nk) - j;
-                    for (int i = j + 1 + lane; i < nk; i += LS) sc[i] -= col[i] * t;
-                    __syncwarp();
-                }
-                for (int i = lane; i < nk; i += LS) sc[i] *= dinv[i];     // z = D^-1 y
-                __syncwarp();
-                for (int j = nk - 1; j > 0; --j) {        // L'^T x = z
-                    const F xj = sc[j];
-                    for (int i = lane; i < j; i += LS) sc[i] -= Lm[tri_off(i, nk) + (j - i)] * xj;
-                    __syncwarp();
-                }
-                for (int i = lane; i < nk; i += LS) out[i] = (double)sc[i];
             }
         }
         __syncthreads();
-        PH_ADD(5, ph_s);
+        PH_ADD(12, ph_s);
     }
 };
 
@@ -746,7 +885,7 @@ __device__ __forceinline__ double sym_row_dot(const double* H, int n, int i, int
     return acc;
 }
 template <class Sys>
-__device__ inline void sym_matvec(const double* H, int n, const double* x, double* out, Sys* acct) {
+__device__ __noinline__ void sym_matvec(const double* H, int n, const double* x, double* out, Sys* acct) {
     if (acct) acct->flops += flops_matvec(n);
     const int tid = threadIdx.x, T = blockDim.x;
     if (T >= 2 * n) {
@@ -766,6 +905,82 @@ struct SolveInfo { int status, iters, nfac, path; double rho; };
 
 
 // ------------------------------------------------------------------------------------------------
+// KKT test of the ORIGINAL QP at (w.xp, mul) for the active set w.code, shared by the two active-set
+// refinements below.  mul holds the multipliers of the active general rows and zeros on the box rows; the
+// multipliers of the pinned variables are taken from the gradient.  hx_current: w.tmp == H xp already.
+// Returns 1: accepted (w.x <- xp, mul final), 0: give up, 2: w.code was refined (wrong-signed rows released,
+// or -- only when no row was wrong-signed -- violated rows activated), try again.
+// ------------------------------------------------------------------------------------------------
+template <class Sys>
+__device__ inline int verify_active_set(const QpConst& c, Work& w, Sys& sys, const AOp& A, double* mul, const double* bnd,
+                                        bool hx_current) {
+    const int N = c.N, n = 6 * N, m = 11 * N, tid = threadIdx.x, T = blockDim.x;
+    const double tol = c.polish_tol;
+    PH_T0(ph_v);
+    {
+        // ---- pass 1: multipliers of pinned variables, scales ----
+        if (!hx_current) {
+            sym_matvec(w.H, n, w.xp, w.tmp, &sys);
+            __syncthreads();
+        }
+        double v[3] = {0, 0, 0};   // stat, scale, |mult|
+        for (int i = tid; i < n; i += T) {
+            const double aty = A.colT(i, mul);   // mul[i] == 0 on box rows at this point
+            const double G = w.tmp[i] + w.g[i] + aty;
+            v[1] = fmax(v[1], fmax(fabs(w.tmp[i]), fmax(fabs(w.g[i]), fabs(aty))));
+            if (!w.pin[i]) v[0] = fmax(v[0], fabs(G));
+            else { w.sc[i] = -G; v[2] = fmax(v[2], fabs(G)); }
+        }
+        for (int r = n + tid; r < m; r += T) if (w.code[r]) v[2] = fmax(v[2], fabs(mul[r]));
+        block_reduce<3, 0>(v, w.red);
+        for (int i = tid; i < n; i += T) mul[i] = w.pin[i] ? w.sc[i] : 0.0;
+        __syncthreads();
+        const double scale = fmax(1.0, v[1]);
+        const double stol = tol * fmax(scale, v[2]);
+        // ---- pass 2: per-row verdicts and the refined active set ----
+        // Rows whose multiplier has the wrong sign are released first; violated rows are only activated by
+        // a trial that had no wrong-signed row (measured: fewer trials and fewer give-ups than doing both at
+        // once).  w.side (interior-point scratch) holds the proposed change: 1 release, 2 / 3 activate lower / upper.
+        int bad = (v[0] <= 1e-10 * scale) ? 0 : 1, anywrong = 0;
+        if (!(v[0] == v[0]) || !(v[2] == v[2])) bad = 2;
+        for (int r = tid; r < m; r += T) {
+            const double ax = A.row(r, w.xp), lo = w.lo[r], hi = w.hi[r];
+            const int cd = w.code[r];
+            const bool apriori = (r < n) && w.fixed[r];
+            int change = 0;
+            if (cd != 0) {
+                const double lam = mul[r];
+                if ((cd > 0 && lam < -stol) || (cd < 0 && lam > stol)) { change = 1; bad |= 1; anywrong = 1; }
+                if (r >= n && fabs(ax - bnd[r]) > tol * (1.0 + fabs(bnd[r]))) bad |= 1;   // singular / inconsistent set
+            } else if (!apriori) {
+                if (lo - ax > tol * (1.0 + fabs(lo))) { change = 2; bad |= 1; }
+                else if (ax - hi > tol * (1.0 + fabs(hi))) { change = 3; bad |= 1; }
+            }
+            w.side[r] = (int8_t)change;
+        }
+        bad = __syncthreads_or(bad);
+        anywrong = __syncthreads_or(anywrong);
+        if (!bad) {
+            for (int i = tid; i < n; i += T) w.x[i] = w.xp[i];
+            for (int r = n + tid; r < m; r += T) if (!w.code[r]) mul[r] = 0.0;
+            __syncthreads();
+            PH_ADD(7, ph_v);
+            return 1;
+        }
+        int changed = 0;
+        for (int r = tid; r < m; r += T) {
+            const int change = w.side[r];
+            if (change == 1) { w.code[r] = 0; changed = 1; }
+            else if (change >= 2 && !anywrong) { w.code[r] = (int8_t)(change == 2 ? -1 : 1); changed = 1; }
+        }
+        changed = __syncthreads_or(changed);
+        PH_ADD(7, ph_v);
+        if (!changed || (bad & 2)) return 0;
+    }
+    return 2;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Verified primal-dual active-set refinement (numpy statement: oracle/device_port.py polish_verified).
 //
 // w.code holds the active-set guess, w.xp the starting point.  Box-active and a-priori fixed variables
@@ -781,7 +996,6 @@ struct SolveInfo { int status, iters, nfac, path; double rho; };
 template <class Sys>
 __device__ inline int polish_verified(const QpConst& c, Work& w, Sys& sys, const AOp& A, SolveInfo& info) {
     const int N = c.N, n = 6 * N, m = 11 * N, tid = threadIdx.x, T = blockDim.x;
-    const double tol = c.polish_tol;
     double* mul = w.mv[0];
     double* bnd = w.mv[1];
     for (int r = tid; r < m; r += T) {
@@ -852,64 +1066,239 @@ __device__ inline int polish_verified(const QpConst& c, Work& w, Sys& sys, const
             __syncthreads();
         }
         PH_ADD(6, ph_rf);
-        PH_T0(ph_v);
-        // ---- pass 1: multipliers of pinned variables, scales ----
-        if (!hx_current) {
+        const int verdict = verify_active_set(c, w, sys, A, mul, bnd, hx_current);
+        if (verdict != 2) return verdict;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Active-set refinement on ONE inversion per QP (FP64 only).
+//
+// At the optimum of these QPs only a handful of constraints are active (measured on closed-loop batches:
+// 1.6 box bounds and 0.5 friction / height rows on average, 11 at most), but the set changes a little from
+// tick to tick, and every change cost polish_verified a new factorisation of the whole KKT matrix.  Here the
+// Hessian of ALL non-fixed variables, H_vv, is inverted once per QP (LinSys::sweep_invert: one pass and one
+// barrier per pivot, no serial chain); every active constraint -- a box bound e_j or a friction / height row --
+// is a row of G, and the KKT system
+//      [ H_vv  G' ] [dx]   [rd]
+//      [ G    -E  ] [dl] = [rp]
+// is solved through the small Schur complement  S = G W,  W = H_vv^-1 G'  (one matrix-vector product per
+// constraint; columns are kept while their row stays active):
+//      t = H_vv^-1 rd,   S dl = G t - rp,   dx = t - W dl.
+// S (at most 16 x 16) is factorised by one warp; a pivot below 1e-7 of its diagonal entry (dependent rows,
+// e.g. both friction rows of a stage whose fz sits at 0) is replaced by that floor and the correction-form
+// refinement removes the perturbation.  Trial logic, stopping rules and the KKT test of the original QP
+// are those of polish_verified (verify_active_set).  Returns 0 without a verdict when the active set does
+// not fit; the caller then falls back to the interior point / polish_verified.
+// On entry w.xp = starting point, w.code = active-set guess.  Uses w.mv[2..10] (W), w.grow, w.xt, w.rhs, w.sc
+// and the unused tail of the factor storage (S); w.x is only written on success.
+// ------------------------------------------------------------------------------------------------
+template <class Sys>
+__device__ inline int polish_schur(const QpConst& c, Work& w, Sys& sys, const AOp& A, SolveInfo& info) {
+    constexpr int CAP = 16;
+    if (sizeof(typename Sys::real) != 8) return 0;
+    const int N = c.N, n = 6 * N, m = 11 * N, tid = threadIdx.x, T = blockDim.x;
+    const int LS = T < 32 ? T : 32;
+    if (kkt_max(N) < 3 * CAP) return 0;
+    double* mul = w.mv[0];
+    double* bnd = w.mv[1];
+    double* Wm = w.mv[2];                      // [CAP][n], full variable index, zero at fixed variables
+    int *prow = w.grow, *newrows = w.grow + CAP, *freeslots = w.grow + 2 * CAP;
+#if HMPC_SCHUR == 1
+    double *rp = w.sc, *dl = w.sc + CAP, *dref = w.sc + 2 * CAP;         // w.dinv belongs to the factor
+#else
+    double *rp = w.dinv, *dl = w.dinv + CAP, *dref = w.dinv + 2 * CAP;   // w.sc receives the matrix-vector products
+#endif
+    double* tf = w.xt;                         // H_vv^-1 rd in full variable index (kkt_max >= n)
+    for (int r = tid; r < m; r += T) {
+        int cd = w.code[r];
+        if (cd > 0 && w.hi[r] > kInfThresh) cd = 0;
+        if (cd < 0 && w.lo[r] < -kInfThresh) cd = 0;
+        if (r < n && w.fixed[r]) cd = 0;
+        w.code[r] = (int8_t)cd;
+    }
+    for (int p = tid; p < CAP; p += T) prow[p] = -1;
+    compact_indices(0, n, n, w.idx, w.cnt + 0, [&](int i) { return w.fixed[i] == 0; });
+    __syncthreads();
+    const int nv = w.cnt[0];
+    const int kk = kkt_max(N);
+    if (kk * (kk + 1) / 2 - nv * (nv + 1) / 2 < CAP * CAP) return 0;
+    double* Sm = reinterpret_cast<double*>(sys.Lm) + (size_t)nv * (nv + 1) / 2;   // [CAP][CAP], lower triangle used
+    sys.nF = nv; sys.ng = 0;
+    ++info.nfac;
+#if HMPC_SCHUR == 1
+    if (sys.factor(A, nullptr, 0.0, 0.0, w.tmp)) return 0;
+#else
+    if (sys.sweep_invert(A, w.tmp)) return 0;
+    const double* Minv = reinterpret_cast<const double*>(sys.Lm);     // -H_vv^-1, packed, compact index
+#endif
+    for (int i = tid; i < n; i += T) tf[i] = 0.0;      // after sweep_invert(): its scratch spans tmp | xt
+    for (int trial = 0; trial <= c.retries; ++trial) {
+        PH_T0(ph_b);
+        for (int r = tid; r < m; r += T) {
+            const int cd = w.code[r];
+            bnd[r] = cd < 0 ? w.lo[r] : w.hi[r];
+            mul[r] = 0.0;
+            if (r < n) {
+                const int pin = (w.fixed[r] || cd != 0) ? 1 : 0;
+                w.pin[r] = (int8_t)pin;
+                if (pin) w.xp[r] = w.fixed[r] ? 0.0 : bnd[r];
+            }
+        }
+        for (int p = tid; p < CAP; p += T) { const int r = prow[p]; if (r >= 0 && w.code[r] == 0) prow[p] = -1; }
+        __syncthreads();
+        // ---- columns of W for the rows that became active ----
+        compact_indices(0, m, CAP, newrows, w.cnt + 2, [&](int r) {
+            if (w.code[r] == 0) return false;
+            for (int p = 0; p < CAP; ++p) if (prow[p] == r) return false;
+            return true;
+        });
+        compact_indices(0, CAP, CAP, freeslots, w.cnt + 3, [&](int p) { return prow[p] < 0; });
+        __syncthreads();
+        const int nn = w.cnt[2];
+        if (nn > w.cnt[3]) return 0;           // more active rows than columns
+#if HMPC_SCHUR == 1
+        for (int e = tid; e < nn * n; e += T) {
+            const int q = e / n, v = e - q * n, r = newrows[q];
+            Wm[(size_t)freeslots[q] * n + v] = w.fixed[v] ? 0.0 : (r < n ? (v == r ? 1.0 : 0.0) : A.coef(r, v));
+        }
+        if (nn > 0) sys.solve_columns(nn, Wm, n, freeslots, w.idx, w.rhs);
+#else
+        for (int q = 0; q < nn; ++q) {
+            const int r = newrows[q];
+            double* col = Wm + (size_t)freeslots[q] * n;
+            for (int i = tid; i < nv; i += T) { const int v = w.idx[i]; w.rhs[i] = r < n ? (v == r ? 1.0 : 0.0) : A.coef(r, v); }
+            for (int v = tid; v < n; v += T) if (w.fixed[v]) col[v] = 0.0;
+            __syncthreads();
+            sym_matvec(Minv, nv, w.rhs, w.sc, &sys);
+            __syncthreads();
+            for (int i = tid; i < nv; i += T) col[w.idx[i]] = -w.sc[i];
+        }
+#endif
+        for (int q = tid; q < nn; q += T) prow[freeslots[q]] = newrows[q];
+        __syncthreads();
+        int ns = 0;
+        for (int p = 0; p < CAP; ++p) if (prow[p] >= 0) ns = p + 1;
+        // ---- S = G W, factorised by one warp ----
+        for (int e = tid; e < ns * ns; e += T) {
+            const int a = e / ns, b = e - a * ns;
+            if (b > a) continue;
+            const int ra = prow[a], rb = prow[b];
+            const double sv = (ra < 0 || rb < 0) ? (a == b ? 1.0 : 0.0) : A.row(ra, Wm + (size_t)b * n);
+            Sm[a * CAP + b] = sv;
+            if (a == b) dref[a] = ra < 0 ? 1.0 : sv;    // 0: a row without any non-fixed variable (decoupled)
+        }
+        __syncthreads();
+        int regularised = 0;
+        if (tid < LS) {
+            const int lane = tid;
+            for (int j = 0; j < ns; ++j) {
+                double d = Sm[j * CAP + j];
+                const double dr = dref[j];
+                if (!(dr > 0.0)) { d = 1.0; }
+                else if (!(d > 1e-7 * dr)) { d = 1e-7 * dr; regularised = 1; }
+                __syncwarp();
+                if (lane == 0) Sm[j * CAP + j] = d;
+                const double di = 1.0 / d;
+                const int t = ns - j - 1;
+                for (int e = lane; e < t * t; e += LS) {          // trailing update with the unscaled column
+                    const int i = j + 1 + e / t, k = j + 1 + e % t;
+                    if (k <= i) Sm[i * CAP + k] -= Sm[i * CAP + j] * di * Sm[k * CAP + j];
+                }
+                __syncwarp();
+                for (int i = j + 1 + lane; i < ns; i += LS) Sm[i * CAP + j] *= di;   // unit lower L
+                __syncwarp();
+            }
+        }
+        regularised = __syncthreads_or(regularised);
+        sys.flops += (double)ns * ns * ns / 3.0 + 2.0 * ns * ns * 3;
+        PH_ADD(11, ph_b);
+        PH_T0(ph_rf);
+        // ---- correction-form refinement ----
+        double prev = 1e300;
+        bool hx_current = false;
+        for (int k = 0; k < c.max_refine; ++k) {
             sym_matvec(w.H, n, w.xp, w.tmp, &sys);
             __syncthreads();
-        }
-        double v[3] = {0, 0, 0};   // stat, scale, |mult|
-        for (int i = tid; i < n; i += T) {
-            const double aty = A.colT(i, mul);   // mul[i] == 0 on box rows at this point
-            const double G = w.tmp[i] + w.g[i] + aty;
-            v[1] = fmax(v[1], fmax(fabs(w.tmp[i]), fmax(fabs(w.g[i]), fabs(aty))));
-            if (!w.pin[i]) v[0] = fmax(v[0], fabs(G));
-            else { w.sc[i] = -G; v[2] = fmax(v[2], fabs(G)); }
-        }
-        for (int r = n + tid; r < m; r += T) if (w.code[r]) v[2] = fmax(v[2], fabs(mul[r]));
-        block_reduce<3, 0>(v, w.red);
-        for (int i = tid; i < n; i += T) mul[i] = w.pin[i] ? w.sc[i] : 0.0;
-        __syncthreads();
-        const double scale = fmax(1.0, v[1]);
-        const double stol = tol * fmax(scale, v[2]);
-        // ---- pass 2: per-row verdicts and the refined active set ----
-        // Rows whose multiplier has the wrong sign are released first; violated rows are only activated by
-        // a trial that had no wrong-signed row (measured: fewer trials and fewer give-ups than doing both at
-        // once).  w.side (interior-point scratch) holds the proposed change: 1 release, 2 / 3 activate lower / upper.
-        int bad = (v[0] <= 1e-10 * scale) ? 0 : 1, anywrong = 0;
-        if (!(v[0] == v[0]) || !(v[2] == v[2])) bad = 2;
-        for (int r = tid; r < m; r += T) {
-            const double ax = A.row(r, w.xp), lo = w.lo[r], hi = w.hi[r];
-            const int cd = w.code[r];
-            const bool apriori = (r < n) && w.fixed[r];
-            int change = 0;
-            if (cd != 0) {
-                const double lam = mul[r];
-                if ((cd > 0 && lam < -stol) || (cd < 0 && lam > stol)) { change = 1; bad |= 1; anywrong = 1; }
-                if (r >= n && fabs(ax - bnd[r]) > tol * (1.0 + fabs(bnd[r]))) bad |= 1;   // singular / inconsistent set
-            } else if (!apriori) {
-                if (lo - ax > tol * (1.0 + fabs(lo))) { change = 2; bad |= 1; }
-                else if (ax - hi > tol * (1.0 + fabs(hi))) { change = 3; bad |= 1; }
+            double v[2] = {0.0, 0.0};
+            for (int i = tid; i < nv; i += T) {
+                const int vi = w.idx[i];
+                const double aty = A.colT(vi, mul);
+                const double r_ = -(w.tmp[vi] + w.g[vi] + aty);
+#if HMPC_SCHUR == 1
+                tf[vi] = r_;
+#else
+                w.rhs[i] = r_;
+#endif
+                v[0] = fmax(v[0], fabs(r_));
+                v[1] = fmax(v[1], fabs(r_) / (fabs(w.tmp[vi]) + fabs(w.g[vi]) + fabs(aty) + 1e-300));
             }
-            w.side[r] = (int8_t)change;
-        }
-        bad = __syncthreads_or(bad);
-        anywrong = __syncthreads_or(anywrong);
-        if (!bad) {
-            for (int i = tid; i < n; i += T) w.x[i] = w.xp[i];
-            for (int r = n + tid; r < m; r += T) if (!w.code[r]) mul[r] = 0.0;
+            for (int p = tid; p < ns; p += T) {
+                const int rr = prow[p];
+                double r_ = 0.0;
+                if (rr >= 0 && dref[p] > 0.0) {
+                    const double ax = A.row(rr, w.xp);
+                    r_ = bnd[rr] - ax;
+                    v[1] = fmax(v[1], fabs(r_) / (fabs(bnd[rr]) + fabs(ax) + 1e-300));
+                }
+                rp[p] = r_;
+                v[0] = fmax(v[0], fabs(r_));
+            }
+            block_reduce<2, 0>(v, w.red);
+            if (!(v[0] == v[0])) return 0;
+#if HMPC_SCHUR == 1
+            if (k == 1 && !regularised && v[0] <= 1e-7 * prev) { hx_current = true; break; }   // backward-stable solve
+#endif
+            if (k >= 1 && (v[1] <= 1e-12 || (k >= 2 && v[0] > c.stagnation * prev))) { hx_current = true; break; }
+            prev = v[0];
+#if HMPC_SCHUR == 1
+            sys.solve(tf, tf, w.rhs, w.idx);
+#else
+            sym_matvec(Minv, nv, w.rhs, w.sc, &sys);
             __syncthreads();
-            return 1;
+            for (int i = tid; i < nv; i += T) tf[w.idx[i]] = -w.sc[i];
+            __syncthreads();
+#endif
+            if (ns > 0) {
+                for (int p = tid; p < ns; p += T) {
+                    const int rr = prow[p];
+                    dl[p] = (rr >= 0 && dref[p] > 0.0) ? A.row(rr, tf) - rp[p] : 0.0;
+                }
+                __syncthreads();
+                if (tid < LS) {
+                    const int lane = tid;
+                    for (int j = 0; j < ns; ++j) {                 // L z = b
+                        __syncwarp();
+                        const double t = dl[j];
+                        for (int i = j + 1 + lane; i < ns; i += LS) dl[i] -= Sm[i * CAP + j] * t;
+                    }
+                    __syncwarp();
+                    for (int i = lane; i < ns; i += LS) dl[i] /= Sm[i * CAP + i];
+                    for (int j = ns - 1; j > 0; --j) {             // L' y = z
+                        __syncwarp();
+                        const double t = dl[j];
+                        for (int i = lane; i < j; i += LS) dl[i] -= Sm[j * CAP + i] * t;
+                    }
+                }
+                __syncthreads();
+            }
+            for (int i = tid; i < nv; i += T) {
+                const int vi = w.idx[i];
+                if (w.pin[vi]) continue;                           // stays exactly at its bound
+                double dx = tf[vi];
+                for (int p = 0; p < ns; ++p) if (prow[p] >= 0) dx -= Wm[(size_t)p * n + vi] * dl[p];
+                w.xp[vi] += dx;
+            }
+            for (int p = tid; p < ns; p += T) if (prow[p] >= 0) mul[prow[p]] += dl[p];
+            sys.flops += 2.0 * nv * ns + 2.0 * ns * ns;
+            __syncthreads();
         }
-        int changed = 0;
-        for (int r = tid; r < m; r += T) {
-            const int change = w.side[r];
-            if (change == 1) { w.code[r] = 0; changed = 1; }
-            else if (change >= 2 && !anywrong) { w.code[r] = (int8_t)(change == 2 ? -1 : 1); changed = 1; }
-        }
-        changed = __syncthreads_or(changed);
-        PH_ADD(7, ph_v);
-        if (!changed || (bad & 2)) return 0;
+        PH_ADD(6, ph_rf);
+        for (int i = tid; i < n; i += T) mul[i] = 0.0;    // the box multipliers are re-derived from the gradient
+        __syncthreads();
+        const int verdict = verify_active_set(c, w, sys, A, mul, bnd, hx_current);
+        if (verdict != 2) return verdict;
     }
     return 0;
 }
@@ -1124,25 +1513,35 @@ template <class Sys>
 __device__ inline SolveInfo solve_exact(const QpConst& c, Work& w, Sys& sys, const AOp& A, int warm) {
     const int n = 6 * c.N, tid = threadIdx.x, T = blockDim.x;
     SolveInfo info{ST_MAX_ITER, 0, 0, PATH_NONE, 0.0};
-    if (warm) {
-        if (polish_verified(c, w, sys, A, info)) { info.status = ST_SOLVED; info.path = PATH_WARM; return info; }
+    // FP64: the single-factorisation refinement first; polish_verified only after the interior point when the
+    // active set does not fit it.  FP32 factor: polish_verified (its refinement copes with the FP32 factor).
+    const bool schur = HMPC_SCHUR != 0 && sizeof(typename Sys::real) == 8;
+    int conv = 0;
+    for (int stage = warm ? 0 : 1; stage < 2; ++stage) {
+        if (stage == 1) {
+            conv = ipm_solve(c, w, sys, A, info);
+            int nonfinite = 0;
+            for (int i = tid; i < n; i += T) {
+                const double v = w.x[i];
+                if (!(fabs(v) < 1e300)) nonfinite = 1;
+                w.xp[i] = v;
+            }
+            nonfinite = __syncthreads_or(nonfinite);
+            if (nonfinite) {
+                for (int i = tid; i < n; i += T) w.x[i] = 0.0;
+                __syncthreads();
+                info.status = ST_NON_FINITE; info.path = PATH_IPM;
+                return info;
+            }
+        }
+        int ok = schur ? polish_schur(c, w, sys, A, info) : 0;
+        if (!ok && (!schur || stage == 1)) {
+            __syncthreads();
+            ok = polish_verified(c, w, sys, A, info);
+        }
+        if (ok) { info.status = ST_SOLVED; info.path = stage ? PATH_IPM_POLISH : PATH_WARM; return info; }
         __syncthreads();
     }
-    const int conv = ipm_solve(c, w, sys, A, info);
-    int nonfinite = 0;
-    for (int i = tid; i < n; i += T) {
-        const double v = w.x[i];
-        if (!(fabs(v) < 1e300)) nonfinite = 1;
-        w.xp[i] = v;
-    }
-    nonfinite = __syncthreads_or(nonfinite);
-    if (nonfinite) {
-        for (int i = tid; i < n; i += T) w.x[i] = 0.0;
-        __syncthreads();
-        info.status = ST_NON_FINITE; info.path = PATH_IPM;
-        return info;
-    }
-    if (polish_verified(c, w, sys, A, info)) { info.status = ST_SOLVED; info.path = PATH_IPM_POLISH; return info; }
     info.status = conv ? ST_INEXACT : ST_MAX_ITER;
     info.path = PATH_IPM;
     return info;

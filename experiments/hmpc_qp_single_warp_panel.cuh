@@ -576,6 +576,7 @@ struct LinSys {
         F* P = reinterpret_cast<F*>(scratch);
         const int tid = threadIdx.x, T = blockDim.x, nk = nF + ng;
         const int LS = T < 32 ? T : 32, lane = tid % LS, wid = tid / LS, nw = T / LS;
+        const int pw = solver_warp % nw;     // the warp that runs the panels (differs between co-resident CTAs)
         flops += flops_factor(nk);
         // ---- assemble the lower triangle (packed, column by column); entries are formed in FP64 ----
         for (int jj = wid; jj < nk; jj += nw) {          // warp per column, lane per row: no index division
@@ -593,27 +594,33 @@ struct LinSys {
                 for (int r = tid; r < ng; r += T) Lm[tri_off(nF + r, nk)] *= (F)(1.0 + eps);
                 __syncthreads();
             }
-            // panel: eliminate column j inside the panel only; keep P[i - t0][p] = U(i, j) / d_j for the rows below
-            for (int p = 0; p < bs; ++p) {
-                const int j = j0 + p;
-                const F* colj = Lm + tri_off(j, nk) - j;      // colj[i] = U(i, j), i >= j
-                const F piv = colj[j];
-                const F ap = (j < nF) ? piv : -piv;
-                const bool ok = (ap > (F)0) && (ap < (F)1e30);
-                if (!ok) bad = 1;
-                const F rinv = (F)1 / (ok ? piv : (F)1);
-                if (tid == 0) dinv[j] = rinv;
-                for (int i = j + 1 + tid; i < nk; i += T) {
-                    const F uij = colj[i];
-                    if (i >= t0) {
-                        P[4 * (i - t0) + p] = uij * rinv;
-                        if (p == bs - 1) for (int pp = bs; pp < 4; ++pp) P[4 * (i - t0) + pp] = (F)0;   // short block
+            // panel: eliminate column j inside the panel only; keep P[i - t0][p] = U(i, j) / d_j for the rows below.
+            // ONE warp runs the whole panel (at most 4 columns, lane per row) with warp-level syncs: a
+            // __syncwarp() per column instead of a CTA barrier (the barriers were the two hottest lines of the
+            // kernel); the other warps wait at the single barrier behind the panel.
+            if (wid == pw) {
+                for (int p = 0; p < bs; ++p) {
+                    const int j = j0 + p;
+                    const F* colj = Lm + tri_off(j, nk) - j;      // colj[i] = U(i, j), i >= j
+                    const F piv = colj[j];
+                    const F ap = (j < nF) ? piv : -piv;
+                    const bool ok = (ap > (F)0) && (ap < (F)1e30);
+                    if (!ok) bad = 1;
+                    const F rinv = (F)1 / (ok ? piv : (F)1);
+                    if (lane == 0) dinv[j] = rinv;
+                    for (int i = j + 1 + lane; i < nk; i += LS) {
+                        const F uij = colj[i];
+                        if (i >= t0) {
+                            P[4 * (i - t0) + p] = uij * rinv;
+                            if (p == bs - 1) for (int pp = bs; pp < 4; ++pp) P[4 * (i - t0) + pp] = (F)0;   // short block
+                        }
+                        for (int k = j + 1; k < t0 && k <= i; ++k)
+                            Lm[tri_off(k, nk) + (i - k)] -= uij * (colj[k] * rinv);
                     }
-                    for (int k = j + 1; k < t0 && k <= i; ++k)
-                        Lm[tri_off(k, nk) + (i - k)] -= uij * (colj[k] * rinv);
+                    __syncwarp();
                 }
-                __syncthreads();
             }
+            __syncthreads();
             // trailing matrix: rank-4 update.  Lanes own row pairs (short row t0+q, long row nk-1-q: equal
             // work per lane, consecutive addresses across lanes), warps own the columns k = t0 + wid (mod nw).
             const int t = nk - t0;
@@ -649,7 +656,7 @@ struct LinSys {
             const F dj = dinv[jj];
             for (int ii = jj + 1 + lane; ii < nk; ii += LS) colp[ii] *= dj;
         }
-        __syncthreads();
+        bad = __syncthreads_or(bad);         // only the panel warp has seen the pivots
         PH_ADD(4, ph_f);
         return bad;
     }

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhmpc_b200.so")
+LIB_PATH = os.environ.get("HMPC_LIB_PATH") or os.path.join(_HERE, "libhmpc_b200.so")   # override: experiment builds (tools/)
 
 HMPC_ABI_VERSION = 1
 HMPC_INF = 1e30
@@ -38,7 +38,7 @@ class HmpcConfig(C.Structure):
         ("solver", C.c_int32), ("mode", C.c_int32), ("max_iter", C.c_int32), ("check_interval", C.c_int32),
         ("first_check", C.c_int32), ("polish", C.c_int32), ("adaptive_rho", C.c_int32),
         ("warm_start", C.c_int32), ("polish_retries", C.c_int32), ("ipm_max_iter", C.c_int32),
-        ("on_infeasible", C.c_int32), ("reserved0", C.c_int32),
+        ("on_infeasible", C.c_int32), ("sqp_sweeps", C.c_int32),
         ("mpc_dt", C.c_double), ("sim_dt", C.c_double), ("m", C.c_double), ("g", C.c_double),
         ("mu", C.c_double), ("J", C.c_double * 9), ("Jinv", C.c_double * 9), ("rh", C.c_double * 3),
         ("tau_max", C.c_double * 3), ("fz_max", C.c_double), ("z_min", C.c_double), ("kf", C.c_double),

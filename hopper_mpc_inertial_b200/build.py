@@ -26,12 +26,13 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
-def build_lib(force=False, verbose=False):
+def build_lib(force=False, verbose=False, out=None):
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in DEPS):
         return OUT
     os.makedirs(OBJ_DIR, exist_ok=True)
     nvcc = _nvcc()
     extra = ["-Xptxas", "-v"] if verbose else []
+    extra += os.environ.get("HMPC_EXTRA_NVCC_FLAGS", "").split()     # experiments: -DHMPC_PHASE_TIMING ...
 
     def compile_unit(u):
         obj = os.path.join(OBJ_DIR, u.replace(".cu", ".o"))

@@ -245,7 +245,7 @@ hmpc::QpConst make_qp_const(const hmpc_config& cfg) {
     c.N = cfg.N; c.dyn = cfg.dyn; c.uref_mode = cfg.uref_mode; c.solver = cfg.solver; c.mode = cfg.mode;
     c.max_iter = cfg.max_iter; c.check = cfg.check_interval; c.first_check = cfg.first_check;
     c.retries = cfg.polish_retries; c.adaptive_rho = cfg.adaptive_rho; c.warm_start = cfg.warm_start;
-    c.polish = cfg.polish; c.ipm_max_iter = cfg.ipm_max_iter;
+    c.polish = cfg.polish; c.ipm_max_iter = cfg.ipm_max_iter; c.sqp_sweeps = cfg.sqp_sweeps > 1 ? cfg.sqp_sweeps : 1;
     c.dt = cfg.mpc_dt; c.m = cfg.m; c.g = cfg.g; c.mu = cfg.mu;
     for (int i = 0; i < 9; ++i) c.Jinv[i] = cfg.Jinv[i];
     for (int i = 0; i < 3; ++i) { c.rh[i] = cfg.rh[i]; c.tau_max[i] = cfg.tau_max[i]; }
@@ -304,7 +304,7 @@ int hmpc_default_config(hmpc_config* cfg) {
     cfg->solver = HMPC_SOLVER_EXACT; cfg->mode = HMPC_MODE_EARLY_EXIT;
     cfg->max_iter = 10000; cfg->check_interval = 25; cfg->first_check = 25; cfg->polish = 1;   // cvxpy -> OSQP
     cfg->adaptive_rho = 1; cfg->warm_start = 1; cfg->polish_retries = 8; cfg->ipm_max_iter = 40;
-    cfg->on_infeasible = HMPC_INFEASIBLE_HOLD;
+    cfg->on_infeasible = HMPC_INFEASIBLE_HOLD; cfg->sqp_sweeps = 1;
     cfg->mpc_dt = 0.02; cfg->sim_dt = 1e-3; cfg->m = 7.5; cfg->g = 9.807; cfg->mu = 1.0;
     const double J[9] = {76148072.89e-9, 70089.52e-9, 2067970.36e-9, 70089.52e-9, 45477183.53e-9,
                          -87045.58e-9, 2067970.36e-9, -87045.58e-9, 76287220.47e-9};

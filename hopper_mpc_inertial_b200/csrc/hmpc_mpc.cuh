@@ -91,6 +91,7 @@ __device__ inline void mpc_hopper(const QpConst& c, Work& w, Sys& sys, const AOp
     const int N = c.N, n = 6 * N, m = 11 * N, tid = threadIdx.x, T = blockDim.x;
     double* xs = w.err;   // reused after condense: solution trajectory [(N+1)][12]
     __syncthreads();
+    PH_T0(ph_all);
     load_hopper(c, w, b, B, io.x_in, io.pf, io.Cbits, io.Qd, io.Rd);
     // a hopper without a solved previous tick (first call, or re-initialised after a respawn) takes
     // the reference's init branch: two solves, x_guess[1:] = x_ref (mpc_cvx_euler_3f.py:50-58)
@@ -98,7 +99,8 @@ __device__ inline void mpc_hopper(const QpConst& c, Work& w, Sys& sys, const AOp
     __syncthreads();
     int st = 0, its = 0, nfac = 0, path = 0;
     sys.flops = 0.0;
-    const int passes = init ? 2 : 1;
+    // first call: two solves (reference); later ticks: c.sqp_sweeps relinearisation sweeps (reference: 1)
+    const int passes = init ? 2 : c.sqp_sweeps;
     for (int pass = 0; pass < passes; ++pass) {
         // linearisation point (mpc_cvx_euler_3f.py:50-62); only p and yaw of rows 0..N-1 matter
         for (int k = tid; k < N; k += T) {
@@ -108,7 +110,7 @@ __device__ inline void mpc_hopper(const QpConst& c, Work& w, Sys& sys, const AOp
                 const size_t o = (size_t)(k - 1) * 12;
                 gp[0] = io.x_ref[(o + 0) * B + b]; gp[1] = io.x_ref[(o + 1) * B + b];
                 gp[2] = io.x_ref[(o + 2) * B + b]; gp[3] = io.x_ref[(o + 5) * B + b];
-            } else if (init) {   // second pass of the first call: x_guess = x.value of pass 0
+            } else if (init || pass > 0) {   // later passes relinearise about the previous pass: x_guess = x.value
                 gp[0] = xs[12 * k]; gp[1] = xs[12 * k + 1]; gp[2] = xs[12 * k + 2]; gp[3] = xs[12 * k + 5];
             } else {             // time shift: x_guess[k] = x.value[k+1]
                 const size_t o = (size_t)(k + 1) * 12;
@@ -119,13 +121,17 @@ __device__ inline void mpc_hopper(const QpConst& c, Work& w, Sys& sys, const AOp
         // the footstep window and the gains share storage with solver scratch (carve()): reload after a solve
         if (pass > 0) load_hopper(c, w, b, B, io.x_in, io.pf, io.Cbits, io.Qd, io.Rd);
         __syncthreads();
+        PH_ADD(1, ph_all);
+        PH_T0(ph_c);
         const int infeasible = condense(c, w, io.x_ref + b, (size_t)B);
+        PH_ADD(2, ph_c);
+        PH_T0(ph_sv);
         sys.flops += c.condense_flops;
         // warm start: second init pass re-uses pass 0's solution as is; later ticks shift the
         // previous tick's solution and active set by one stage (the last two stages are kept)
         int warm = 0;
         if (c.warm_start && !infeasible) {
-            if (init && pass == 1 && st == 0) {
+            if (pass >= 1 && st == 0) {          // same QP horizon, new linearisation: start from the last pass as is
                 warm = 1;
                 for (int i = tid; i < n; i += T) w.xp[i] = w.x[i];
             } else if (!init && io.valid[b]) {
@@ -172,7 +178,10 @@ __device__ inline void mpc_hopper(const QpConst& c, Work& w, Sys& sys, const AOp
             its += info.iters; nfac += info.nfac; path = info.path;
             if (info.status != 0 && st == 0) st = info.status;
         }
+        PH_ADD(3, ph_sv);
+        PH_T0(ph_r);
         rollout_solution(c, w, w.x, xs);
+        PH_ADD(9, ph_r);
     }
     // outputs
     for (int i = tid; i < (N + 1) * 12; i += T) {
@@ -202,6 +211,7 @@ __device__ inline void mpc_hopper(const QpConst& c, Work& w, Sys& sys, const AOp
             io.ninf[b] = (st == ST_INFEASIBLE);
         }
     }
+    PH_ADD(0, ph_all);
 }
 
 }  // namespace hmpc

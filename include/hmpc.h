@@ -90,7 +90,10 @@ typedef struct hmpc_config {
     int32_t ipm_max_iter;  /* interior-point iteration cap */
     int32_t on_infeasible; /* rollout: HMPC_INFEASIBLE_HOLD (apply U = 0) | HMPC_INFEASIBLE_RESPAWN
                               (reset the hopper onto its reference at the next tick and re-initialise) */
-    int32_t reserved0;
+    int32_t sqp_sweeps;    /* relinearisation sweeps per (non-first) tick: 1 = the reference's single linearisation
+                              about the time-shifted previous solution (mpc_cvx_euler_3f.py:59-68); k > 1 relinearises
+                              about the sweep's own solution and solves again (the SQP the reference's docstring
+                              gestures at, mpc_cvx_euler_3f.py:41-46).  0 is treated as 1 */
     double mpc_dt;         /* robotrunner.py:47  0.02  */
     double sim_dt;         /* run.py:24          1e-3  */
     double m, g, mu;       /* robotrunner.py:37,42,68 */

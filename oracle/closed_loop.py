@@ -19,8 +19,9 @@ class QPFailed(Exception):
 
 
 class OracleMpc:
-    def __init__(self, prm: ho.Params, solver="exact", osqp_opts=None):
+    def __init__(self, prm: ho.Params, solver="exact", osqp_opts=None, sqp_sweeps=1):
         self.prm, self.solver = prm, solver
+        self.sqp_sweeps = max(1, int(sqp_sweeps))   # 1 = the reference; k > 1: product extension (hmpc_config.sqp_sweeps)
         self.osqp_opts = dict(osqp_opts or {})
         self.xval = None
         self.uval = None
@@ -61,15 +62,18 @@ class OracleMpc:
             x_guess[0] = x_in
             x_guess[1:-1] = self.xval[2:]
             x_guess[-1] = self.xval[-1]
+            for _ in range(self.sqp_sweeps - 1):
+                self._solve(x_in, x_ref_in, pf, C, x_guess)
+                x_guess = self.xval.copy()
         return self._solve(x_in, x_ref_in, pf, C, x_guess)
 
 
 def closed_loop(prm: ho.Params, X0, xref_tab, pf_tab, C, pf_switch, n_ticks, solver="exact", osqp_opts=None,
-                u_perturb=None):
+                u_perturb=None, sqp_sweeps=1):
     """X0 (13,), xref_tab (T+N,12), pf_tab (T+N+1,3), C (T,N), pf_switch (T,).  Returns X_log
     (n_ticks+1,13), U_log (n_ticks,6).  ``u_perturb(t)`` optionally adds a perturbation to U[0] (used by
     the sensitivity study that justifies the closed-loop tolerance)."""
-    mpc = OracleMpc(prm, solver, osqp_opts)
+    mpc = OracleMpc(prm, solver, osqp_opts, sqp_sweeps)
     X = np.array(X0, float)
     N = prm.N
     X_log = np.zeros((n_ticks + 1, 13)); U_log = np.zeros((n_ticks, 6))

@@ -42,6 +42,7 @@ def default_config(**over):
     cfg.precision = cfg.uref_mode = cfg.solver = cfg.mode = 0
     cfg.max_iter, cfg.check_interval, cfg.first_check, cfg.polish = 10000, 25, 25, 1
     cfg.adaptive_rho, cfg.warm_start, cfg.polish_retries, cfg.ipm_max_iter, cfg.on_infeasible = 1, 1, 8, 40, 0
+    cfg.sqp_sweeps = 1
     cfg.mpc_dt, cfg.sim_dt, cfg.m, cfg.g, cfg.mu = 0.02, 1e-3, 7.5, 9.807, 1.0
     J = np.array([[76148072.89e-9, 70089.52e-9, 2067970.36e-9], [70089.52e-9, 45477183.53e-9, -87045.58e-9],
                   [2067970.36e-9, -87045.58e-9, 76287220.47e-9]])

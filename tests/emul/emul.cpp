@@ -19,7 +19,7 @@ static QpConst qp_const(const hmpc_config& cfg) {
     c.N = cfg.N; c.dyn = cfg.dyn; c.uref_mode = cfg.uref_mode; c.solver = cfg.solver; c.mode = cfg.mode;
     c.max_iter = cfg.max_iter; c.check = cfg.check_interval; c.first_check = cfg.first_check;
     c.retries = cfg.polish_retries; c.adaptive_rho = cfg.adaptive_rho; c.warm_start = cfg.warm_start;
-    c.polish = cfg.polish; c.ipm_max_iter = cfg.ipm_max_iter;
+    c.polish = cfg.polish; c.ipm_max_iter = cfg.ipm_max_iter; c.sqp_sweeps = cfg.sqp_sweeps > 1 ? cfg.sqp_sweeps : 1;
     c.dt = cfg.mpc_dt; c.m = cfg.m; c.g = cfg.g; c.mu = cfg.mu;
     for (int i = 0; i < 9; ++i) c.Jinv[i] = cfg.Jinv[i];
     for (int i = 0; i < 3; ++i) { c.rh[i] = cfg.rh[i]; c.tau_max[i] = cfg.tau_max[i]; }

@@ -49,14 +49,16 @@ def test_condense_matches_reference_qp_data(dyn):
         assert inf[0] == 0
 
 
-@pytest.mark.parametrize("dyn,N,precision", [("3f", 10, 0), ("2f", 10, 0), ("3f", 20, 0), ("3f", 10, 1), ("2f", 10, 1)])
-def test_closed_loop_matches_oracle(dyn, N, precision):
-    """precision 1 = FP32 factorisation / substitution with FP64 data and refinement: same parity bound."""
+@pytest.mark.parametrize("dyn,N,precision,sweeps", [("3f", 10, 0, 1), ("2f", 10, 0, 1), ("3f", 20, 0, 1), ("3f", 10, 1, 1),
+                                                    ("2f", 10, 1, 1), ("3f", 10, 0, 2), ("2f", 10, 0, 3)])
+def test_closed_loop_matches_oracle(dyn, N, precision, sweeps):
+    """precision 1 = FP32 factorisation / substitution with FP64 data and refinement: same parity bound.
+    sweeps > 1 = hmpc_config.sqp_sweeps: relinearise about the tick's own solution and solve again."""
     B, n_ticks = (6, 25) if N == 10 else (2, 8)
     sc = scenarios.make_batch(B, N=N, n_ticks=n_ticks, seed=21, dyn=dyn)
-    em = EmulMpc(B, dyn=dyn, N=N, precision=precision)
+    em = EmulMpc(B, dyn=dyn, N=N, precision=precision, sqp_sweeps=sweeps)
     em.set_gains(sc["Qdiag"], sc["Rdiag"])
-    mpcs = [OracleMpc(ho.Params(dyn=dyn, N=N, Qdiag=sc["Qdiag"][:, b].copy(), Rdiag=sc["Rdiag"][:, b].copy()))
+    mpcs = [OracleMpc(ho.Params(dyn=dyn, N=N, Qdiag=sc["Qdiag"][:, b].copy(), Rdiag=sc["Rdiag"][:, b].copy()), sqp_sweeps=sweeps)
             for b in range(B)]
     X = sc["X0"].copy()
     paths = np.zeros(5, int)

@@ -129,6 +129,28 @@ def test_closed_loop_rollout_matches_oracle(dyn, precision):
         np.testing.assert_allclose(Xg[:, :, b], Xo, rtol=0, atol=1e-6)
 
 
+def test_sqp_sweeps_match_oracle():
+    """hmpc_config.sqp_sweeps = 2: every tick relinearises about its own solution once and solves
+    again; same parity bound against the oracle driver doing the same."""
+    B, N, n_ticks = 4, 10, 20
+    sc = scenarios.make_batch(B, N=N, n_ticks=n_ticks, seed=11)
+    bm = mk(B, "3f", N, sqp_sweeps=2)
+    bm.set_gains(T(sc["Qdiag"]), T(sc["Rdiag"]))
+    out = bm.rollout(T(sc["X0"]).clone(), T(sc["xref_tab"]), T(sc["pf_tab"]), cb64(sc["C_tab"]), T(sc["pf_switch"]),
+                     0, n_ticks, True, log=True)
+    assert np.all(out["status"].cpu().numpy() == 0)
+    Xg, Ug = out["X_log"].cpu().numpy(), out["U_log"].cpu().numpy()
+    for b in range(B):
+        p = ho.Params(dyn="3f", N=N, Qdiag=sc["Qdiag"][:, b].copy(), Rdiag=sc["Rdiag"][:, b].copy())
+        Xo, Uo = closed_loop(p, sc["X0"][:, b], sc["xref_tab"][:, :, b], sc["pf_tab"][:, :, b], sc["C"][:, b],
+                             sc["pf_switch"][:, b], n_ticks, sqp_sweeps=2)
+        assert np.all(np.abs(Ug[:, :, b] - Uo) <= 10 * u_tol(Uo)), np.abs(Ug[:, :, b] - Uo).max()
+        np.testing.assert_allclose(Xg[:, :, b], Xo, rtol=0, atol=1e-6)
+        Xo1, _ = closed_loop(p, sc["X0"][:, b], sc["xref_tab"][:, :, b], sc["pf_tab"][:, :, b], sc["C"][:, b],
+                             sc["pf_switch"][:, b], n_ticks)
+        assert np.abs(Xo1 - Xo).max() > 1e-5           # the option does change the loop
+
+
 @pytest.mark.parametrize("tag,dyn", [("loop_2f", "2f"), ("loop_3f_curve", "3f"), ("loop_3f_curve_5s", "3f")])
 def test_reference_runs_2000ms_N60(tag, dyn):
     """BASELINE configs[0] and [1]: run.py 2f --N_run 2000, run.py 3f --curve --N_run 2000 and run.py 3f --curve
