@@ -542,6 +542,23 @@ __device__ inline void compact_indices(int first, int len, int cap, int* list, i
 // U is stored packed (lower triangle, column by column): the forward sweep reads contiguous columns, the
 // backward sweep reads a row with the slowly varying stride nk - i.
 // ------------------------------------------------------------------------------------------------
+// Reciprocal of a pivot without the library's division slow path: MUFU seed + two Newton steps (relative error
+// ~1e-16, not correctly rounded -- the factor only feeds an iteratively refined, KKT-verified solve).  The
+// library division was 4.6 % of all executed instructions of the kernel (every thread divides once per pivot)
+// and sits on the critical path of every pivot (tools/micro/tiled.cu: 145 vs ~70 cycles).
+__device__ __forceinline__ double fast_rcp(double d) {
+#ifdef HMPC_HOST_EMUL
+    return 1.0 / d;
+#else
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    r = fma(fma(-d, r, 1.0), r, r);
+    r = fma(fma(-d, r, 1.0), r, r);
+    return r;
+#endif
+}
+__device__ __forceinline__ float fast_rcp(float d) { return 1.0f / d; }
+
 template <typename F>
 struct LinSys {
     typedef F real;
@@ -601,7 +618,7 @@ struct LinSys {
                 const F ap = (j < nF) ? piv : -piv;
                 const bool ok = (ap > (F)0) && (ap < (F)1e30);
                 if (!ok) bad = 1;
-                const F rinv = (F)1 / (ok ? piv : (F)1);
+                const F rinv = fast_rcp(ok ? piv : (F)1);
                 if (tid == 0) dinv[j] = rinv;
                 for (int i = j + 1 + tid; i < nk; i += T) {
                     const F uij = colj[i];
