@@ -79,6 +79,39 @@ def test_closed_loop_matches_oracle(dyn, N, precision, sweeps):
     assert paths[dp.ST_SOLVED + 1] > 0            # the warm path was exercised
 
 
+@pytest.mark.parametrize("N", [3, 5])
+def test_short_horizons_match_oracle(N):
+    """Short horizons (the reference only ever runs N = 60): same parity bound; when the oracle finds the QP
+    infeasible (the reference would raise) the device flags the hopper instead of returning a point."""
+    B, n_ticks = 3, 10
+    sc = scenarios.make_batch(B, N=N, n_ticks=n_ticks, seed=9)
+    em = EmulMpc(B, N=N)
+    em.set_gains(sc["Qdiag"], sc["Rdiag"])
+    mpcs = [OracleMpc(ho.Params(N=N, Qdiag=sc["Qdiag"][:, b].copy(), Rdiag=sc["Rdiag"][:, b].copy())) for b in range(B)]
+    X = sc["X0"].copy()
+    alive = [True] * B
+    checked = 0
+    for t in range(n_ticks):
+        x_in = np.stack([ho.convert(X[:, b]) for b in range(B)], 1)
+        U, Xs, st, it, nf, pa = em.solve(x_in, sc["xref_tab"][t:t + N], sc["pf_tab"][t:t + N], sc["C_tab"][t], t == 0)
+        for b in range(B):
+            if not alive[b]:
+                continue
+            try:
+                Uo = mpcs[b].mpcontrol(x_in[:, b], sc["xref_tab"][t:t + N, :, b], sc["pf_tab"][t:t + N, :, b], sc["C"][t, b], t == 0)
+            except QPFailed:
+                assert st[b] == dp.ST_INFEASIBLE
+                alive[b] = False
+                continue
+            assert st[b] == 0
+            assert np.all(np.abs(U[:, :, b] - Uo) <= u_tol(Uo))
+            checked += 1
+            for i in range(20):
+                pf = sc["pf_tab"][t, :, b] if i < sc["pf_switch"][t, b] else sc["pf_tab"][t + 1, :, b]
+                X[:, b] = ho.rk4_normalized(X[:, b], Uo[0], pf, mpcs[b].prm)
+    assert checked >= 20
+
+
 def test_infeasible_hopper_is_flagged_and_gets_zero_input():
     N = 10
     sc = scenarios.make_batch(2, N=N, n_ticks=2, seed=3)

@@ -77,10 +77,13 @@ def test_linearise_and_condense_against_reference_golden(dyn):
 
 
 # ---- QP solutions -----------------------------------------------------------------------------
-@pytest.mark.parametrize("dyn,N,B", [("3f", 10, 24), ("2f", 10, 24), ("3f", 20, 4), ("2f", 20, 4), ("3f", 60, 2)])
+@pytest.mark.parametrize("dyn,N,B", [("3f", 10, 24), ("2f", 10, 24), ("3f", 20, 4), ("2f", 20, 4), ("3f", 60, 2),
+                                     ("3f", 3, 5), ("2f", 5, 7), ("3f", 12, 3), ("3f", 40, 1)])
 def test_mpcontrol_matches_oracle_optimum(dyn, N, B):
     """Per-step QP solutions within 1e-5 abs + 1e-4 rel of the exact optimum (FP64), first call (two solves)
-    and a warm-started second call."""
+    and a warm-started second call.  Horizons cover every kernel instantiation: 128-thread shared-memory
+    (N <= 10, incl. the short horizons 3 and 5 and odd batch sizes), 256-thread shared-memory (12, 20) and the
+    global-workspace path (40, 60)."""
     sc = scenarios.make_batch(B, N=N, n_ticks=3, seed=13, dyn=dyn)
     bm = mk(B, dyn, N)
     bm.set_gains(T(sc["Qdiag"]), T(sc["Rdiag"]))
