@@ -26,7 +26,7 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
-def build_lib(force=False, verbose=False, out=None):
+def build_lib(force=False, verbose=False):
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in DEPS):
         return OUT
     os.makedirs(OBJ_DIR, exist_ok=True)
