@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--precision", choices=["fp64", "fp32"], default="fp64",
                     help="fp32: FP32 factorisation / substitution with FP64 data and refinement (mixed precision)")
     ap.add_argument("--sqp-sweeps", type=int, default=1, help="relinearisation sweeps per tick (1 = the reference)")
+    ap.add_argument("--hot-path", choices=["auto", "cta"], default="auto",
+                    help="auto: warp-per-hopper kernel + CTA fallback (default); cta: round-1 CTA-per-hopper kernel only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="wall-clock budget of the CPU baseline sample")
     return ap.parse_args()
@@ -186,7 +188,7 @@ def run_b200(args):
     # ---- synthetic scenario for this shard (host, numpy), tables resident in HBM ----
     sc = scenarios.make_batch(B, idx0=idx0, N=N, n_ticks=n_ticks + 1, dyn=args.dyn)
     bm = BatchMpc(B, dyn=args.dyn, N=N, device=local, solver=args.solver, precision=args.precision,
-                  on_infeasible="respawn", sqp_sweeps=args.sqp_sweeps)
+                  on_infeasible="respawn", sqp_sweeps=args.sqp_sweeps, hot_path=args.hot_path)
     T = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
     bm.set_gains(T(sc["Qdiag"]), T(sc["Rdiag"]))
     xref_h = torch.from_numpy(np.ascontiguousarray(sc["xref_tab"])).pin_memory()
@@ -223,6 +225,7 @@ def run_b200(args):
     st = out["status"].cpu().numpy()
     it = out["iters"].cpu().numpy()
     nf, pa, ni = [a.cpu().numpy() for a in bm.solve_stats()]
+    hot = bm.hot_path_info()
     flops = float(bm.solve_flops().sum().item())
     ms_max = sharding.max_over_ranks(ms, dev)
 
@@ -293,7 +296,7 @@ def run_b200(args):
     # handle replays the warm-up from the initial states, then the e2e region covers ticks W .. W+K-1.
     bm_res, X_res = bm, X
     bm = BatchMpc(B, dyn=args.dyn, N=N, device=local, solver=args.solver, precision=args.precision, on_infeasible="respawn",
-                  sqp_sweeps=args.sqp_sweeps)
+                  sqp_sweeps=args.sqp_sweeps, hot_path=args.hot_path)
     bm.set_gains(T(sc["Qdiag"]), T(sc["Rdiag"]))
     X = T(sc["X0"]).clone()
     bm.rollout(X, xref_d, pf_d, C_d, sw_d, 0, W - 2, True)
@@ -379,6 +382,7 @@ def run_b200(args):
             "solver_stats": {"solved_exact_frac": solved, "infeasible_ticks": int(inf_ticks),
                              "ipm_iters_per_tick": float(it.mean() / K), "factorisations_per_tick": float(nf.mean() / K),
                              "warm_path_frac_last_tick": float(np.mean(pa == 1)),
+                             "hot_path": dict(hot, mode=args.hot_path, deferred_frac=hot["deferred"] / float(B * K)),
                              "mpc_kernel_ms_per_tick": mpc_ms / max(nt, 1), "sim_kernel_ms_per_tick": sim_ms / max(nt, 1)}}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference_sample(args.dyn, N, args.cpu_seconds)

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HMPC_LIB_PATH") or os.path.join(_HERE, "libhmpc_b200.so")   # override: experiment builds (tools/)
 
-HMPC_ABI_VERSION = 1
+HMPC_ABI_VERSION = 2
 HMPC_INF = 1e30
 DYN = {"2f": 2, "3f": 3}
 STATUS_SOLVED, STATUS_MAX_ITER, STATUS_INFEASIBLE, STATUS_NON_FINITE, STATUS_INEXACT = 0, 1, 2, 3, 4
@@ -20,12 +20,13 @@ SOLVER = {"exact": 0, "admm": 1}
 MODE = {"early_exit": 0, "fixed_iter": 1}
 ON_INFEASIBLE = {"hold": 0, "respawn": 1}
 PRECISION = {"fp64": 0, "fp32": 1}
+HOT_PATH = {"auto": 0, "cta": 1}
 
 # every symbol include/hmpc.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = [
     "hmpc_default_config", "hmpc_create", "hmpc_destroy", "hmpc_set_stream", "hmpc_synchronize",
     "hmpc_set_gains", "hmpc_convert", "hmpc_rk4", "hmpc_linearize", "hmpc_condense", "hmpc_solve",
-    "hmpc_rollout", "hmpc_solve_stats", "hmpc_set_timing", "hmpc_kernel_times", "hmpc_launch_count", "hmpc_measure_fp64_peak", "hmpc_last_error",
+    "hmpc_rollout", "hmpc_solve_stats", "hmpc_set_timing", "hmpc_kernel_times", "hmpc_launch_count", "hmpc_hot_path_info", "hmpc_measure_fp64_peak", "hmpc_last_error",
     "hmpc_abi_version",
 ]
 
@@ -38,7 +39,7 @@ class HmpcConfig(C.Structure):
         ("solver", C.c_int32), ("mode", C.c_int32), ("max_iter", C.c_int32), ("check_interval", C.c_int32),
         ("first_check", C.c_int32), ("polish", C.c_int32), ("adaptive_rho", C.c_int32),
         ("warm_start", C.c_int32), ("polish_retries", C.c_int32), ("ipm_max_iter", C.c_int32),
-        ("on_infeasible", C.c_int32), ("sqp_sweeps", C.c_int32),
+        ("on_infeasible", C.c_int32), ("sqp_sweeps", C.c_int32), ("hot_path", C.c_int32),
         ("mpc_dt", C.c_double), ("sim_dt", C.c_double), ("m", C.c_double), ("g", C.c_double),
         ("mu", C.c_double), ("J", C.c_double * 9), ("Jinv", C.c_double * 9), ("rh", C.c_double * 3),
         ("tau_max", C.c_double * 3), ("fz_max", C.c_double), ("z_min", C.c_double), ("kf", C.c_double),
@@ -83,6 +84,7 @@ def load():
     lib.hmpc_set_timing.argtypes = [vp, i32]
     lib.hmpc_kernel_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
     lib.hmpc_launch_count.argtypes = [vp, i64p]
+    lib.hmpc_hot_path_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), i64p]
     lib.hmpc_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
     for name in SYMBOLS:
         fn = getattr(lib, name)

@@ -56,6 +56,8 @@ class BatchMpc:
                 v = _lib.ON_INFEASIBLE[v]
             if k == "precision" and isinstance(v, str):
                 v = _lib.PRECISION[v]
+            if k == "hot_path" and isinstance(v, str):
+                v = _lib.HOT_PATH[v]
             cur = getattr(cfg, k)
             if hasattr(cur, "__len__"):
                 arr = np.asarray(v, dtype=float).reshape(-1)
@@ -205,6 +207,13 @@ class BatchMpc:
         n = C.c_int64()
         _lib.check(self.lib.hmpc_launch_count(self._h, C.byref(n)))
         return n.value
+
+    def hot_path_info(self):
+        """dict(warps_per_sm, kcap, regs, deferred): the warp-per-hopper kernel's geometry and how many hopper-ticks
+        of the last solve / rollout it handed to the CTA kernel (warps_per_sm = 0: warp kernel not in use)."""
+        a, b, r, d = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+        _lib.check(self.lib.hmpc_hot_path_info(self._h, C.byref(a), C.byref(b), C.byref(r), C.byref(d)))
+        return dict(warps_per_sm=a.value, kcap=b.value, regs=r.value, deferred=d.value)
 
     def measure_fp64_peak(self):
         v = C.c_double()

@@ -23,6 +23,7 @@
 #include "hmpc_qp.cuh"
 #include "hmpc_mpc.cuh"
 #include "hmpc_kernel.cuh"
+#include "hmpc_warp.cuh"
 
 namespace {
 
@@ -74,6 +75,14 @@ struct hmpc_handle {
     bool mats_in_smem = false;
     double* ws = nullptr;     // per-CTA matrix workspace when the matrices do not fit in shared memory
     int64_t launches = 0;
+    // warp-per-hopper warm path (hmpc_warp.cuh): geometry, per-warp Hessian workspace, deferral list
+    bool warp_ok = false;
+    int warp_rounds = 0;
+    int warp_grid = 0, warp_wpc = 1, warp_kcap = 0, warp_wdoubles = 0, warp_per_sm = 0, warp_regs = 0;
+    size_t warp_smem = 0, hstride = 0;
+    double* hws = nullptr;
+    int* defer_list = nullptr;    // [B] hoppers the warp kernel handed to the CTA kernel this tick
+    int32_t* n_defer = nullptr;   // [1] accumulated deferrals of the most recent solve / rollout
 };
 
 namespace hmpc {
@@ -323,7 +332,8 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
     *out = nullptr;
     if (cfg->abi_version != HMPC_ABI_VERSION) return fail(HMPC_ERR_BAD_ARG, "abi_version mismatch");
     if (cfg->batch < 1) return fail(HMPC_ERR_BAD_ARG, "batch must be >= 1");
-    if (cfg->N < 2 || cfg->N > HMPC_MAX_N) return fail(HMPC_ERR_BAD_ARG, "N must be in [2, 64]");
+    if (cfg->N < 3 || cfg->N > HMPC_MAX_N) return fail(HMPC_ERR_BAD_ARG, "N must be in [3, 64]");
+    if (cfg->hot_path != HMPC_HOT_AUTO && cfg->hot_path != HMPC_HOT_CTA) return fail(HMPC_ERR_BAD_ARG, "hot_path must be HMPC_HOT_AUTO or HMPC_HOT_CTA");
     if (cfg->dyn != HMPC_DYN_2F && cfg->dyn != HMPC_DYN_3F) return fail(HMPC_ERR_BAD_ARG, "dyn must be 2 or 3");
     if (cfg->precision != HMPC_FP64 && cfg->precision != HMPC_FP32) return fail(HMPC_ERR_BAD_ARG, "precision must be HMPC_FP64 or HMPC_FP32");
     if (cfg->precision == HMPC_FP32 && cfg->N > 10) return fail(HMPC_ERR_UNSUPPORTED, "FP32 mode is built for horizons N <= 10 only");
@@ -342,7 +352,10 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
     if (!h) return fail(HMPC_ERR_ALLOC, "host allocation failed");
     h->cfg = *cfg;
     cudaDeviceProp prop;
-    HMPC_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    {
+        cudaError_t ep = cudaGetDeviceProperties(&prop, cfg->device);
+        if (ep != cudaSuccess) { hmpc_destroy(h); return fail(HMPC_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(ep)); }
+    }
     h->sm_count = prop.multiProcessorCount;
     const size_t B = (size_t)cfg->batch, N = (size_t)cfg->N, n = 6 * N;
     auto dalloc = [&](void** p, size_t bytes) { return cudaMalloc(p, bytes); };
@@ -355,16 +368,20 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
         (e = dalloc((void**)&h->st_tick, B * 4)) != cudaSuccess || (e = dalloc((void**)&h->nfac, B * 4)) != cudaSuccess ||
         (e = dalloc((void**)&h->path, B * 4)) != cudaSuccess || (e = dalloc((void**)&h->ninf, B * 4)) != cudaSuccess ||
         (e = dalloc((void**)&h->code, 11 * N * B)) != cudaSuccess || (e = dalloc((void**)&h->valid, B)) != cudaSuccess ||
-        (e = dalloc((void**)&h->flops, B * 8)) != cudaSuccess || (e = dalloc((void**)&h->work_ctr, 64)) != cudaSuccess) {
+        (e = dalloc((void**)&h->flops, B * 8)) != cudaSuccess || (e = dalloc((void**)&h->work_ctr, 64)) != cudaSuccess ||
+        (e = dalloc((void**)&h->defer_list, B * 4)) != cudaSuccess || (e = dalloc((void**)&h->n_defer, 4)) != cudaSuccess) {
         hmpc_destroy(h);
         return fail(HMPC_ERR_ALLOC, std::string("cudaMalloc: ") + cudaGetErrorString(e));
     }
-    cudaMemset(h->Xsol, 0, (N + 1) * 12 * B * 8);
-    cudaMemset(h->Usol, 0, N * 6 * B * 8);
-    cudaMemset(h->code, 0, 11 * N * B);
-    cudaMemset(h->valid, 0, B);
-    cudaMemset(h->st_tick, 0, B * 4); cudaMemset(h->nfac, 0, B * 4);
-    cudaMemset(h->path, 0, B * 4); cudaMemset(h->ninf, 0, B * 4); cudaMemset(h->flops, 0, B * 8);
+    if ((e = cudaMemset(h->Xsol, 0, (N + 1) * 12 * B * 8)) != cudaSuccess || (e = cudaMemset(h->Usol, 0, N * 6 * B * 8)) != cudaSuccess ||
+        (e = cudaMemset(h->code, 0, 11 * N * B)) != cudaSuccess || (e = cudaMemset(h->valid, 0, B)) != cudaSuccess ||
+        (e = cudaMemset(h->st_tick, 0, B * 4)) != cudaSuccess || (e = cudaMemset(h->nfac, 0, B * 4)) != cudaSuccess ||
+        (e = cudaMemset(h->path, 0, B * 4)) != cudaSuccess || (e = cudaMemset(h->ninf, 0, B * 4)) != cudaSuccess ||
+        (e = cudaMemset(h->flops, 0, B * 8)) != cudaSuccess || (e = cudaMemset(h->work_ctr, 0, 64)) != cudaSuccess ||
+        (e = cudaMemset(h->n_defer, 0, 4)) != cudaSuccess) {
+        hmpc_destroy(h);
+        return fail(HMPC_ERR_CUDA, std::string("cudaMemset: ") + cudaGetErrorString(e));
+    }
     // default gains = the reference's (mpc_cvx_euler_3f.py:35,37)
     {
         const double Qref[12] = {50., 50., 2., 1., 1., 50., 1., 1., 1., 10., 10., 10.};
@@ -372,9 +389,10 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
         if (!tmp) { hmpc_destroy(h); return fail(HMPC_ERR_ALLOC, "host allocation failed"); }
         for (size_t i = 0; i < 12; ++i) for (size_t b = 0; b < B; ++b) tmp[i * B + b] = Qref[i];
         for (size_t i = 0; i < 6; ++i) for (size_t b = 0; b < B; ++b) tmp[(12 + i) * B + b] = 0.001;
-        cudaMemcpy(h->Qd, tmp, 12 * B * 8, cudaMemcpyHostToDevice);
-        cudaMemcpy(h->Rd, tmp + 12 * B, 6 * B * 8, cudaMemcpyHostToDevice);
+        e = cudaMemcpy(h->Qd, tmp, 12 * B * 8, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(h->Rd, tmp + 12 * B, 6 * B * 8, cudaMemcpyHostToDevice);
         delete[] tmp;
+        if (e != cudaSuccess) { hmpc_destroy(h); return fail(HMPC_ERR_CUDA, std::string("cudaMemcpy gains: ") + cudaGetErrorString(e)); }
     }
     // solver geometry
     const size_t vec_bytes = ((hmpc::work_vec_doubles((int)N) + 1) & ~(size_t)1) * 8;
@@ -387,6 +405,8 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
     if (const char* pad = getenv("HMPC_SMEM_PAD")) h->mpc_smem += (size_t)atol(pad);
     if (h->mpc_smem > smem_cap) { hmpc_destroy(h); return fail(HMPC_ERR_UNSUPPORTED, "horizon too large for shared memory"); }
     h->mpc_threads = (n <= 64) ? 128 : 256;   // one CTA per SM beyond N = 10: use the wider CTA
+    // the 128-thread instantiations are compiled for shared-memory matrices only
+    if (h->mpc_threads == 128 && !h->mats_in_smem) { hmpc_destroy(h); return fail(HMPC_ERR_UNSUPPORTED, "shared memory too small for the N <= 10 solver kernel"); }
     int per_sm = 1;
     if (h->mats_in_smem) per_sm = std::max<int>(1, (int)((size_t)prop.sharedMemPerMultiprocessor / (h->mpc_smem + 1024)));
     else per_sm = std::max<int>(1, std::min<int>(8, (int)((size_t)prop.sharedMemPerMultiprocessor / (h->mpc_smem + 1024))));
@@ -397,17 +417,73 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
             return fail(HMPC_ERR_ALLOC, std::string("cudaMalloc workspace: ") + cudaGetErrorString(e));
         }
     }
-    const int smem_i = (int)h->mpc_smem;
+    // the attribute is process-global per kernel: always the device maximum (minus room for static shared memory),
+    // so that a second handle never lowers it for the first
+    const int smem_i = (int)smem_cap - 512;
     if (h->mpc_threads == 128) {
         if (cfg->precision == HMPC_FP32) e = hmpc::mpc_set_smem_n10_f32(smem_i);
         else e = (cfg->solver == HMPC_SOLVER_ADMM) ? hmpc::mpc_set_smem_n10_f64_admm(smem_i) : hmpc::mpc_set_smem_n10_f64(smem_i);
     }
     else e = h->mats_in_smem ? hmpc::mpc_set_smem_wide_smem(smem_i) : hmpc::mpc_set_smem_wide_gmem(smem_i);
     if (e != cudaSuccess ||
-        (e = cudaFuncSetAttribute(hmpc::condense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mpc_smem)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(hmpc::linearize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vec_bytes)) != cudaSuccess) {
+        (e = cudaFuncSetAttribute(hmpc::condense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_i)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(hmpc::linearize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_i)) != cudaSuccess) {
         hmpc_destroy(h);
         return fail(HMPC_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    }
+    // ---- warp-per-hopper warm path: cut the SM's shared memory into per-warp slices ----
+    if (hmpc::warp_path_applies(*cfg, 0)) {
+        h->warp_kcap = hmpc::warp_kcap(*cfg);
+        h->warp_wdoubles = (int)hmpc::warp_work_doubles((int)N, h->warp_kcap);
+        const size_t wbytes = (size_t)h->warp_wdoubles * 8;
+        const size_t sm_smem = (size_t)prop.sharedMemPerMultiprocessor;
+        int best_w = 0, best_wpc = 1;
+        int rounds = 0;
+        if (const char* ev = getenv("HMPC_WARP_ROUNDS")) rounds = atoi(ev) ? 1 : 0;
+        auto warps_for = [&](int wpc, int* regs_out) -> int {
+            int regs = 128;
+            if (hmpc::warp_regs(rounds, wpc, &regs) != cudaSuccess) { cudaGetLastError(); return 0; }
+            if (wbytes * wpc + 512 > smem_cap) return 0;
+            int ctas = (int)(sm_smem / (wbytes * wpc + 1024));
+            const int by_regs = (int)(65536 / ((size_t)((regs + 7) & ~7) * 32 * wpc));
+            ctas = std::min(std::min(ctas, by_regs), 32);
+            *regs_out = regs;
+            return ctas * wpc;
+        };
+        const int cand_free[3] = {4, 2, 1}, cand_rounds[5] = {10, 8, 5, 4, 2};
+        const int* cand = rounds ? cand_rounds : cand_free;
+        for (int ci = 0; ci < (rounds ? 5 : 3); ++ci) {
+            int regs = 0;
+            const int wtot = warps_for(cand[ci], &regs);
+            if (wtot > best_w) { best_w = wtot; best_wpc = cand[ci]; h->warp_regs = regs; }
+        }
+        if (const char* ev = getenv("HMPC_WARP_WPC")) {
+            const int v = atoi(ev);
+            int regs = 0;
+            if (hmpc::warp_wpc_supported(rounds, v)) { const int wtot = warps_for(v, &regs); if (wtot > 0) { best_wpc = v; best_w = wtot; h->warp_regs = regs; } }
+        }
+        if (const char* ev = getenv("HMPC_WARP_PER_SM")) {
+            const int v = atoi(ev);
+            if (v >= best_wpc && v < best_w) best_w = (v / best_wpc) * best_wpc;
+        }
+        if (best_w > 0) {
+            h->warp_wpc = best_wpc;
+            h->warp_per_sm = best_w;
+            h->warp_smem = wbytes * best_wpc;
+            const size_t want = ((size_t)B + best_wpc - 1) / best_wpc;
+            h->warp_grid = (int)std::min<size_t>(want, (size_t)h->sm_count * (best_w / best_wpc));
+            h->hstride = (n * n + 15) & ~(size_t)15;
+            if ((e = cudaMalloc((void**)&h->hws, (size_t)h->warp_grid * best_wpc * h->hstride * 8)) != cudaSuccess) {
+                hmpc_destroy(h);
+                return fail(HMPC_ERR_ALLOC, std::string("cudaMalloc warp workspace: ") + cudaGetErrorString(e));
+            }
+            h->warp_rounds = rounds;
+            if ((e = hmpc::warp_set_smem(rounds, best_wpc, smem_i)) != cudaSuccess) {
+                hmpc_destroy(h);
+                return fail(HMPC_ERR_CUDA, std::string("cudaFuncSetAttribute (warp kernel): ") + cudaGetErrorString(e));
+            }
+            h->warp_ok = true;
+        }
     }
     if ((e = cudaDeviceSynchronize()) != cudaSuccess) {
         hmpc_destroy(h);
@@ -423,6 +499,7 @@ int hmpc_destroy(hmpc_handle* h) {
     cudaFree(h->Qd); cudaFree(h->Rd); cudaFree(h->Xsol); cudaFree(h->Usol); cudaFree(h->xin);
     cudaFree(h->U0); cudaFree(h->st_tmp); cudaFree(h->it_tmp); cudaFree(h->ws);
     cudaFree(h->code); cudaFree(h->valid); cudaFree(h->st_tick); cudaFree(h->nfac); cudaFree(h->path); cudaFree(h->ninf); cudaFree(h->flops); cudaFree(h->work_ctr);
+    cudaFree(h->hws); cudaFree(h->defer_list); cudaFree(h->n_defer);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     delete h;
     return HMPC_OK;
@@ -496,15 +573,30 @@ int hmpc_condense(hmpc_handle* h, const double* x_in, const double* x_guess, con
 
 namespace {
 // small horizons: 128 threads, registers capped so that four CTAs share an SM; large: 256 threads
-void launch_mpc(hmpc_handle* h, const hmpc::QpConst& qc, const hmpc::MpcIo& io) {
-    cudaMemsetAsync(h->work_ctr, 0, sizeof(int), h->stream);
-    const hmpc::MpcLaunch l{h->mpc_grid, h->mpc_threads, h->mpc_smem, h->stream, h->cfg.batch, h->sm_count, h->ws, h->work_ctr};
+// work_ctr: [0] next hopper of the warp kernel, [1] deferred hoppers, [2] next entry of the CTA kernel
+__global__ void defer_stats_kernel(const int* __restrict__ work_ctr, int32_t* __restrict__ n_defer) { *n_defer += work_ctr[1]; }
+
+cudaError_t launch_mpc(hmpc_handle* h, const hmpc::QpConst& qc, const hmpc::MpcIo& io) {
+    cudaError_t e = cudaMemsetAsync(h->work_ctr, 0, 4 * sizeof(int), h->stream);
+    if (e != cudaSuccess) return e;
+    const bool warp = h->warp_ok && hmpc::warp_path_applies(h->cfg, io.init);
+    if (warp) {
+        const hmpc::WarpLaunch wl{h->warp_grid, h->warp_wpc, h->warp_rounds, h->warp_smem, h->stream, h->cfg.batch, h->warp_kcap,
+                                  h->warp_wdoubles, h->hws, h->hstride, h->work_ctr, h->defer_list, h->work_ctr + 1};
+        hmpc::warp_launch(wl, qc, io);
+        defer_stats_kernel<<<1, 1, 0, h->stream>>>(h->work_ctr, h->n_defer);
+        h->launches += 2;
+    }
+    const hmpc::MpcLaunch l{h->mpc_grid, h->mpc_threads, h->mpc_smem, h->stream, h->cfg.batch, h->sm_count, h->ws,
+                            h->work_ctr + 2, warp ? h->defer_list : nullptr, warp ? h->work_ctr + 1 : nullptr};
     if (h->mpc_threads == 128) {
         if (h->cfg.precision == HMPC_FP32) hmpc::mpc_launch_n10_f32(l, qc, io);
         else if (h->cfg.solver == HMPC_SOLVER_ADMM) hmpc::mpc_launch_n10_f64_admm(l, qc, io);
         else hmpc::mpc_launch_n10_f64(l, qc, io);
     } else if (h->mats_in_smem) hmpc::mpc_launch_wide_smem(l, qc, io);
     else hmpc::mpc_launch_wide_gmem(l, qc, io);
+    ++h->launches;
+    return cudaGetLastError();
 }
 
 hmpc::MpcIo make_io(hmpc_handle* h, const double* x_in, const double* x_ref, const double* pf,
@@ -528,9 +620,8 @@ int hmpc_solve(hmpc_handle* h, const double* x_in, const double* x_ref, const do
     if (!x_in || !x_ref || !pf || !Cbits) return fail(HMPC_ERR_BAD_ARG, "null input array");
     hmpc::MpcIo io = make_io(h, x_in, x_ref, pf, Cbits, init ? 1 : 0, 0, U, Xsol, nullptr, status, iters);
     io.respawn = 0;   // per-hopper re-initialisation only exists inside hmpc_rollout
-    launch_mpc(h, make_qp_const(h->cfg), io);
-    ++h->launches;
-    HMPC_CUDA(cudaGetLastError());
+    HMPC_CUDA(cudaMemsetAsync(h->n_defer, 0, 4, h->stream));
+    HMPC_CUDA(launch_mpc(h, make_qp_const(h->cfg), io));
     return HMPC_OK;
 }
 
@@ -549,6 +640,7 @@ int hmpc_rollout(hmpc_handle* h, double* X, const double* xref_tab, const double
     HMPC_CUDA(cudaMemsetAsync(h->nfac, 0, B * 4, h->stream));
     HMPC_CUDA(cudaMemsetAsync(h->ninf, 0, B * 4, h->stream));
     HMPC_CUDA(cudaMemsetAsync(h->flops, 0, B * 8, h->stream));
+    HMPC_CUDA(cudaMemsetAsync(h->n_defer, 0, 4, h->stream));
     if (h->timing) {
         while ((int)h->ev.size() < 3 * n_ticks) {
             cudaEvent_t e;
@@ -569,16 +661,16 @@ int hmpc_rollout(hmpc_handle* h, double* X, const double* xref_tab, const double
         const size_t row = (size_t)(tick0 + t);
         hmpc::MpcIo io = make_io(h, h->xin, xref_tab + row * 12 * B, pf_tab + row * 3 * B, C_tab + row * B,
                                  (init && t == 0) ? 1 : 0, 1, nullptr, nullptr, h->U0, st, it);
-        if (h->timing) cudaEventRecord(h->ev[3 * t], h->stream);
-        launch_mpc(h, qc, io);
-        if (h->timing) cudaEventRecord(h->ev[3 * t + 1], h->stream);
+        if (h->timing) HMPC_CUDA(cudaEventRecord(h->ev[3 * t], h->stream));
+        HMPC_CUDA(launch_mpc(h, qc, io));
+        if (h->timing) HMPC_CUDA(cudaEventRecord(h->ev[3 * t + 1], h->stream));
         hmpc::sim_kernel<<<sim_grid, 128, 0, h->stream>>>(
             sc, Bi, X, h->U0, pf_tab + row * 3 * B, pf_tab + (row + 1) * 3 * B,
             pf_switch ? pf_switch + row * B : nullptr, h->cfg.mpc_factor, h->xin,
             X_log ? X_log + (size_t)(t + 1) * 13 * B : nullptr, U_log ? U_log + (size_t)t * 6 * B : nullptr,
             nullptr, respawn ? h->st_tick : nullptr, respawn ? xref_tab + (row + 1) * 12 * B : nullptr);
-        if (h->timing) cudaEventRecord(h->ev[3 * t + 2], h->stream);
-        h->launches += 2;
+        if (h->timing) HMPC_CUDA(cudaEventRecord(h->ev[3 * t + 2], h->stream));
+        ++h->launches;
     }
     HMPC_CUDA(cudaGetLastError());
     return HMPC_OK;
@@ -613,6 +705,20 @@ int hmpc_solve_stats(hmpc_handle* h, int32_t* nfac, int32_t* path, int32_t* n_in
     if (nfac) HMPC_CUDA(cudaMemcpyAsync(nfac, h->nfac, B * 4, cudaMemcpyDeviceToDevice, h->stream));
     if (path) HMPC_CUDA(cudaMemcpyAsync(path, h->path, B * 4, cudaMemcpyDeviceToDevice, h->stream));
     if (n_infeasible) HMPC_CUDA(cudaMemcpyAsync(n_infeasible, h->ninf, B * 4, cudaMemcpyDeviceToDevice, h->stream));
+    return HMPC_OK;
+}
+
+int hmpc_hot_path_info(hmpc_handle* h, int* warps_per_sm, int* kcap, int* regs, int64_t* n_deferred) {
+    if (int rc = check_handle(h)) return rc;
+    if (warps_per_sm) *warps_per_sm = h->warp_ok ? h->warp_per_sm : 0;
+    if (kcap) *kcap = h->warp_ok ? h->warp_kcap : 0;
+    if (regs) *regs = h->warp_ok ? h->warp_regs : 0;
+    if (n_deferred) {
+        int32_t v = 0;
+        HMPC_CUDA(cudaMemcpyAsync(&v, h->n_defer, 4, cudaMemcpyDeviceToHost, h->stream));
+        HMPC_CUDA(cudaStreamSynchronize(h->stream));
+        *n_deferred = v;
+    }
     return HMPC_OK;
 }
 

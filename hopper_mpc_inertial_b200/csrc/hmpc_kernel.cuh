@@ -16,7 +16,8 @@ namespace hmpc {
 // iterates and residuals stay FP64 and the refinement loops recover FP64-level accuracy)
 template <int THREADS, int MIN_CTAS, bool SMEM_MATS, typename F, bool WITH_ADMM>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
-mpc_kernel(QpConst c, int B, int sm_count, double* __restrict__ ws, int* __restrict__ work_ctr, MpcIo io) {
+mpc_kernel(QpConst c, int B, int sm_count, double* __restrict__ ws, int* __restrict__ work_ctr,
+           const int* __restrict__ list, const int* __restrict__ list_cnt, MpcIo io) {
     extern __shared__ double smem[];
     __shared__ int s_next;
     Work w;
@@ -28,13 +29,15 @@ mpc_kernel(QpConst c, int B, int sm_count, double* __restrict__ ws, int* __restr
     sys.solver_warp = blockIdx.x / sm_count;
     // dynamic distribution of hoppers over the persistent CTAs (solve times differ: warm active-set path
     // vs interior-point path); results do not depend on the order
+    // list mode: only the hoppers the warp kernel deferred (hmpc_warp.cuh), in any order
+    const int count = list ? *list_cnt : B;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_next = atomicAdd(work_ctr, 1);
         __syncthreads();
-        const int b = s_next;
-        if (b >= B) break;
-        mpc_hopper<WITH_ADMM>(c, w, sys, A, b, B, io);
+        const int i = s_next;
+        if (i >= count) break;
+        mpc_hopper<WITH_ADMM>(c, w, sys, A, list ? list[i] : i, B, io);
     }
 }
 
@@ -46,6 +49,8 @@ struct MpcLaunch {
     int B, sm_count;
     double* ws;
     int* work_ctr;
+    const int* list;        // null: hoppers 0..B-1; else the deferral list of the warp kernel
+    const int* list_cnt;
 };
 
 template <int THREADS, int MIN_CTAS, bool SMEM_MATS, typename F, bool WITH_ADMM>
@@ -54,7 +59,7 @@ inline cudaError_t mpc_set_smem(int bytes) {
 }
 template <int THREADS, int MIN_CTAS, bool SMEM_MATS, typename F, bool WITH_ADMM>
 inline void mpc_launch(const MpcLaunch& l, const QpConst& qc, const MpcIo& io) {
-    mpc_kernel<THREADS, MIN_CTAS, SMEM_MATS, F, WITH_ADMM><<<l.grid, THREADS, l.smem, l.stream>>>(qc, l.B, l.sm_count, l.ws, l.work_ctr, io);
+    mpc_kernel<THREADS, MIN_CTAS, SMEM_MATS, F, WITH_ADMM><<<l.grid, THREADS, l.smem, l.stream>>>(qc, l.B, l.sm_count, l.ws, l.work_ctr, l.list, l.list_cnt, io);
 }
 
 // the instantiations the library ships (defined in csrc/inst_*.cu)
@@ -68,5 +73,21 @@ cudaError_t mpc_set_smem_wide_smem(int bytes);    // 256 threads, 1 CTA/SM, shar
 void mpc_launch_wide_smem(const MpcLaunch&, const QpConst&, const MpcIo&);
 cudaError_t mpc_set_smem_wide_gmem(int bytes);    // 256 threads, matrices in the L2-resident workspace, FP64 factor
 void mpc_launch_wide_gmem(const MpcLaunch&, const QpConst&, const MpcIo&);
+
+
+// the warp-per-hopper warm-path kernel (hmpc_warp.cuh, instantiated in inst_warp.cu)
+struct WarpLaunch {
+    int grid, wpc, rounds;  // CTAs, warps per CTA, 1: lock-step rounds kernel
+    size_t smem;            // dynamic shared memory per CTA
+    cudaStream_t stream;
+    int B, kcap, wdoubles;
+    double* hws;            // per-warp Hessian workspace
+    size_t hstride;
+    int *work_ctr, *defer_list, *defer_cnt;
+};
+bool warp_wpc_supported(int rounds, int wpc);
+cudaError_t warp_set_smem(int rounds, int wpc, int bytes);
+cudaError_t warp_regs(int rounds, int wpc, int* regs);
+void warp_launch(const WarpLaunch&, const QpConst&, const MpcIo&);
 
 }  // namespace hmpc

@@ -1,0 +1,56 @@
+// inst_warp.cu -- instantiations of the warp-per-hopper warm-path kernel (hmpc_warp.cuh), its own translation unit.
+#include "hmpc_kernel.cuh"
+#include "hmpc_warp.cuh"
+
+namespace hmpc {
+
+// SLOTS = 2: systems of order <= 64 (N <= 10).  Warps per CTA only changes how the SM's shared memory is cut up
+// (free-running kernel) / how many hoppers run their trials in lock-step (rounds kernel).
+#define HMPC_WARP_DISPATCH(rounds, wpc, CALL)                      \
+    if (rounds) {                                                  \
+        switch (wpc) {                                             \
+            case 2: CALL(mpc_warp_rounds_kernel, 2, 8); break;     \
+            case 4: CALL(mpc_warp_rounds_kernel, 4, 4); break;     \
+            case 5: CALL(mpc_warp_rounds_kernel, 5, 3); break;     \
+            case 8: CALL(mpc_warp_rounds_kernel, 8, 2); break;     \
+            default: CALL(mpc_warp_rounds_kernel, 10, 1); break;   \
+        }                                                          \
+    } else {                                                       \
+        switch (wpc) {                                             \
+            case 1: CALL(mpc_warp_kernel, 1, 16); break;           \
+            case 2: CALL(mpc_warp_kernel, 2, 8); break;            \
+            default: CALL(mpc_warp_kernel, 4, 4); break;           \
+        }                                                          \
+    }
+
+bool warp_wpc_supported(int rounds, int wpc) {
+    return rounds ? (wpc == 2 || wpc == 4 || wpc == 5 || wpc == 8 || wpc == 10) : (wpc == 1 || wpc == 2 || wpc == 4);
+}
+
+cudaError_t warp_set_smem(int rounds, int wpc, int bytes) {
+    cudaError_t e = cudaSuccess;
+#define CALL(K, W, M) e = cudaFuncSetAttribute(K<2, W, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
+    HMPC_WARP_DISPATCH(rounds, wpc, CALL)
+#undef CALL
+    return e;
+}
+
+cudaError_t warp_regs(int rounds, int wpc, int* regs) {
+    cudaFuncAttributes a;
+    cudaError_t e = cudaSuccess;
+#define CALL(K, W, M) e = cudaFuncGetAttributes(&a, K<2, W, M>)
+    HMPC_WARP_DISPATCH(rounds, wpc, CALL)
+#undef CALL
+    if (e == cudaSuccess) *regs = a.numRegs;
+    return e;
+}
+
+void warp_launch(const WarpLaunch& l, const QpConst& qc, const MpcIo& io) {
+#define CALL(K, W, M)                                                                                     \
+    K<2, W, M><<<l.grid, 32 * W, l.smem, l.stream>>>(qc, l.B, l.kcap, l.wdoubles, l.hws, l.hstride,       \
+                                                     l.work_ctr, l.defer_list, l.defer_cnt, io)
+    HMPC_WARP_DISPATCH(l.rounds, l.wpc, CALL)
+#undef CALL
+}
+
+}  // namespace hmpc

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define HMPC_ABI_VERSION 1
+#define HMPC_ABI_VERSION 2
 #define HMPC_INF 1e30          /* "no bound" marker (same convention as OSQP's OSQP_INFTY) */
 #define HMPC_NX 12             /* Euler MPC state  [p, rpy, pdot_w, omega_w]  (mpc_cvx_euler_3f.py:21) */
 #define HMPC_NU 6              /* control [f(3), tau_body(3)]                 (mpc_cvx_euler_3f.py:22) */
@@ -62,6 +62,7 @@ enum { HMPC_UREF_ALIASED = 0, HMPC_UREF_PER_STAGE = 1 };   /* SURVEY App. D1    
 enum { HMPC_SOLVER_EXACT = 0, HMPC_SOLVER_ADMM = 1 };
 enum { HMPC_MODE_EARLY_EXIT = 0, HMPC_MODE_FIXED_ITER = 1 };
 enum { HMPC_INFEASIBLE_HOLD = 0, HMPC_INFEASIBLE_RESPAWN = 1 };
+enum { HMPC_HOT_AUTO = 0, HMPC_HOT_CTA = 1 };
 
 /* Constants of Mpc.__init__ (mpc_cvx_euler_3f.py:12-39), Runner.__init__ (robotrunner.py:37-79) and
  * the literals inside build_qp (mpc_cvx_euler_3f.py:113-146), plus solver settings. */
@@ -94,6 +95,9 @@ typedef struct hmpc_config {
                               about the time-shifted previous solution (mpc_cvx_euler_3f.py:59-68); k > 1 relinearises
                               about the sweep's own solution and solves again (the SQP the reference's docstring
                               gestures at, mpc_cvx_euler_3f.py:41-46).  0 is treated as 1 */
+    int32_t hot_path;      /* HMPC_HOT_AUTO: warm ticks run the warp-per-hopper kernel, hoppers it cannot finish (and
+                              first calls, ADMM, FP32, sqp_sweeps > 1, long horizons) the CTA-per-hopper kernel;
+                              HMPC_HOT_CTA: CTA-per-hopper kernel only (round-1 path, kept for A/B measurements) */
     double mpc_dt;         /* robotrunner.py:47  0.02  */
     double sim_dt;         /* run.py:24          1e-3  */
     double m, g, mu;       /* robotrunner.py:37,42,68 */
@@ -196,6 +200,13 @@ int hmpc_solve_stats(hmpc_handle* h, int32_t* nfac, int32_t* path, int32_t* n_in
  * of the solver kernel and of the simulator kernel over the most recent hmpc_rollout and its tick count. */
 int hmpc_set_timing(hmpc_handle* h, int enable);
 int hmpc_kernel_times(hmpc_handle* h, double* mpc_ms, double* sim_ms, int* n_ticks);
+
+/* The warp-per-hopper hot path of this handle (hmpc_config.hot_path): resident warps (= hoppers in flight) per SM,
+ * the cap on the order of the compact KKT system it keeps in shared memory, registers per thread, and how many
+ * hopper-ticks of the most recent hmpc_solve / hmpc_rollout it handed to the CTA-per-hopper kernel (host value;
+ * synchronises the stream).  warps_per_sm = 0 when the handle's configuration does not use the warp kernel.
+ * Each pointer may be NULL. */
+int hmpc_hot_path_info(hmpc_handle* h, int* warps_per_sm, int* kcap, int* regs, int64_t* n_deferred);
 
 /* Counters since handle creation: kernels launched by this library (for bench gpu_launches). */
 int hmpc_launch_count(hmpc_handle* h, int64_t* n_launches);

@@ -11,7 +11,7 @@ _ROOT = os.path.dirname(os.path.dirname(_HERE))
 _SO = os.path.join(_HERE, "libhmpc_emul.so")
 _DEPS = [os.path.join(_HERE, "emul.cpp"), os.path.join(_HERE, "fake_cuda", "cuda_runtime.h"),
          os.path.join(_ROOT, "include", "hmpc.h")] + \
-        [os.path.join(_ROOT, "hopper_mpc_inertial_b200", "csrc", f) for f in ("hmpc_sim.cuh", "hmpc_qp.cuh", "hmpc_mpc.cuh")]
+        [os.path.join(_ROOT, "hopper_mpc_inertial_b200", "csrc", f) for f in ("hmpc_sim.cuh", "hmpc_qp.cuh", "hmpc_mpc.cuh", "hmpc_warp.cuh")]
 _lib = None
 
 
@@ -38,11 +38,12 @@ def default_config(**over):
     hmpc_default_config; tests/test_abi.py checks the two agree)."""
     from hopper_mpc_inertial_b200._lib import HmpcConfig
     cfg = HmpcConfig()
-    cfg.abi_version, cfg.device, cfg.batch, cfg.dyn, cfg.N, cfg.mpc_factor = 1, 0, 1, 3, 60, 20
+    cfg.abi_version, cfg.device, cfg.batch, cfg.dyn, cfg.N, cfg.mpc_factor = 2, 0, 1, 3, 60, 20
     cfg.precision = cfg.uref_mode = cfg.solver = cfg.mode = 0
     cfg.max_iter, cfg.check_interval, cfg.first_check, cfg.polish = 10000, 25, 25, 1
     cfg.adaptive_rho, cfg.warm_start, cfg.polish_retries, cfg.ipm_max_iter, cfg.on_infeasible = 1, 1, 8, 40, 0
     cfg.sqp_sweeps = 1
+    cfg.hot_path = 0
     cfg.mpc_dt, cfg.sim_dt, cfg.m, cfg.g, cfg.mu = 0.02, 1e-3, 7.5, 9.807, 1.0
     J = np.array([[76148072.89e-9, 70089.52e-9, 2067970.36e-9], [70089.52e-9, 45477183.53e-9, -87045.58e-9],
                   [2067970.36e-9, -87045.58e-9, 76287220.47e-9]])
@@ -99,6 +100,7 @@ class EmulMpc:
                                int(bool(init)), _p(self.Xsol), _p(self.Usol), _p(self.code), _p(self.valid),
                                _p(U), _p(Xs), _p(st), _p(it), _p(nf), _p(pa))
         assert rc == 0
+        self.warp_done = load().emul_warp_done()      # hoppers finished by the warp-per-hopper path
         return U, Xs, st, it, nf, pa
 
     def condense(self, x_in, x_guess, x_ref, pf, Cbits):

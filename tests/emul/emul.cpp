@@ -4,15 +4,91 @@
 // kernels execute: arithmetic, control flow, indexing.  It cannot see races or barrier bugs -- those
 // are covered by the -m gpu tests and compute-sanitizer runs on the GPU box.  Never shipped, never
 // loaded by the product package.
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <ucontext.h>
+#include <functional>
 #include <vector>
 
 #include "cuda_runtime.h"   // tests/emul/fake_cuda
 #include "../../hopper_mpc_inertial_b200/csrc/hmpc_sim.cuh"
 #include "../../hopper_mpc_inertial_b200/csrc/hmpc_mpc.cuh"
+#include "../../hopper_mpc_inertial_b200/csrc/hmpc_warp.cuh"
 
 using namespace hmpc;
+
+// ---- 32-lane warp emulation: cooperative fibers that meet at every warp-synchronous primitive ----
+int hmpc_emul_tid = 0, hmpc_emul_bdim = 1;
+double hmpc_emul_xd[32];
+long long hmpc_emul_xi[32];
+
+namespace {
+constexpr int NL = 32;
+constexpr size_t kStack = 512 * 1024;
+ucontext_t g_main, g_ctx[NL];
+std::vector<char> g_stack[NL];
+bool g_done[NL];
+int g_arrived = 0, g_live = 0;
+unsigned long g_gen = 0;
+std::function<void(int)> g_body;
+
+void fiber_switch_from(int me) {
+    int next = me;
+    for (int t = 1; t <= NL; ++t) {
+        const int cand = (me + t) % NL;
+        if (!g_done[cand]) { next = cand; break; }
+    }
+    if (next == me) return;
+    hmpc_emul_tid = next;
+    swapcontext(&g_ctx[me], &g_ctx[next]);
+    hmpc_emul_tid = me;
+}
+
+void fiber_entry(int lane) {
+    g_body(lane);
+    g_done[lane] = true;
+    --g_live;
+    if (g_live == 0) { setcontext(&g_main); }
+    for (int t = 1; t <= NL; ++t) {
+        const int cand = (lane + t) % NL;
+        if (!g_done[cand]) { hmpc_emul_tid = cand; setcontext(&g_ctx[cand]); }
+    }
+    abort();
+}
+
+void run_warp(const std::function<void(int)>& body) {
+    g_body = body;
+    g_arrived = 0; g_live = NL;
+    for (int l = 0; l < NL; ++l) {
+        if (g_stack[l].empty()) g_stack[l].resize(kStack);
+        g_done[l] = false;
+        getcontext(&g_ctx[l]);
+        g_ctx[l].uc_stack.ss_sp = g_stack[l].data();
+        g_ctx[l].uc_stack.ss_size = kStack;
+        g_ctx[l].uc_link = nullptr;
+        makecontext(&g_ctx[l], (void (*)())fiber_entry, 1, l);
+    }
+    hmpc_emul_bdim = NL;
+    hmpc_emul_tid = 0;
+    swapcontext(&g_main, &g_ctx[0]);
+    hmpc_emul_bdim = 1;
+    hmpc_emul_tid = 0;
+}
+}  // namespace
+
+void hmpc_emul_rendezvous() {
+    const unsigned long gen = g_gen;
+    if (++g_arrived == NL) { g_arrived = 0; ++g_gen; return; }
+    long spins = 0;
+    while (g_gen == gen) {
+        if (g_live < NL || ++spins > 100000) {
+            fprintf(stderr, "hmpc emul: warp deadlock (a lane skipped a warp-synchronous primitive or returned early)\n");
+            abort();
+        }
+        fiber_switch_from(hmpc_emul_tid);
+    }
+}
 
 static QpConst qp_const(const hmpc_config& cfg) {
     QpConst c;
@@ -38,6 +114,8 @@ static QpConst qp_const(const hmpc_config& cfg) {
     return c;
 }
 
+static int g_emul_warp_done = 0;
+
 extern "C" {
 
 // Same contract as hmpc_solve, all pointers HOST memory, state arrays owned by the caller:
@@ -59,15 +137,39 @@ int emul_solve(const hmpc_config* cfg, const double* Qd, const double* Rd, const
     io.U_out = U; io.X_out = Xsol; io.U0_out = nullptr;
     io.status = status; io.iters = iters; io.st_tick = st_tick.data(); io.nfac = nfac; io.path = path;
     io.ninf = ninf.data(); io.flops = nullptr; io.init = init; io.accumulate = 0; io.respawn = 0;
+    // the library's dispatch (hmpc_api.cu: launch_mpc): warm ticks go through the warp-per-hopper kernel first,
+    // hoppers it defers (and everything else) through the CTA kernel
+    std::vector<char> deferred(B, 1);
+    g_emul_warp_done = 0;
+    if (warp_path_applies(*cfg, init)) {
+        const int kcap = warp_kcap(*cfg);
+        std::vector<double> wsm(warp_work_doubles(N, kcap) + 8), hc((size_t)n * n + 8);
+        for (int b = 0; b < B; ++b) {
+            int done = 0;
+            run_warp([&](int lane) {
+                WWork ww;
+                wcarve(ww, wsm.data(), N, kcap);
+                ww.Hc = hc.data();
+                const int d = (N <= 10) ? mpc_hopper_warp<2>(c, ww, kcap, b, B, io, lane)
+                                        : mpc_hopper_warp<4>(c, ww, kcap, b, B, io, lane);
+                if (lane == 0) done = d;
+            });
+            deferred[b] = done ? 0 : 1;
+            g_emul_warp_done += done;
+        }
+    }
     if (cfg->precision == HMPC_FP32) {
         LinSys<float> sys{n, 0, 0, reinterpret_cast<float*>(w.Lm), reinterpret_cast<float*>(w.dinv), w.H, w.idx, w.grow};
-        for (int b = 0; b < B; ++b) mpc_hopper<true>(c, w, sys, A, b, B, io);
+        for (int b = 0; b < B; ++b) if (deferred[b]) mpc_hopper<true>(c, w, sys, A, b, B, io);
     } else {
         LinSys<double> sys{n, 0, 0, reinterpret_cast<double*>(w.Lm), reinterpret_cast<double*>(w.dinv), w.H, w.idx, w.grow};
-        for (int b = 0; b < B; ++b) mpc_hopper<true>(c, w, sys, A, b, B, io);
+        for (int b = 0; b < B; ++b) if (deferred[b]) mpc_hopper<true>(c, w, sys, A, b, B, io);
     }
     return 0;
 }
+
+// hoppers the warp path finished in the most recent emul_solve
+int emul_warp_done(void) { return g_emul_warp_done; }
 
 // condense only: H [n][n][B], g [n][B], lo/hi [m][B], infeasible [B]
 int emul_condense(const hmpc_config* cfg, const double* Qd, const double* Rd, const double* x_in,

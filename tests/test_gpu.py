@@ -32,7 +32,7 @@ def cb64(c):
 def test_library_is_loaded_and_has_no_fallback():
     assert torch.cuda.is_available()
     lib = _lib.load()
-    assert lib.hmpc_abi_version() == 1
+    assert lib.hmpc_abi_version() == 2
     bm = mk(4)
     assert bm.launch_count() == 0
     bm.convert(T(np.tile(np.array([0, 0, .3, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0.0])[:, None], (1, 4))))
@@ -130,6 +130,38 @@ def test_closed_loop_rollout_matches_oracle(dyn, precision):
         assert np.all(np.abs(Ug[:, :, b] - Uo) <= 10 * u_tol(Uo)), np.abs(Ug[:, :, b] - Uo).max()
         # closed-loop state tolerance: 1e-6 abs (errors of the per-tick optimum feed back through the loop)
         np.testing.assert_allclose(Xg[:, :, b], Xo, rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("dyn", ["3f", "2f"])
+def test_warp_kernel_equals_cta_kernel_and_oracle(dyn):
+    """hot_path auto (warp-per-hopper kernel + CTA fallback for the hoppers it defers) against hot_path cta (round-1
+    CTA-per-hopper kernel only) and against the oracle loop: same closed loop, every tick KKT-verified, and the warp
+    kernel really carried the warm ticks (deferred fraction small)."""
+    B, N, n_ticks = 256, 10, 40
+    sc = scenarios.make_batch(B, N=N, n_ticks=n_ticks, seed=11, dyn=dyn)
+    logs = {}
+    for mode in ("auto", "cta"):
+        bm = mk(B, dyn, N, hot_path=mode)
+        bm.set_gains(T(sc["Qdiag"]), T(sc["Rdiag"]))
+        X = T(sc["X0"]).clone()
+        out = bm.rollout(X, T(sc["xref_tab"]), T(sc["pf_tab"]), cb64(sc["C_tab"]), T(sc["pf_switch"]), 0, n_ticks, True, log=True)
+        info = bm.hot_path_info()
+        logs[mode] = (out["X_log"].cpu().numpy(), out["U_log"].cpu().numpy(), out["status"].cpu().numpy(), info)
+    Xa, Ua, sa, ia = logs["auto"]
+    Xc, Uc, sc_, ic = logs["cta"]
+    assert ia["warps_per_sm"] >= 8 and ic["warps_per_sm"] == 0
+    assert ia["deferred"] < 0.1 * B * (n_ticks - 1), ia
+    ok = (sa == 0) & (sc_ == 0)
+    assert ok.sum() >= B - 4, (sa, sc_)
+    # both paths return the KKT-verified optimum of every tick: the closed loops agree far below the parity bound
+    assert np.abs(Ua[:, :, ok] - Uc[:, :, ok]).max() < 1e-5
+    np.testing.assert_allclose(Xa[:, :, ok], Xc[:, :, ok], rtol=0, atol=1e-6)
+    for b in np.where(ok)[0][:6]:
+        p = ho.Params(dyn=dyn, N=N, Qdiag=sc["Qdiag"][:, b].copy(), Rdiag=sc["Rdiag"][:, b].copy())
+        Xo, Uo = closed_loop(p, sc["X0"][:, b], sc["xref_tab"][:, :, b], sc["pf_tab"][:, :, b], sc["C"][:, b],
+                             sc["pf_switch"][:, b], n_ticks)
+        assert np.all(np.abs(Ua[:, :, b] - Uo) <= 10 * u_tol(Uo)), np.abs(Ua[:, :, b] - Uo).max()
+        np.testing.assert_allclose(Xa[:, :, b], Xo, rtol=0, atol=1e-6)
 
 
 def test_sqp_sweeps_match_oracle():
