@@ -37,7 +37,8 @@ mpc_kernel(QpConst c, int B, int sm_count, double* __restrict__ ws, int* __restr
         __syncthreads();
         const int i = s_next;
         if (i >= count) break;
-        mpc_hopper<WITH_ADMM>(c, w, sys, A, list ? list[i] : i, B, io);
+        const int e = list ? list[i] : i;     // bit 30: the warp kernel's active-set refinement already gave up
+        mpc_hopper<WITH_ADMM>(c, w, sys, A, e & ~(1 << 30), B, io, (e >> 30) & 1);
     }
 }
 

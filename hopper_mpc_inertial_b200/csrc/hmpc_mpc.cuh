@@ -87,7 +87,8 @@ struct MpcIo {
 // One hopper b of a batch of B.  All threads of the CTA call this together.
 // WITH_ADMM = false compiles the OSQP-style ADMM branch out (smaller kernel for the default exact solver)
 template <bool WITH_ADMM, class Sys>
-__device__ inline void mpc_hopper(const QpConst& c, Work& w, Sys& sys, const AOp& A, int b, int B, const MpcIo& io) {
+__device__ inline void mpc_hopper(const QpConst& c, Work& w, Sys& sys, const AOp& A, int b, int B, const MpcIo& io,
+                                  int skip_warm = 0) {
     const int N = c.N, n = 6 * N, m = 11 * N, tid = threadIdx.x, T = blockDim.x;
     double* xs = w.err;   // reused after condense: solution trajectory [(N+1)][12]
     __syncthreads();
@@ -173,7 +174,8 @@ __device__ inline void mpc_hopper(const QpConst& c, Work& w, Sys& sys, const AOp
                     if (polish_verified(c, w, sys, A, info)) info.status = ST_SOLVED;
                 }
             } else {
-                info = solve_exact(c, w, sys, A, warm);
+                // skip_warm: the warp kernel ran this very refinement from this very start and gave up
+                info = solve_exact(c, w, sys, A, warm && !skip_warm);
             }
             its += info.iters; nfac += info.nfac; path = info.path;
             if (info.status != 0 && st == 0) st = info.status;

@@ -28,6 +28,10 @@
 #include "hmpc_qp.cuh"
 #include "hmpc_mpc.cuh"
 
+#ifndef HMPC_EMUL_COUNT
+#define HMPC_EMUL_COUNT(k) ((void)0)     // tests/emul counts events (factorisations, solves, Hessian products)
+#endif
+
 namespace hmpc {
 
 constexpr unsigned kFullMask = 0xffffffffu;
@@ -46,50 +50,56 @@ struct WWork {
     // QP + solver vectors
     double *g, *xp, *hx;         // [n]
     double *mul;                 // [m]
-    double *rhs;                 // [kcap]  right-hand side / solution of the compact system
-    double *rs;                  // [kcap]  1 / |v_jj| of the factor
-    double *xc;                  // [n]     compact copy of xp for the Hessian product
-    double *L;                   // packed lower triangle of V, order <= kcap (+4 doubles of slack)
-    double *Hc;                  // GLOBAL: Hessian over the non-fixed variables, [nf][nf]
+    double *rhs;                 // [kcap]  right-hand side / solution of the compact system (padded ordering)
+    double *xc;                  // [n + 4] compact copy of xp for the Hessian product
+    double *L;                   // factor: lower block triangle of 8x8 tiles, order <= kcap = 56, + one scratch tile
+    double *Hc;                  // GLOBAL: Hessian over the non-fixed variables, [nf][ld], ld = nf rounded up to 8
     uint8_t *fr;                 // [n]  compact -> variable, the non-fixed variables in order
     uint8_t *cpos;               // [n]  variable -> compact (undefined for fixed variables)
     uint8_t *idx;                // [n]  variables of the current KKT system (compact Hessian index)
     uint8_t *grow;               // [kcap] active general rows of the current system (row index - n)
     int8_t *code, *pin, *fixed, *side, *stance;   // [m] [n] [n] [m] [N]
-    int nf;
+    int nf, ld;
+    int nt_max;                  // tiles per side of the factor storage (kcap / 8)
 };
 
-__host__ __device__ inline size_t warp_tri(int k) { return (size_t)k * (k + 1) / 2; }
+constexpr int kWarpKcap = 56;                       // 7 tiles of 8: largest order of the compact KKT system
+// factor storage for systems of order <= kcap: lower block triangle of 8x8 tiles + one scratch tile
+__host__ __device__ inline size_t warp_factor_doubles(int kcap) { const size_t nt = ((size_t)kcap + 7) / 8; return (nt * (nt + 1) / 2 + 1) * 64; }
+// condense-only arrays (cz sz PC PS Bw err) live on top of the factor, which is dead while they are in use
+__host__ __device__ inline size_t warp_alias_doubles(int N) { return (size_t)(4 * N + 2 + 18 * N + 12 * (N + 1)); }
 // doubles of one warp's shared-memory slice
 __host__ __device__ inline size_t warp_work_doubles(int N, int kcap) {
     const size_t n = 6 * (size_t)N, m = 11 * (size_t)N;
     size_t d = 0;
-    d += 4 * N + 2;                 // cz sz PC PS
-    d += 18 * N;                    // Bw
-    d += 12 + 12 + 6;               // xin Qd Rd
+    const size_t f = warp_factor_doubles(kcap), al = (warp_alias_doubles(N) + 1) & ~(size_t)1;
+    d += f > al ? f : al;           // L | cz sz PC PS Bw err
+    d += ((n + 7) & ~(size_t)7);    // xc | rhs
     d += 2 * N + 24;                // hinv hlo blo bhi
-    d += 12 * (N + 1);              // err
-    d += 4 * n;                     // g xp hx xc
+    d += 12 + 6;                    // Qd Rd
+    d += 12;                        // xin
+    d += 3 * n;                     // g xp hx
     d += m;                         // mul
-    d += 2 * (size_t)kcap;          // rhs rs
-    d += warp_tri(kcap) + 4;        // L
-    d += (4 * n + (size_t)kcap + 2 * m + N + 7) / 8;   // bytes: fr cpos idx fixed(+pin shares below) ...
-    d += (n + 7) / 8;               // pin
+    d += (5 * n + (size_t)kcap + 2 * m + N + 7) / 8;   // bytes: fr cpos idx fixed pin | grow | code side | stance
     return (d + 1) & ~(size_t)1;
 }
 __device__ inline void wcarve(WWork& w, double* base, int N, int kcap) {
     const int n = 6 * N, m = 11 * N;
     double* p = base;
     auto take = [&](size_t k) { double* r = p; p += k; return r; };
-    w.cz = take(N); w.sz = take(N); w.PC = take(N + 1); w.PS = take(N + 1);
-    w.Bw = take(18 * N);
-    w.xin = take(12); w.Qd = take(12); w.Rd = take(6);
+    const size_t f = warp_factor_doubles(kcap), al = (warp_alias_doubles(N) + 1) & ~(size_t)1;
+    w.L = take(f > al ? f : al);                // 16-byte aligned pieces first (the slice itself is)
+    {
+        double* q = w.L;                         // aliases of the factor: condense / roll-out only
+        w.cz = q; q += N; w.sz = q; q += N; w.PC = q; q += N + 1; w.PS = q; q += N + 1;
+        w.Bw = q; q += 18 * N; w.err = q;
+    }
+    w.xc = take((n + 7) & ~7);
+    w.rhs = w.xc;                                // the compact right-hand side is formed after the Hessian product
     w.hinv = take(N); w.hlo = take(N); w.blo = take(12); w.bhi = take(12);
-    w.err = take(12 * (N + 1));
-    w.g = take(n); w.xp = take(n); w.hx = take(n); w.xc = take(n);
+    w.Qd = take(12); w.Rd = take(6); w.xin = take(12);
+    w.g = take(n); w.xp = take(n); w.hx = take(n);
     w.mul = take(m);
-    w.rhs = take(kcap); w.rs = take(kcap);
-    w.L = take(warp_tri(kcap) + 4);
     uint8_t* q = reinterpret_cast<uint8_t*>(p);
     w.fr = q; q += n; w.cpos = q; q += n; w.idx = q; q += n; w.grow = q; q += kcap;
     w.code = reinterpret_cast<int8_t*>(q); q += m;
@@ -97,7 +107,7 @@ __device__ inline void wcarve(WWork& w, double* base, int N, int kcap) {
     w.fixed = reinterpret_cast<int8_t*>(q); q += n;
     w.pin = reinterpret_cast<int8_t*>(q); q += n;
     w.stance = reinterpret_cast<int8_t*>(q); q += N;
-    w.nf = 0;
+    w.nf = 0; w.ld = 0; w.nt_max = (kcap + 7) / 8;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -243,6 +253,25 @@ __device__ __forceinline__ void wbv(const QpConst& c, const WWork& w, int k, dou
     }
 }
 
+// Linearisation of all stages about the time-shifted previous solution: x_guess[0] = x_in, x_guess[k] = x.value[k+1]
+// (mpc_cvx_euler_3f.py:59-62; only p and yaw matter).  Needs w.xin; fills w.cz, w.sz, w.Bw (they alias the factor:
+// wcondense fills them before the first factorisation, wfinish again after the last solve).
+__device__ inline void wlinearize_all(const QpConst& c, WWork& w, int b, int B, const MpcIo& io, int lane) {
+    const int N = c.N;
+    const size_t Bs = (size_t)B;
+    for (int k = lane; k < N; k += 32) {
+        double gp[4], pf[3];
+        if (k == 0) { gp[0] = w.xin[0]; gp[1] = w.xin[1]; gp[2] = w.xin[2]; gp[3] = w.xin[5]; }
+        else {
+            const size_t o = (size_t)(k + 1) * 12;
+            gp[0] = io.Xsol[(o + 0) * Bs + b]; gp[1] = io.Xsol[(o + 1) * Bs + b];
+            gp[2] = io.Xsol[(o + 2) * Bs + b]; gp[3] = io.Xsol[(o + 5) * Bs + b];
+        }
+        for (int i = 0; i < 3; ++i) pf[i] = io.pf[(size_t)(3 * k + i) * Bs + b];
+        wlinearize_stage(c, gp, pf, w.cz + k, w.sz + k, w.Bw + 18 * k);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // load + time shift + linearise + condense for hopper b (warm tick).  Returns 1 (all lanes) when a height row
 // cannot be met.  Leaves Hc (global, compact), g, bounds, fixed / fr / cpos in place.
@@ -266,19 +295,8 @@ __device__ inline int wcondense(const QpConst& c, WWork& w, int b, int B, const 
         w.blo[lane] = lo; w.bhi[lane] = hi;
     }
     __syncwarp();
-    // linearisation point: x_guess[0] = x_in, x_guess[k] = x.value[k+1] (mpc_cvx_euler_3f.py:59-62); p and yaw only
-    for (int k = lane; k < N; k += 32) {
-        double gp[4], pf[3];
-        if (k == 0) { gp[0] = w.xin[0]; gp[1] = w.xin[1]; gp[2] = w.xin[2]; gp[3] = w.xin[5]; }
-        else {
-            const size_t o = (size_t)(k + 1) * 12;
-            gp[0] = io.Xsol[(o + 0) * Bs + b]; gp[1] = io.Xsol[(o + 1) * Bs + b];
-            gp[2] = io.Xsol[(o + 2) * Bs + b]; gp[3] = io.Xsol[(o + 5) * Bs + b];
-        }
-        for (int i = 0; i < 3; ++i) pf[i] = io.pf[(size_t)(3 * k + i) * Bs + b];
-        wlinearize_stage(c, gp, pf, w.cz + k, w.sz + k, w.Bw + 18 * k);
-        w.hinv[k] = (k >= 2) ? 1.0 / (double)(k - 1) : 0.0;
-    }
+    wlinearize_all(c, w, b, B, io, lane);
+    for (int k = lane; k < N; k += 32) w.hinv[k] = (k >= 2) ? 1.0 / (double)(k - 1) : 0.0;
     for (int v = lane; v < n; v += 32) w.fixed[v] = (wbox_hi(w, v) - wbox_lo(w, v)) < 1e-12 ? 1 : 0;
     __syncwarp();
     // prefix sums of cos / sin (same summation order as condense())
@@ -289,6 +307,7 @@ __device__ inline int wcondense(const QpConst& c, WWork& w, int b, int B, const 
     }
     // non-fixed variables, in order
     w.nf = wcompact(0, n, n, w.fr, 0, lane, [&](int v) { return w.fixed[v] == 0; });
+    w.ld = (w.nf + 7) & ~7;
     __syncwarp();
     for (int i = lane; i < w.nf; i += 32) w.cpos[w.fr[i]] = (uint8_t)i;
     const double dt = c.dt, gdt = -c.g * dt;
@@ -320,8 +339,10 @@ __device__ inline int wcondense(const QpConst& c, WWork& w, int b, int B, const 
     infeasible = __any_sync(kFullMask, infeasible);
     __syncwarp();
     // ---- Hessian blocks (a >= b), non-fixed entries only, written to both triangles of the compact square ----
-    const int nf = w.nf;
+    const int nf = w.ld;                 // leading dimension of the compact square
     double* Hc = w.Hc;
+    for (int i = lane; i < w.nf; i += 32)   // zero pad columns: the tiled Hessian product reads whole 8-column tiles
+        for (int j = w.nf; j < nf; ++j) Hc[i * nf + j] = 0.0;
     const int nblk = N * (N + 1) / 2;
     const double q3 = w.Qd[3], q4 = w.Qd[4], q5 = w.Qd[5];
     const double dt2 = dt * dt;
@@ -416,225 +437,291 @@ __device__ inline int wcondense(const QpConst& c, WWork& w, int b, int B, const 
 }
 
 // ------------------------------------------------------------------------------------------------
-// hx = H xp over the non-fixed variables (H compact square in global memory): lanes over the compact row,
-// one coalesced row segment per column.  Ends with a __syncwarp().
+// FP64 tensor-core building blocks.  The kernel is bound by instruction issue, not by FP64 throughput
+// (profiles/README.md): one DMMA.8x8x4 does the work of eight warp-wide DFMAs at the full FP64 rate
+// (tools/micro/dmma.cu: 17.5 cycles per DMMA per SM sub-partition = 14.6 FMA/clk, 26 cycles latency), so the
+// dense linear algebra -- factorisation, substitutions, Hessian products -- is organised in 8x8 tiles.
+//
+// mma.sync.m8n8k4.f64 fragments, lane = 4 g + t:  A[g][t],  B[t][g],  C/D[g][2t], [g][2t+1].
+// tile_mac(acc, a, b) adds X Y^T for two row-major 8x8 tiles X, Y when lane (g, t) passes a = X[g][2t..2t+1] and
+// b = Y[g][2t..2t+1]: the two DMMAs sum over the even and the odd columns (the summation index may be permuted
+// freely).  With this order an accumulator fragment (c0, c1) IS the A fragment of the next product, so chained
+// products need no data movement, and every operand is one conflict-free 16-byte load per lane.
 // ------------------------------------------------------------------------------------------------
-template <int SLOTS>
+constexpr int kMaxTiles = 7;                       // compact KKT systems of (padded) order <= 56
+struct d2 { double x, y; };
+__device__ __forceinline__ d2 ld2(const double* p) {
+#ifdef HMPC_HOST_EMUL
+    return d2{p[0], p[1]};
+#else
+    const double2 v = *reinterpret_cast<const double2*>(p);
+    return d2{v.x, v.y};
+#endif
+}
+__device__ __forceinline__ void st2(double* p, double x, double y) {
+#ifdef HMPC_HOST_EMUL
+    p[0] = x; p[1] = y;
+#else
+    *reinterpret_cast<double2*>(p) = make_double2(x, y);
+#endif
+}
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+#ifdef HMPC_HOST_EMUL
+    hmpc_emul_dmma(&c0, &c1, a, b);
+#else
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+#endif
+}
+__device__ __forceinline__ void tile_mac(double& c0, double& c1, const d2& a, const d2& b) {
+    dmma(c0, c1, a.x, b.x);
+    dmma(c0, c1, a.y, b.y);
+}
+// lower block triangle of 8x8 row-major tiles: tile (I, J), J <= I
+__host__ __device__ __forceinline__ int tile_off(int I, int J) { return ((I * (I + 1)) / 2 + J) * 64; }
+// a vector piece v[0..8) held as "lane 4 g has v[g]" (column 0 of an accumulator) -> B fragment of the 8x1 operand:
+// lanes 0..3 get (v[2t], v[2t+1]), every other lane zero
+__device__ __forceinline__ d2 vec_to_b(double v, int lane) {
+    const int t = lane & 3;
+    const double x = __shfl_sync(kFullMask, v, 8 * t), y = __shfl_sync(kFullMask, v, 8 * t + 4);
+    return (lane < 4) ? d2{x, y} : d2{0.0, 0.0};
+}
+
+// ------------------------------------------------------------------------------------------------
+// Code-size rule for everything below: the kernel is bound by instruction FETCH (profiles/README.md: with the tile
+// loops unrolled the trial code was 140 KB and `no_instruction` the top stall even with every warp of the SM in
+// lock-step), so the tile loops are real loops (#pragma unroll 1), vectors travel through shared memory instead of
+// statically indexed register arrays, and the hot code of a trial stays within the instruction cache.
+// ------------------------------------------------------------------------------------------------
+
+// B fragment of an 8x1 operand v[0..8) read from shared memory: lanes 0..3 get (v[2t], v[2t+1]), all others zero
+__device__ __forceinline__ d2 vec_b(const double* v, int lane) {
+    return (lane < 4) ? ld2(v + 2 * lane) : d2{0.0, 0.0};
+}
+
+// ------------------------------------------------------------------------------------------------
+// hx = H xp over the non-fixed variables.  H: compact square in global memory, row-major, leading dimension
+// w.ld = nf rounded up to 8 with zero pad columns.  8x8 tiles through the tensor core, the vector as an 8x1 operand.
+// Ends with a __syncwarp().
+// ------------------------------------------------------------------------------------------------
 __device__ inline void wmatvec(WWork& w, int lane) {
-    const int nf = w.nf;
-    for (int j = lane; j < nf; j += 32) w.xc[j] = w.xp[w.fr[j]];
+    const int nf = w.nf, ld = w.ld, ntf = ld >> 3, g = lane >> 2, t = lane & 3;
+    HMPC_EMUL_COUNT(1);
+    for (int j = lane; j < ld; j += 32) w.xc[j] = j < nf ? w.xp[w.fr[j]] : 0.0;
     __syncwarp();
-    double acc[SLOTS];
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) acc[s] = 0.0;
-    const double* Hc = w.Hc;
-    int off = lane;
-#pragma unroll 4
-    for (int j = 0; j < nf; ++j) {
-        const double xj = w.xc[j];
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s) {
-            const int i = lane + 32 * s;
-            if (i < nf) acc[s] = fma(Hc[off + 32 * s], xj, acc[s]);
+    const double* hp = w.Hc + g * ld + 2 * t;
+#pragma unroll 1
+    for (int I = 0; I < ntf; ++I) {
+        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;            // two chains: even / odd column tiles
+        int K = 0;
+#pragma unroll 1
+        for (; K + 1 < ntf; K += 2) {
+            const d2 h0 = ld2(hp + 8 * K), h1 = ld2(hp + 8 * K + 8);
+            tile_mac(a0, a1, h0, vec_b(w.xc + 8 * K, lane));
+            tile_mac(b0, b1, h1, vec_b(w.xc + 8 * K + 8, lane));
         }
-        off += nf;
-    }
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-        const int i = lane + 32 * s;
-        if (i < nf) w.hx[w.fr[i]] = acc[s];
+        if (K < ntf) tile_mac(a0, a1, ld2(hp + 8 * K), vec_b(w.xc + 8 * K, lane));
+        const int i = 8 * I + g;
+        if (t == 0 && i < nf) w.hx[w.fr[i]] = a0 + b0;
+        hp += 8 * ld;
     }
     __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------
-// Signed Cholesky  K = V S V'  of the compact KKT system of order nk = nF + ng (see LinSys in hmpc_qp.cuh for
-// the system: variables idx[0..nF), active general rows grow[0..ng); K_vv = H, K_rv = A.coef, K_rr = 0 with the
-// Schur complement's diagonal scaled by (1 + eps) once the variables are eliminated, -1 for a decoupled row).
-// V is stored packed, column by column: V(i, j), i >= j, at tri_off(j, nk) + i - j;  rs[j] = 1 / V(j, j).
+// 8x8 diagonal block starting at pivot j0 of the system, in place in shared memory: signed Cholesky  C = V S V'
+// of the tile D (row-major, lower triangle), S = +1 for pivots < nF (variables), -1 for the active rows, then the
+// inverse  W = V^-1  (lower triangular, zeros above the diagonal) into Wt.  When the first active-row pivot lies in
+// this block, the diagonal of the remaining (Schur complement) rows is scaled by 1 + eps at that point
+// (hmpc_qp.cuh: LinSys::factor).  Lane l holds entries (l >> 3, l & 7) and (4 + (l >> 3), l & 7).
+// Returns nonzero when a pivot has the wrong sign or is not finite.  Ends with a __syncwarp().
+// ------------------------------------------------------------------------------------------------
+__device__ inline int wdiag8(double* D, double* Wt, int j0, int nF, double eps, int lane) {
+    const int kk = lane & 7, i0 = lane >> 3, i1 = i0 + 4;
+    int bad = 0;
+    // W starts as the identity and receives the row operations of the elimination (forward substitution on I):
+    // after pivot j, row j of W is final and rows i > j have  W(i, 0..j) -= V(i, j) W(j, 0..j)
+    double w0 = (i0 == kk) ? 1.0 : 0.0, w1 = (i1 == kk) ? 1.0 : 0.0;     // W(i0, kk), W(i1, kk) in registers
+    double c0 = D[8 * i0 + kk], c1 = D[8 * i1 + kk];                      // C(i0, kk), C(i1, kk)
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) {
+        if (j0 + j == nF && j > 0) {            // all variables eliminated: regularise the rows' Schur complement
+            if (i0 == kk && kk >= j) c0 *= 1.0 + eps;
+            if (i1 == kk && kk >= j) c1 *= 1.0 + eps;
+        }
+        const double s = (j0 + j < nF) ? 1.0 : -1.0;
+        // column j of C lives in the lanes with kk == j: lane 8 r + j holds rows r (c0) and r + 4 (c1)
+        const double piv = (j < 4) ? __shfl_sync(kFullMask, c0, 9 * j) : __shfl_sync(kFullMask, c1, 9 * j - 32);
+        const double ap = s * piv;
+        const bool ok = (ap > 0.0) && (ap < 1e30);
+        if (!ok) bad = 1;
+        const double rsq = fast_rsqrt(ok ? ap : 1.0);
+        // V(i, j) for this lane's two rows, V(kk, j) for its column
+        const double cj0 = __shfl_sync(kFullMask, c0, 8 * i0 + j), cj1 = __shfl_sync(kFullMask, c1, 8 * i0 + j);
+        const double ck0 = __shfl_sync(kFullMask, c0, 8 * (kk & 3) + j), ck1 = __shfl_sync(kFullMask, c1, 8 * (kk & 3) + j);
+        const double vi0 = (i0 == j) ? ap * rsq : s * cj0 * rsq, vi1 = (i1 == j) ? ap * rsq : s * cj1 * rsq;
+        const double vk = s * (kk < 4 ? ck0 : ck1) * rsq;
+        // row j of W, scaled: W(j, kk) / V(j, j)
+        const double wj = ((j < 4) ? __shfl_sync(kFullMask, w0, 8 * j + kk) : __shfl_sync(kFullMask, w1, 8 * (j - 4) + kk)) * rsq;
+        if (kk == j) { c0 = vi0; c1 = vi1; }                                   // column j of V
+        else if (kk > j) {                                                     // rank-1 update of the trailing part
+            if (i0 >= kk) c0 = fma(-s * vi0, vk, c0);
+            if (i1 >= kk) c1 = fma(-s * vi1, vk, c1);
+        }
+        if (kk <= j) {
+            w0 = (i0 == j) ? wj : (i0 > j ? fma(-vi0, wj, w0) : w0);
+            w1 = (i1 == j) ? wj : (i1 > j ? fma(-vi1, wj, w1) : w1);
+        }
+    }
+    Wt[8 * i0 + kk] = w0;
+    Wt[8 * i1 + kk] = w1;
+    (void)D;
+    __syncwarp();
+    return bad;
+}
+
+// entry (i, j), i >= j, of the compact KKT system in the ordering [nF variables | ng rows]
+static __device__ __noinline__ double wentry(const QpConst& c, const WWork& w, const AOp& A, int nF, int nk, int i, int j) {
+    const int n = 6 * c.N;
+    if (i < j || i >= nk) return 0.0;
+    if (i < nF) return w.Hc[(int)w.idx[j] * w.ld + (int)w.idx[i]];
+    if (j < nF) return A.coef(n + (int)w.grow[i - nF], (int)w.fr[w.idx[j]]);
+    if (i == j) return wrow_coupled(c, w, (int)w.grow[i - nF]) ? 0.0 : -1.0;
+    return 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Signed Cholesky  K = V S V'  of the compact KKT system of order nk = nF + ng (LinSys in hmpc_qp.cuh describes K:
+// variables idx[0..nF), active general rows grow[0..ng), K_vv = H, K_rv = A.coef, K_rr = 0 with the Schur
+// complement's diagonal scaled by (1 + eps) once the variables are eliminated, -1 for a decoupled row).
+// Left-looking, tile by tile (block column J, row tile I >= J):
+//   C(I,J) = K(I,J) - sum_{K<J} V(I,K) S_K V(J,K)'      tile products on the tensor core
+//   C(J,J) = V(J,J) S_J V(J,J)',  W_J = V(J,J)^-1        wdiag8
+//   V(I,J) = C(I,J) W_J' S_J                             the accumulator fragment is the A operand as it stands
+// The tile that holds pivot nF mixes both signs: its columns are applied in two masked passes, the regularisation of
+// the diagonal in between.  Storage w.L: lower block triangle of row-major 8x8 tiles, the diagonal tiles hold W_J.
 // Returns nonzero (all lanes) when a pivot has the wrong sign or is not finite.
 // ------------------------------------------------------------------------------------------------
-template <int SLOTS>
 __device__ inline int wfactor(const QpConst& c, WWork& w, const AOp& A, int nF, int ng, double eps, int lane) {
-    const int nk = nF + ng, n = 6 * c.N, nf = w.nf;
+    HMPC_EMUL_COUNT(2);
+    const int nk = nF + ng, nt = (nk + 7) >> 3;
+    const int Jb = nF >> 3;                                          // tile of the first active-row pivot
+    const bool mixed = (nF & 7) != 0;                                // ... which also holds variables
+    const int g = lane >> 2, t = lane & 3, fo = 8 * g + 2 * t;      // fragment offset inside a tile
     double* L = w.L;
-    const double* Hc = w.Hc;
+    double* scratch = w.L + tile_off(w.nt_max, 0);                   // one spare tile behind the factor
+    // masks of the mixed tile for the two columns of this lane's B fragment: 1 variable column, 0 row column
+    const double mv0 = (8 * Jb + 2 * t < nF) ? 1.0 : 0.0, mv1 = (8 * Jb + 2 * t + 1 < nF) ? 1.0 : 0.0;
+    const bool ondiag0 = (2 * t == g), ondiag1 = (2 * t + 1 == g);
     int bad = 0;
-    for (int J0 = 0; J0 < nk;) {
-        const int lim = (J0 < nF ? nF : nk) - J0;      // blocks never straddle the variable / row boundary
-        const int bs = lim < 4 ? lim : 4;
-        const int R = nk - J0;
-        // lanes -> (row in block, split of the summation index)
-        const int S = R > 16 ? 1 : (R > 8 ? 2 : (R > 4 ? 4 : 8));
-        const int RP = 32 / S, rl = lane & (RP - 1), q = lane / RP;
-        int irow[SLOTS];
-        bool on[SLOTS];
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s) {
-            const int i = J0 + rl + 32 * s;
-            on[s] = (i < nk) && (s == 0 || S == 1);
-            irow[s] = on[s] ? i : nk - 1;
-        }
-        // K's entries of the block (independent of the sums below: the loads overlap the update loop)
-        double kv[SLOTS][4];
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s) {
-            const int i = irow[s];
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                const int j = J0 + cc;
-                double v = 0.0;
-                if (on[s] && cc < bs && i >= j) {
-                    if (i < nF) v = Hc[(int)w.idx[j] * nf + (int)w.idx[i]];
-                    else if (j < nF) v = A.coef(n + (int)w.grow[i - nF], (int)w.fr[w.idx[j]]);
-                    else if (i == j) v = wrow_coupled(c, w, (int)w.grow[i - nF]) ? 0.0 : -1.0;
-                }
-                kv[s][cc] = v;
-            }
-        }
-        double acc[SLOTS][4];
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s)
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) acc[s][cc] = 0.0;
-        // variable columns: + V(i,k) V(j,k)
-        const int k1 = J0 < nF ? J0 : nF;
-#pragma unroll 2
-        for (int k = q; k < k1; k += S) {
-            const double* col = L + (k * nk - ((k * (k + 1)) >> 1));   // col[i] = V(i, k)
-            const double b0 = col[J0], b1 = col[J0 + 1], b2 = col[J0 + 2], b3 = col[J0 + 3];
-#pragma unroll
-            for (int s = 0; s < SLOTS; ++s) {
-                const double a = col[irow[s]];
-                acc[s][0] = fma(a, b0, acc[s][0]); acc[s][1] = fma(a, b1, acc[s][1]);
-                acc[s][2] = fma(a, b2, acc[s][2]); acc[s][3] = fma(a, b3, acc[s][3]);
-            }
-        }
-        if (J0 >= nF) {
-            // the Schur complement of the variables: relative regularisation of its diagonal
-#pragma unroll
-            for (int s = 0; s < SLOTS; ++s)
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc)
-                    if (irow[s] == J0 + cc) { acc[s][cc] *= (1.0 + eps); kv[s][cc] *= (1.0 + eps); }
-            // active-row columns: - V(i,k) V(j,k)
-            for (int k = nF + q; k < J0; k += S) {
-                const double* col = L + (k * nk - ((k * (k + 1)) >> 1));
-                const double b0 = col[J0], b1 = col[J0 + 1], b2 = col[J0 + 2], b3 = col[J0 + 3];
-#pragma unroll
-                for (int s = 0; s < SLOTS; ++s) {
-                    const double a = col[irow[s]];
-                    acc[s][0] = fma(-a, b0, acc[s][0]); acc[s][1] = fma(-a, b1, acc[s][1]);
-                    acc[s][2] = fma(-a, b2, acc[s][2]); acc[s][3] = fma(-a, b3, acc[s][3]);
+#pragma unroll 1
+    for (int J = 0; J < nt; ++J) {
+        const int j0 = 8 * J + 2 * t;
+        const double s0 = (j0 < nF) ? 1.0 : -1.0, s1 = (j0 + 1 < nF) ? 1.0 : -1.0;
+        const double* Lj = L + tile_off(J, 0) + fo;                  // tiles (J, K), K = 0 .. J
+        const bool scaled = (J > Jb) || (J == Jb && !mixed);        // diagonal regularised here (else inside wdiag8)
+        d2 bw = d2{0.0, 0.0};
+#pragma unroll 1
+        for (int I = J; I < nt; ++I) {
+            const double* Li = L + tile_off(I, 0) + fo;              // tiles (I, K)
+            double a0 = 0.0, a1 = 0.0;
+            const int kplain = J < Jb ? J : Jb;
+#pragma unroll 1
+            for (int K = 0; K < kplain; ++K) tile_mac(a0, a1, ld2(Li + 64 * K), ld2(Lj + 64 * K));   // variables: +
+            if (J > Jb) {
+                if (mixed) {                                         // variable columns of the mixed tile
+                    const d2 b = ld2(Lj + 64 * Jb);
+                    tile_mac(a0, a1, ld2(Li + 64 * Jb), d2{b.x * mv0, b.y * mv1});
                 }
             }
-        }
-        // combine the splits (every lane ends up with the total of its row)
-        for (int o = RP; o < 32; o <<= 1) {
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) acc[0][cc] += __shfl_xor_sync(kFullMask, acc[0][cc], o);
-        }
-        double cv[SLOTS][4];
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s)
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) cv[s][cc] = kv[s][cc] - acc[s][cc];
-        // ---- the block's own columns: pivot by pivot, rows J0 + p live in lane p (slot 0) ----
-        const double sgn = (J0 < nF) ? 1.0 : -1.0;
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            if (p < bs) {
-                const int j = J0 + p;
-                const double piv = __shfl_sync(kFullMask, cv[0][p], p);
-                const double ap = sgn * piv;
-                const bool ok = (ap > 0.0) && (ap < 1e30);
-                if (!ok) bad = 1;
-                const double rsq = fast_rsqrt(ok ? ap : 1.0);
-                double* colj = L + (j * nk - ((j * (j + 1)) >> 1));
-                double vn[SLOTS];
-#pragma unroll
-                for (int s = 0; s < SLOTS; ++s) {
-                    vn[s] = (irow[s] == j) ? ap * rsq : sgn * cv[s][p] * rsq;
-                    if (on[s] && q == 0 && irow[s] >= j) colj[irow[s]] = vn[s];
+            if (scaled && I == J) {                                  // the Schur complement's diagonal
+                if (ondiag0) a0 *= 1.0 + eps;
+                if (ondiag1) a1 *= 1.0 + eps;
+            }
+            if (J > Jb) {
+                if (mixed) {                                         // row columns of the mixed tile: -
+                    const d2 b = ld2(Lj + 64 * Jb);
+                    tile_mac(a0, a1, ld2(Li + 64 * Jb), d2{b.x * (mv0 - 1.0), b.y * (mv1 - 1.0)});
                 }
-                if (lane == 0) w.rs[j] = rsq;
-#pragma unroll
-                for (int p2 = p + 1; p2 < 4; ++p2) {
-                    if (p2 < bs) {
-                        const double u = sgn * __shfl_sync(kFullMask, vn[0], p2);   // S_j V(J0 + p2, j)
-#pragma unroll
-                        for (int s = 0; s < SLOTS; ++s) cv[s][p2] = fma(-vn[s], u, cv[s][p2]);
-                    }
+#pragma unroll 1
+                for (int K = Jb + (mixed ? 1 : 0); K < J; ++K) {     // active-row columns: -
+                    const d2 b = ld2(Lj + 64 * K);
+                    tile_mac(a0, a1, ld2(Li + 64 * K), d2{-b.x, -b.y});
                 }
+            }
+            // C = K - acc
+            const int i = 8 * I + g;
+            double k0 = wentry(c, w, A, nF, nk, i, j0), k1 = wentry(c, w, A, nF, nk, i, j0 + 1);
+            if (I == J) {
+                if (i >= nk) { if (ondiag0) k0 = -1.0; if (ondiag1) k1 = -1.0; }          // past the end: unit pivots
+                else if (scaled && i >= nF) { if (ondiag0) k0 *= 1.0 + eps; if (ondiag1) k1 *= 1.0 + eps; }
+            }
+            const double c0 = k0 - a0, c1 = k1 - a1;
+            if (I == J) {                                            // diagonal tile -> W_J
+                st2(scratch + fo, c0, c1);
+                __syncwarp();
+                bad |= wdiag8(scratch, L + tile_off(J, J), 8 * J, nF, eps, lane);
+                bw = ld2(L + tile_off(J, J) + fo);
+            } else {                                                 // panel: V(I,J) = C(I,J) W_J' S_J
+                double d0 = 0.0, d1 = 0.0;
+                tile_mac(d0, d1, d2{c0, c1}, bw);
+                st2(L + tile_off(I, J) + fo, s0 * d0, s1 * d1);
             }
         }
         __syncwarp();
-        J0 += bs;
     }
     return bad;
 }
 
 // ------------------------------------------------------------------------------------------------
-// Solves K x = b in place on w.rhs (length nk) with K = V S V': forward V z = b, w = S z, backward V' x = w.
-// Each lane keeps the entries of its rows (lane, lane + 32, ...) in registers; the pivot entry travels by shuffle.
-// Ends with a __syncwarp().
+// Solves K x = b in place on w.rhs (length nk, padded with zeros to 8 nt) with K = V S V':
+//   forward   z_I = W_I (b_I - sum_{J<I} V(I,J) z_J)        backward   x_J = W_J' (S z_J - sum_{I>J} V(I,J)' x_I)
+// Tile-times-vector products on the tensor core; the vector pieces travel through w.rhs.  Ends with a __syncwarp().
 // ------------------------------------------------------------------------------------------------
-template <int SLOTS>
 __device__ inline void wsolve(WWork& w, int nF, int ng, int lane) {
-    const int nk = nF + ng;
+    HMPC_EMUL_COUNT(3);
+    const int nk = nF + ng, nt = (nk + 7) >> 3;
+    const int g = lane >> 2, t = lane & 3, fo = 8 * g + 2 * t;
     const double* L = w.L;
-    double bv[SLOTS], rsv[SLOTS];
-    int rowoff[SLOTS];
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-        const int i = lane + 32 * s;
-        bv[s] = i < nk ? w.rhs[i] : 0.0;
-        rsv[s] = i < nk ? w.rs[i] : 0.0;
-        rowoff[s] = i < nk ? (i * nk - ((i * (i + 1)) >> 1)) : 0;     // V(j, i) = L[rowoff + j], j >= i
-    }
-    // forward
-#pragma unroll
-    for (int sj = 0; sj < SLOTS; ++sj) {
-        const int jend = nk - 32 * sj < 32 ? nk - 32 * sj : 32;
-#pragma unroll 2
-        for (int jl = 0; jl < jend; ++jl) {
-            const int j = 32 * sj + jl;
-            const double t = __shfl_sync(kFullMask, bv[sj], jl) * w.rs[j];
-            const double* col = L + (j * nk - ((j * (j + 1)) >> 1));
-#pragma unroll
-            for (int s = 0; s < SLOTS; ++s) {
-                const int i = lane + 32 * s;
-                if (s >= sj && i > j && i < nk) bv[s] = fma(-col[i], t, bv[s]);
-            }
-        }
-    }
-    // z = b / v_jj, w = S z
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-        const int i = lane + 32 * s;
-        bv[s] *= (i < nF) ? rsv[s] : -rsv[s];
-    }
-    // backward
-#pragma unroll
-    for (int sj = SLOTS - 1; sj >= 0; --sj) {
-        const int jend = nk - 32 * sj < 32 ? nk - 32 * sj : 32;
-#pragma unroll 2
-        for (int jl = jend - 1; jl >= 0; --jl) {
-            const int j = 32 * sj + jl;
-            const double xj = __shfl_sync(kFullMask, bv[sj], jl) * w.rs[j];
-#pragma unroll
-            for (int s = 0; s < SLOTS; ++s) {
-                const int i = lane + 32 * s;
-                if (s <= sj && i < j) bv[s] = fma(-L[rowoff[s] + j], xj, bv[s]);
-            }
-        }
-    }
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-        const int i = lane + 32 * s;
-        if (i < nk) w.rhs[i] = bv[s] * rsv[s];
-    }
+    double* v = w.rhs;
+    if (lane < 8 * nt - nk) v[nk + lane] = 0.0;
     __syncwarp();
+#pragma unroll 1
+    for (int I = 0; I < nt; ++I) {
+        const double* Li = L + tile_off(I, 0) + fo;
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll 1
+        for (int J = 0; J < I; ++J) tile_mac(a0, a1, ld2(Li + 64 * J), vec_b(v + 8 * J, lane));
+        const double r = v[8 * I + g] - a0;
+        __syncwarp();
+        if (t == 0) v[8 * I + g] = r;
+        __syncwarp();
+        double z0 = 0.0, z1 = 0.0;
+        tile_mac(z0, z1, ld2(Li + 64 * I), vec_b(v + 8 * I, lane));
+        __syncwarp();
+        if (t == 0) v[8 * I + g] = z0;
+        __syncwarp();
+    }
+#pragma unroll 1
+    for (int J = nt - 1; J >= 0; --J) {
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll 1
+        for (int I = nt - 1; I > J; --I) {
+            const double* T = L + tile_off(I, J);                     // A = V(I,J)': A[g][2t + h] = T[2t + h][g]
+            tile_mac(a0, a1, d2{T[8 * (2 * t) + g], T[8 * (2 * t + 1) + g]}, vec_b(v + 8 * I, lane));
+        }
+        const int i = 8 * J + g;
+        const double zi = v[i];
+        const double r = (i < nF ? zi : -zi) - a0;
+        __syncwarp();
+        if (t == 0) v[i] = r;
+        __syncwarp();
+        const double* Wt = L + tile_off(J, J);
+        double x0 = 0.0, x1 = 0.0;
+        tile_mac(x0, x1, d2{Wt[8 * (2 * t) + g], Wt[8 * (2 * t + 1) + g]}, vec_b(v + i - g, lane));
+        __syncwarp();
+        if (t == 0) v[i] = x0;
+        __syncwarp();
+    }
 }
 
 struct WInfo { int nfac; double flops; };
@@ -656,7 +743,8 @@ __device__ inline void wpolish_init(const QpConst& c, WWork& w, int lane) {
     }
     __syncwarp();
 }
-// One trial: 1 = verified optimum (w.xp, w.mul, w.code), 0 = active set updated, try again, -1 = give up.
+// One trial: 1 = verified optimum (w.xp, w.mul, w.code), 0 = active set updated, try again, -1 = give up,
+// -2 = the system does not fit this kernel's factor storage.
 template <int SLOTS>
 __device__ inline int wtrial(const QpConst& c, WWork& w, const AOp& A, int kcap, WInfo& info, int lane) {
     const int N = c.N, n = 6 * N, m = 11 * N;
@@ -678,14 +766,14 @@ __device__ inline int wtrial(const QpConst& c, WWork& w, const AOp& A, int kcap,
         const int ng = wcompact(n, m - n, kcap, w.grow, n, lane, [&](int r) { return w.code[r] != 0; });
         __syncwarp();
         const int nk = nF + ng;
-        if (nk > kcap || nk > 32 * SLOTS) return -1;
+        if (nk > kcap) { HMPC_EMUL_COUNT(6); return -2; }     // too large for this kernel, not a failed attempt
         ++info.nfac;
         info.flops += flops_factor(nk);
-        if (wfactor<SLOTS>(c, w, A, nF, ng, c.kkt_eps, lane)) return -1;
+        if (wfactor(c, w, A, nF, ng, c.kkt_eps, lane)) return -1;
         double prev = 1e300;
         bool hx_current = false;
         for (int k = 0; k < c.max_refine; ++k) {
-            wmatvec<SLOTS>(w, lane);
+            wmatvec(w, lane);
             info.flops += flops_matvec(n);
             double v0 = 0.0, v1 = 0.0;   // residual; largest residual relative to the terms it is the difference of
             for (int i = lane; i < nk; i += 32) {
@@ -712,7 +800,7 @@ __device__ inline int wtrial(const QpConst& c, WWork& w, const AOp& A, int kcap,
             if (k == 1 && ng == 0 && v0 <= 1e-7 * prev) { hx_current = true; break; }
             if (k >= 1 && (v1 <= 1e-12 || (k >= 2 && v0 > c.stagnation * prev))) { hx_current = true; break; }
             prev = v0;
-            wsolve<SLOTS>(w, nF, ng, lane);
+            wsolve(w, nF, ng, lane);
             info.flops += flops_solve(nk);
             for (int i = lane; i < nk; i += 32) {
                 if (i < nF) w.xp[w.fr[w.idx[i]]] += w.rhs[i];
@@ -721,7 +809,7 @@ __device__ inline int wtrial(const QpConst& c, WWork& w, const AOp& A, int kcap,
             __syncwarp();
         }
         // ---- pass 1: multipliers of pinned variables, scales ----
-        if (!hx_current) { wmatvec<SLOTS>(w, lane); info.flops += flops_matvec(n); }
+        if (!hx_current) { wmatvec(w, lane); info.flops += flops_matvec(n); }
         double s_stat = 0.0, s_scale = 0.0, s_mult = 0.0;
         for (int i = lane; i < n; i += 32) {
             if (w.fixed[i]) continue;                     // eliminated a priori: no Hessian row, multiplier unused
@@ -774,6 +862,7 @@ __device__ inline int wtrial(const QpConst& c, WWork& w, const AOp& A, int kcap,
         }
         changed = __any_sync(kFullMask, changed);
         __syncwarp();
+        if (!changed) HMPC_EMUL_COUNT(7);
         return changed ? 0 : -1;
     }
 }
@@ -796,8 +885,8 @@ __device__ inline int wpolish(const QpConst& c, WWork& w, const AOp& A, int kcap
 __device__ inline int wbegin(const QpConst& c, WWork& w, int b, int B, const MpcIo& io, int lane) {
     const int N = c.N, n = 6 * N, m = 11 * N;
     const size_t Bs = (size_t)B;
-    if (!io.valid[b]) return 0;
-    if (wcondense(c, w, b, B, io, lane)) return 0;
+    if (!io.valid[b]) { HMPC_EMUL_COUNT(4); return 0; }
+    if (wcondense(c, w, b, B, io, lane)) { HMPC_EMUL_COUNT(5); return 0; }
     // warm start: stage k starts from the previous tick's stage k+1, the last two stages keep their own previous
     // pattern (mpc_hopper in hmpc_mpc.cuh)
     for (int i = lane; i < n; i += 32) {
@@ -823,6 +912,8 @@ __device__ inline void wfinish(const QpConst& c, WWork& w, int b, int B, const M
     double* xs = w.err;
     const double* u = w.xp;
     const double dt = c.dt, gdt = -c.g * dt;
+    wlinearize_all(c, w, b, B, io, lane);       // the factor overwrote cz / sz / Bw
+    __syncwarp();
     if (lane < 12) xs[lane] = w.xin[lane];
     if (lane < 6) {          // velocities
         const int q = lane;
@@ -889,6 +980,10 @@ __device__ inline void wfinish(const QpConst& c, WWork& w, int b, int B, const M
         }
     }
 }
+// Returns 1: done;  0: not attempted (no valid previous tick / infeasible height row / system larger than kcap): the
+// CTA kernel runs its whole solver;  -1: the active-set refinement itself gave up: the CTA kernel goes straight to
+// its interior point (same QP, same verified polish afterwards).
+constexpr int kDeferWarmFailed = 1 << 30;     // flag bit in a deferral-list entry
 template <int SLOTS>
 __device__ inline int mpc_hopper_warp(const QpConst& c, WWork& w, int kcap, int b, int B, const MpcIo& io, int lane) {
     if (!wbegin(c, w, b, B, io, lane)) return 0;
@@ -896,10 +991,11 @@ __device__ inline int mpc_hopper_warp(const QpConst& c, WWork& w, int kcap, int 
     WInfo info{0, c.condense_flops};
     for (int trial = 0; trial <= c.retries; ++trial) {
         const int r = wtrial<SLOTS>(c, w, A, kcap, info, lane);
-        if (r < 0) return 0;
+        if (r == -2) return 0;
+        if (r < 0) return -1;
         if (r > 0) { wfinish(c, w, b, B, io, info, lane); return 1; }
     }
-    return 0;
+    return -1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -909,10 +1005,9 @@ constexpr int kWarpMaxN = 10;     // horizons the warp kernel is instantiated fo
 // cap on the order of the compact KKT system (unpinned variables + active friction / height rows): it sizes the
 // factor in shared memory; a trial that needs more goes to the CTA kernel
 inline int warp_kcap(const hmpc_config& cfg) {
-    int k = 7 * cfg.N + 2;
-    const int lim = cfg.N <= 10 ? 56 : 104;
-    if (k > lim) k = lim;
-    if (const char* e = getenv("HMPC_WARP_KCAP")) { const int v = atoi(e); if (v >= 8 && v <= 128) k = v; }
+    int k = kWarpKcap;                 // 7 tiles of 8 (variables padded to a multiple of 8, then the active rows)
+    if (const char* e = getenv("HMPC_WARP_KCAP")) { const int v = atoi(e); if (v >= 8 && v <= kWarpKcap) k = v; }
+    (void)cfg;
     return k;
 }
 inline bool warp_path_applies(const hmpc_config& cfg, int init) {
@@ -941,7 +1036,7 @@ mpc_warp_kernel(QpConst c, int B, int kcap, int wdoubles, double* __restrict__ h
         if (b >= B) break;
         const int done = mpc_hopper_warp<SLOTS>(c, w, kcap, b, B, io, lane);
         __syncwarp();
-        if (!done && lane == 0) defer_list[atomicAdd(defer_cnt, 1)] = b;
+        if (done <= 0 && lane == 0) defer_list[atomicAdd(defer_cnt, 1)] = b | (done < 0 ? kDeferWarmFailed : 0);
     }
 }
 
@@ -974,7 +1069,7 @@ mpc_warp_rounds_kernel(QpConst c, int B, int kcap, int wdoubles, double* __restr
             const int r = wtrial<SLOTS>(c, w, A, kcap, info, lane);
             if (r > 0) { wfinish(c, w, b, B, io, info, lane); have = false; }
             else if (r < 0 || ++trial > c.retries) {
-                if (lane == 0) defer_list[atomicAdd(defer_cnt, 1)] = b;
+                if (lane == 0) defer_list[atomicAdd(defer_cnt, 1)] = b | (r == -2 ? 0 : kDeferWarmFailed);
                 have = false;
             }
             __syncwarp();

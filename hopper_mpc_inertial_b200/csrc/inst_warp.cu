@@ -9,22 +9,28 @@ namespace hmpc {
 #define HMPC_WARP_DISPATCH(rounds, wpc, CALL)                      \
     if (rounds) {                                                  \
         switch (wpc) {                                             \
-            case 2: CALL(mpc_warp_rounds_kernel, 2, 8); break;     \
-            case 4: CALL(mpc_warp_rounds_kernel, 4, 4); break;     \
-            case 5: CALL(mpc_warp_rounds_kernel, 5, 3); break;     \
-            case 8: CALL(mpc_warp_rounds_kernel, 8, 2); break;     \
-            default: CALL(mpc_warp_rounds_kernel, 10, 1); break;   \
+            case 4: CALL(mpc_warp_rounds_kernel, 4, 3); break;     \
+            case 5: CALL(mpc_warp_rounds_kernel, 5, 2); break;     \
+            case 6: CALL(mpc_warp_rounds_kernel, 6, 2); break;     \
+            case 7: CALL(mpc_warp_rounds_kernel, 7, 2); break;     \
+            case 8: CALL(mpc_warp_rounds_kernel, 8, 1); break;     \
+            case 10: CALL(mpc_warp_rounds_kernel, 10, 1); break;   \
+            case 11: CALL(mpc_warp_rounds_kernel, 11, 1); break;   \
+            case 12: CALL(mpc_warp_rounds_kernel, 12, 1); break;   \
+            case 13: CALL(mpc_warp_rounds_kernel, 13, 1); break;   \
+            case 14: CALL(mpc_warp_rounds_kernel, 14, 1); break;   \
+            default: CALL(mpc_warp_rounds_kernel, 15, 1); break;   \
         }                                                          \
     } else {                                                       \
         switch (wpc) {                                             \
-            case 1: CALL(mpc_warp_kernel, 1, 16); break;           \
-            case 2: CALL(mpc_warp_kernel, 2, 8); break;            \
-            default: CALL(mpc_warp_kernel, 4, 4); break;           \
+            case 1: CALL(mpc_warp_kernel, 1, 12); break;           \
+            case 2: CALL(mpc_warp_kernel, 2, 6); break;            \
+            default: CALL(mpc_warp_kernel, 4, 3); break;           \
         }                                                          \
     }
 
 bool warp_wpc_supported(int rounds, int wpc) {
-    return rounds ? (wpc == 2 || wpc == 4 || wpc == 5 || wpc == 8 || wpc == 10) : (wpc == 1 || wpc == 2 || wpc == 4);
+    return rounds ? ((wpc >= 4 && wpc <= 8) || (wpc >= 10 && wpc <= 15)) : (wpc == 1 || wpc == 2 || wpc == 4);
 }
 
 cudaError_t warp_set_smem(int rounds, int wpc, int bytes) {

@@ -20,8 +20,9 @@ using namespace hmpc;
 
 // ---- 32-lane warp emulation: cooperative fibers that meet at every warp-synchronous primitive ----
 int hmpc_emul_tid = 0, hmpc_emul_bdim = 1;
-double hmpc_emul_xd[32];
+double hmpc_emul_xd[32], hmpc_emul_ma[32], hmpc_emul_mb[32];
 long long hmpc_emul_xi[32];
+long long hmpc_emul_count[8];
 
 namespace {
 constexpr int NL = 32;
@@ -139,37 +140,41 @@ int emul_solve(const hmpc_config* cfg, const double* Qd, const double* Rd, const
     io.ninf = ninf.data(); io.flops = nullptr; io.init = init; io.accumulate = 0; io.respawn = 0;
     // the library's dispatch (hmpc_api.cu: launch_mpc): warm ticks go through the warp-per-hopper kernel first,
     // hoppers it defers (and everything else) through the CTA kernel
-    std::vector<char> deferred(B, 1);
+    std::vector<char> deferred(B, 1), skipw(B, 0);
     g_emul_warp_done = 0;
     if (warp_path_applies(*cfg, init)) {
         const int kcap = warp_kcap(*cfg);
-        std::vector<double> wsm(warp_work_doubles(N, kcap) + 8), hc((size_t)n * n + 8);
+        std::vector<double> wsm(warp_work_doubles(N, kcap) + 8), hc((size_t)(n + 8) * (n + 8) + 8);
         for (int b = 0; b < B; ++b) {
             int done = 0;
             run_warp([&](int lane) {
                 WWork ww;
                 wcarve(ww, wsm.data(), N, kcap);
                 ww.Hc = hc.data();
-                const int d = (N <= 10) ? mpc_hopper_warp<2>(c, ww, kcap, b, B, io, lane)
-                                        : mpc_hopper_warp<4>(c, ww, kcap, b, B, io, lane);
+                const int d = mpc_hopper_warp<2>(c, ww, kcap, b, B, io, lane);
                 if (lane == 0) done = d;
             });
-            deferred[b] = done ? 0 : 1;
-            g_emul_warp_done += done;
+            deferred[b] = done > 0 ? 0 : 1;
+            skipw[b] = done < 0 ? 1 : 0;
+            g_emul_warp_done += done > 0;
         }
     }
     if (cfg->precision == HMPC_FP32) {
         LinSys<float> sys{n, 0, 0, reinterpret_cast<float*>(w.Lm), reinterpret_cast<float*>(w.dinv), w.H, w.idx, w.grow};
-        for (int b = 0; b < B; ++b) if (deferred[b]) mpc_hopper<true>(c, w, sys, A, b, B, io);
+        for (int b = 0; b < B; ++b) if (deferred[b]) mpc_hopper<true>(c, w, sys, A, b, B, io, skipw[b]);
     } else {
         LinSys<double> sys{n, 0, 0, reinterpret_cast<double*>(w.Lm), reinterpret_cast<double*>(w.dinv), w.H, w.idx, w.grow};
-        for (int b = 0; b < B; ++b) if (deferred[b]) mpc_hopper<true>(c, w, sys, A, b, B, io);
+        for (int b = 0; b < B; ++b) if (deferred[b]) mpc_hopper<true>(c, w, sys, A, b, B, io, skipw[b]);
     }
     return 0;
 }
 
 // hoppers the warp path finished in the most recent emul_solve
 int emul_warp_done(void) { return g_emul_warp_done; }
+// event counters of the warp emulation since the last reset ([0] = DMMA lane-calls)
+void emul_counters(long long* out, int reset) {
+    for (int i = 0; i < 8; ++i) { out[i] = hmpc_emul_count[i]; if (reset) hmpc_emul_count[i] = 0; }
+}
 
 // condense only: H [n][n][B], g [n][B], lo/hi [m][B], infeasible [B]
 int emul_condense(const hmpc_config* cfg, const double* Qd, const double* Rd, const double* x_in,

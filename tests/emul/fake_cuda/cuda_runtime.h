@@ -44,6 +44,32 @@ static inline double __shfl_sync(unsigned, double v, int src) {
     hmpc_emul_rendezvous();
     return r;
 }
+static inline double __shfl_sync(unsigned, double v, int src, int width) {
+    if (hmpc_emul_bdim == 1) return v;
+    hmpc_emul_xd[hmpc_emul_tid] = v;
+    hmpc_emul_rendezvous();
+    const double r = hmpc_emul_xd[(hmpc_emul_tid & ~(width - 1)) | (src & (width - 1))];
+    hmpc_emul_rendezvous();
+    return r;
+}
+// mma.sync.aligned.m8n8k4.row.col.f64: lane = 4 g + t holds A[g][t], B[t][g], C/D[g][2t], [g][2t+1]
+extern double hmpc_emul_ma[32], hmpc_emul_mb[32];
+extern long long hmpc_emul_count[8];               // [0] DMMA lane-calls, [1..] user counters (HMPC_EMUL_COUNT)
+#define HMPC_EMUL_COUNT(k) (++hmpc_emul_count[k])
+static inline void hmpc_emul_dmma(double* c0, double* c1, double a, double b) {
+    ++hmpc_emul_count[0];
+    hmpc_emul_ma[hmpc_emul_tid] = a;
+    hmpc_emul_mb[hmpc_emul_tid] = b;
+    hmpc_emul_rendezvous();
+    const int g = hmpc_emul_tid >> 2, t = hmpc_emul_tid & 3;
+    double d0 = *c0, d1 = *c1;
+    for (int k = 0; k < 4; ++k) {
+        d0 = fma(hmpc_emul_ma[4 * g + k], hmpc_emul_mb[4 * (2 * t) + k], d0);
+        d1 = fma(hmpc_emul_ma[4 * g + k], hmpc_emul_mb[4 * (2 * t + 1) + k], d1);
+    }
+    hmpc_emul_rendezvous();
+    *c0 = d0; *c1 = d1;
+}
 static inline int __shfl_sync(unsigned, int v, int src) {
     if (hmpc_emul_bdim == 1) return v;
     hmpc_emul_xi[hmpc_emul_tid] = v;

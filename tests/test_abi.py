@@ -40,7 +40,7 @@ def test_config_struct_mirror_matches_c_defaults():
             assert a == pytest.approx(b, rel=1e-12), name
     # the trailing field is where a layout mismatch would show up
     assert cfg.ipm_tol == 1e-6 and cfg.polish_tol == 1e-9 and cfg.kkt_eps == 1e-9
-    assert C.sizeof(_lib.HmpcConfig) == 20 * 4 + (5 + 9 + 9 + 3 + 3 + 3 + 5 + 3) * 8
+    assert C.sizeof(_lib.HmpcConfig) == 22 * 4 + (5 + 9 + 9 + 3 + 3 + 3 + 5 + 3) * 8     # 21 int32 + padding
 
 
 def test_bad_arguments_are_rejected_without_a_device_call():
