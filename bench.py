@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--hot-path", choices=["auto", "cta"], default="auto",
                     help="auto: warp-per-hopper kernel + CTA fallback (default); cta: round-1 CTA-per-hopper kernel only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the 4096-hopper and hard-workload records")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="wall-clock budget of the CPU baseline sample")
     return ap.parse_args()
 
@@ -94,12 +95,33 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the reference's algorithm (oracle port) on the host cores, one process per core
+# CPU arm: the reference's per-tick recipe on the host cores, one process per core.
+#   port-c++ : oracle/c/hopper_ref.cpp (g++ -O3): fresh cvxpy-shaped full QP every tick, restated OSQP (sparse banded
+#              LDL', Ruiz scaling, eps 1e-5, adaptive rho, polish, cold start), 20 RK4 steps -- the compiled baseline
+#   port     : the same recipe in numpy (oracle/closed_loop.py solver='osqp'), kept as a second figure
+# Neither is the cvxpy/OSQP binary (not installable here: no network); both restate its published algorithm.
 # ------------------------------------------------------------------------------------------------
-def _cpu_worker(args):
-    """One hopper's closed loop with the reference's own per-tick recipe: a fresh cvxpy-shaped QP every tick,
-    OSQP cold start at cvxpy's settings (eps 1e-5, polish) -- oracle/closed_loop.py solver='osqp' -- plus
-    20 numpy RK4 steps.  Returns (ticks done, seconds)."""
+def _cpu_worker_cpp(args):
+    """Closed loops of hoppers idx, idx + stride, ... with the compiled restatement until the budget is used.
+    Returns (ticks done, seconds, per-tick mpcontrol micro-seconds, OSQP iterations per tick, hoppers started, failed)."""
+    idx, stride, dyn, N, seconds, max_ticks = args
+    from hopper_mpc_inertial_b200 import scenarios
+    from oracle import cref
+    t0 = time.perf_counter()
+    done, us, its, started, failed, inacc = 0, [], [], 0, 0, 0
+    while time.perf_counter() - t0 < seconds:
+        sc = scenarios.make_batch(1, idx0=idx, N=N, n_ticks=max_ticks, dyn=dyn)
+        left = seconds - (time.perf_counter() - t0)
+        r = cref.closed_loop(int(dyn[0]), N, sc["Qdiag"][:, 0], sc["Rdiag"][:, 0], sc["X0"][:, 0], sc["xref_tab"][:, :, 0],
+                             sc["pf_tab"][:, :, 0], sc["C"][:, 0], sc["pf_switch"][:, 0], max_ticks, budget_s=max(left, 0.05))
+        done += r["ticks"]; us += list(r["solve_us"]); its += list(r["iters"]); started += 1; failed += int(r["failed"])
+        inacc += r["inaccurate"]
+        idx += stride
+    return done, time.perf_counter() - t0, us, its, started, failed, inacc
+
+
+def _cpu_worker_py(args):
+    """The same recipe in numpy (oracle/closed_loop.py solver='osqp').  Returns (ticks done, seconds)."""
     idx, dyn, N, seconds, max_ticks = args
     os.environ["OMP_NUM_THREADS"] = "1"
     from hopper_mpc_inertial_b200 import scenarios
@@ -126,22 +148,35 @@ def _cpu_worker(args):
     return done, time.perf_counter() - t0
 
 
-def cpu_reference_sample(dyn, N, seconds, cores=None):
+def cpu_reference_sample(dyn, N, seconds, cores=None, python_seconds=None):
     import multiprocessing as mp
+    from oracle import cref
+    cref.build()                                      # before the pool: one build, not one per process
     cores = cores or os.cpu_count() or 1
     ctx = mp.get_context("spawn")
     t0 = time.perf_counter()
     with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(i, dyn, N, seconds, 400) for i in range(cores)])
+        res = pool.map(_cpu_worker_cpp, [(i, cores, dyn, N, seconds, 200) for i in range(cores)])
+        py = pool.map(_cpu_worker_py, [(i, dyn, N, python_seconds, 400) for i in range(cores)]) if python_seconds else None
     wall = time.perf_counter() - t0
     ticks = sum(r[0] for r in res)
-    # per-core rates add up: every process ran for its own measured time
-    value = sum(r[0] / r[1] for r in res if r[1] > 0)
-    return {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "wall_s": wall,
-            "sample": (f"{cores} hoppers (one process per core), {ticks} closed-loop ticks in total, "
-                       f"{seconds:.0f} s budget each ({wall:.1f} s wall incl. process start); numpy restatement of the "
-                       f"reference's per-tick recipe: cvxpy-shaped full QP rebuilt every tick, OSQP algorithm cold "
-                       f"start, eps_abs=eps_rel=1e-5, polish, + 20 numpy RK4 steps; horizon {N}, {dyn}")}
+    value = sum(r[0] / r[1] for r in res if r[1] > 0)    # per-core rates add up: every process timed itself
+    us = np.array([u for r in res for u in r[2]]) if ticks else np.zeros(1)
+    its = np.array([i for r in res for i in r[3]]) if ticks else np.zeros(1)
+    out = {"value": value, "unit": UNIT, "cores": cores, "kind": "port-c++", "wall_s": wall, "same_config": False,
+           "p50_qp_solve_us": float(np.median(us)), "p99_qp_solve_us": float(np.percentile(us, 99)),
+           "mean_osqp_iters_per_tick": float(its.mean()),
+           "hoppers_started": int(sum(r[4] for r in res)), "hoppers_failed": int(sum(r[5] for r in res)),
+           "solves_at_max_iter": int(sum(r[6] for r in res)),
+           "sample": (f"{cores} processes (one per core), {ticks} closed-loop ticks in {seconds:.0f} s each; compiled C++ "
+                      f"restatement (g++ -O3 -march=x86-64-v3) of the reference's per-tick recipe: cvxpy-shaped full QP rebuilt "
+                      f"every tick, OSQP algorithm (banded LDL', Ruiz scaling, eps_abs=eps_rel=1e-5, adaptive rho, polish), "
+                      f"cold start, + 20 RK4 steps; horizon {N}, {dyn}; same scenario generator as the GPU batch but only "
+                      f"these hoppers (same_config=false).  NOT the cvxpy/OSQP binary (not installable: no network)")}
+    if py:
+        out["python_port"] = {"value": sum(r[0] / r[1] for r in py if r[1] > 0), "unit": UNIT, "kind": "port",
+                              "sample": f"numpy restatement of the same recipe, {python_seconds:.0f} s per process"}
+    return out
 
 
 def run_reference_arm(args):
@@ -152,16 +187,18 @@ def run_reference_arm(args):
     cores = os.cpu_count() or 1
     per = []
     for s in range(args.warmup + args.steps):
-        budget = max(2.0, min(args.cpu_seconds, 120.0 / max(1, args.warmup + args.steps)))
+        budget = max(1.5, min(args.cpu_seconds, 100.0 / max(1, args.warmup + args.steps)))
         r = cpu_reference_sample(args.dyn, args.horizon, budget, cores)
         if s >= args.warmup:
             per.append(r)
     value = float(np.mean([r["value"] for r in per]))
+    last = per[-1]
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": float(np.mean([r["wall_s"] for r in per])) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args, world), "note": "CPU arm: each step is a bounded sample of the same workload"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": per[-1]["sample"]},
+            "cpu_baseline": {k: last[k] for k in ("unit", "cores", "kind", "sample", "same_config", "p50_qp_solve_us",
+                                                   "mean_osqp_iters_per_tick")} | {"value": value},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     _emit(line)
@@ -170,6 +207,41 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # product arm
 # ------------------------------------------------------------------------------------------------
+def quick_run(args, dev, local, B, W, K, tag, **scenario_kw):
+    """A secondary configuration measured in the same process: W warm-up ticks (first = init), K timed ticks with the
+    tables resident in HBM.  Returns a small record (steps/s, ms per tick, solver statistics)."""
+    import torch
+    from hopper_mpc_inertial_b200 import scenarios
+    from hopper_mpc_inertial_b200.batch import BatchMpc
+    N = args.horizon
+    sc = scenarios.make_batch(B, N=N, n_ticks=W + K + 1, dyn=args.dyn, **scenario_kw)
+    bm = BatchMpc(B, dyn=args.dyn, N=N, device=local, solver=args.solver, precision=args.precision,
+                  on_infeasible="respawn", sqp_sweeps=args.sqp_sweeps, hot_path=args.hot_path)
+    T = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
+    bm.set_gains(T(sc["Qdiag"]), T(sc["Rdiag"]))
+    xr, pf, Cd, sw = T(sc["xref_tab"]), T(sc["pf_tab"]), T(np.ascontiguousarray(sc["C_tab"]).view(np.int64)), T(sc["pf_switch"])
+    X = T(sc["X0"]).clone()
+    bm.rollout(X, xr, pf, Cd, sw, 0, W, True)
+    torch.cuda.synchronize()
+    bm.set_timing(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = bm.rollout(X, xr, pf, Cd, sw, W, K, False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    mpc_t, _ = bm.tick_times()
+    st = out["status"].cpu().numpy()
+    nf, pa, ni = [a.cpu().numpy() for a in bm.solve_stats()]
+    hot = bm.hot_path_info()
+    rec = {"workload": tag, "batch": B, "steps": K, "warmup": W, "value": B * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K,
+           "p50_qp_solve_us_amortised": float(np.median(mpc_t)) * 1e3 / B, "p50_qp_batch_latency_us": float(np.median(mpc_t)) * 1e3,
+           "solved_exact_frac": float(np.mean(st == 0)), "infeasible_ticks": int(ni.sum()),
+           "factorisations_per_tick": float(nf.mean() / K), "deferred_frac": hot["deferred"] / float(B * K)}
+    bm.close()
+    return rec
+
+
 def run_b200(args):
     import torch
     from hopper_mpc_inertial_b200 import scenarios, sharding
@@ -221,6 +293,7 @@ def run_b200(args):
     launches = bm.launch_count() - l0
     ms = e0.elapsed_time(e1)
     mpc_ms, sim_ms, nt = bm.kernel_times()
+    mpc_tick, sim_tick = bm.tick_times()
     bm.set_timing(False)
     st = out["status"].cpu().numpy()
     it = out["iters"].cpu().numpy()
@@ -351,18 +424,31 @@ def run_b200(args):
         prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "mpc_kernel", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": ach_gbs / hbm_peak,
+    # The solver kernels' arithmetic runs on the FP64 pipe (DMMA.8x8x4 tensor-core tiles + DFMA): that is the roofline
+    # the kernel is measured against.  It is far from it: the binding resource is instruction issue / fetch (ncu, see
+    # profiles/README.md: issue slots ~25 % busy, top stalls no_instruction / long_scoreboard / wait), not FP64 and not HBM.
+    kname = "mpc_warp_rounds_kernel + mpc_kernel (deferred hoppers)" if hot["warps_per_sm"] else "mpc_kernel"
+    roofline = {"bound": "tensor", "pipe": "FP64 (DMMA.8x8x4 tensor-core tiles and DFMA share the FP64 pipe)", "kernel": kname,
+                "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak if fp64_peak else None,
                 "traffic": (prof["mpc_kernel_dram_bytes_per_hopper"] * B) if "mpc_kernel_dram_bytes_per_hopper" in prof else None,
                 "traffic_source": ("ncu dram__bytes_read+write per hopper at batch %d (profiles/%s) x this batch" % (prof.get("capture_batch", 0), prof.get("source", "?"))) if prof else None,
-                "peak_source": hbm_src, "algorithmic_bytes_per_launch": bytes_tick * B,
+                "peak_source": "measured in this run: dependent-chain-free FP64 FMA microbenchmark (hmpc_measure_fp64_peak); "
+                               "tools/micro/dmma.cu measures the same 37 TFLOP/s through DMMA",
+                "algorithmic_flops_per_launch": flops / max(nt, 1), "algorithmic_flops_per_hopper_tick": flops / max(nt, 1) / B,
                 "avg_launch_ms": mpc_s * 1e3, "share_of_step": mpc_ms / ms,
-                "note": "not HBM-bound (arithmetic intensity >> machine balance); the binding resource is FP64 "
-                        "issue latency / shared memory, see roofline_fp64 and DESIGN.md"}
-    roofline_fp64 = {"bound": "fp64_fma", "kernel": "mpc_kernel", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                     "frac": ach_tf / fp64_peak if fp64_peak else None,
-                     "peak_source": "measured here: dependent-chain-free DFMA microbenchmark (hmpc_measure_fp64_peak)",
-                     "algorithmic_flops_per_hopper_tick": flops / max(nt, 1) / B}
+                "binding_resource": "instruction issue / fetch, not FP64 and not HBM: see profiles/README.md (ncu issue-slot "
+                                    "utilisation and stall breakdown of the same command)"}
+    roofline_hbm = {"bound": "hbm", "kernel": kname, "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                    "peak_source": hbm_src, "algorithmic_bytes_per_launch": bytes_tick * B,
+                    "note": "reported for completeness: arithmetic intensity >> machine balance, HBM does not bind"}
+    working_set_mb = B * (bytes_tick + 13 * 16 + 15 * 8 * 2) / 1e6
+    cache_note = ("inputs larger than L2 (per-tick working set %.0f MB per GPU > 126 MB L2)" % working_set_mb) if working_set_mb > 126 \
+        else ("per-tick working set %.0f MB per GPU fits the 126 MB L2; every tick reads new reference rows and rewrites the "
+              "whole per-hopper state, no flush between ticks" % working_set_mb)
+    p50 = {"amortised_us_per_solve": float(np.median(mpc_tick)) * 1e3 / B, "batch_latency_us": float(np.median(mpc_tick)) * 1e3,
+           "p99_batch_latency_us": float(np.percentile(mpc_tick, 99)) * 1e3,
+           "definition": "median over the timed ticks of the solver kernels' device time (time shift + linearise + condense + QP "
+                         "solve for the whole batch of one tick, CUDA events); amortised = that / hoppers per GPU"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -370,22 +456,28 @@ def run_b200(args):
             "data": "synthetic",
             "config": {"workload": workload_name(args, world), "precision": args.precision, "dyn": args.dyn, "horizon": N, "batch_per_gpu": B,
                        "solver": args.solver, "sqp_sweeps": args.sqp_sweeps, "mpc_factor": 20, "parallelism": f"shard-by-hopper x{world}, no data-path collective",
-                       "cache": "inputs larger than L2 (per-tick working set %.0f MB per GPU > 126 MB L2)"
-                                % (B * (bytes_tick + 13 * 16 + 15 * 8 * 2) / 1e6),
+                       "cache": cache_note, "hot_path": args.hot_path,
                        "on_infeasible": "respawn"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / K, "same_ticks_as_value": True, "final_state_equals_resident_run": e2e_state_matches,
                     "overlap": "double-buffered: uploads of tick t+1 / downloads of tick t-1 on a copy stream"},
             "gpu_launches": int(launches_all),
             "clocks": clocks, "log_gather": gather_info,
-            "roofline": roofline, "roofline_fp64": roofline_fp64,
+            "roofline": roofline, "roofline_hbm": roofline_hbm, "p50_qp_solve_us": p50,
             "solver_stats": {"solved_exact_frac": solved, "infeasible_ticks": int(inf_ticks),
                              "ipm_iters_per_tick": float(it.mean() / K), "factorisations_per_tick": float(nf.mean() / K),
                              "warm_path_frac_last_tick": float(np.mean(pa == 1)),
                              "hot_path": dict(hot, mode=args.hot_path, deferred_frac=hot["deferred"] / float(B * K)),
                              "mpc_kernel_ms_per_tick": mpc_ms / max(nt, 1), "sim_kernel_ms_per_tick": sim_ms / max(nt, 1)}}
+    if world == 1 and not args.no_extra_configs:
+        # BASELINE.json configs[2] (4096 hoppers on one B200) and a harder synthetic workload (gains x logU(0.5, 2),
+        # full-size initial perturbations: SURVEY 8(d)), measured in this same process
+        line["configs"] = [quick_run(args, dev, local, 4096, W, K, "BASELINE configs[2]: 3f batch of 4096 hoppers, 1 B200" if args.dyn == "3f" else "4096 hoppers"),
+                           quick_run(args, dev, local, 32768, W, K, "hard: 32768 hoppers, gain_spread 2.0 (logU(0.5,2)), perturb 1.0",
+                                     gain_spread=2.0, perturb=1.0)]
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_reference_sample(args.dyn, N, args.cpu_seconds)
+        line["cpu_baseline"] = cpu_reference_sample(args.dyn, N, args.cpu_seconds, python_seconds=4.0)
+        line["p50_qp_solve_us"]["cpu_us_per_solve"] = line["cpu_baseline"]["p50_qp_solve_us"]
     if world > 1:
         torch.distributed.destroy_process_group()
     _emit(line)

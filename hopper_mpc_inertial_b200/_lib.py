@@ -26,7 +26,7 @@ HOT_PATH = {"auto": 0, "cta": 1}
 SYMBOLS = [
     "hmpc_default_config", "hmpc_create", "hmpc_destroy", "hmpc_set_stream", "hmpc_synchronize",
     "hmpc_set_gains", "hmpc_convert", "hmpc_rk4", "hmpc_linearize", "hmpc_condense", "hmpc_solve",
-    "hmpc_rollout", "hmpc_solve_stats", "hmpc_set_timing", "hmpc_kernel_times", "hmpc_launch_count", "hmpc_hot_path_info", "hmpc_measure_fp64_peak", "hmpc_last_error",
+    "hmpc_rollout", "hmpc_solve_stats", "hmpc_set_timing", "hmpc_kernel_times", "hmpc_tick_times", "hmpc_launch_count", "hmpc_hot_path_info", "hmpc_measure_fp64_peak", "hmpc_last_error",
     "hmpc_abi_version",
 ]
 
@@ -83,6 +83,7 @@ def load():
     lib.hmpc_solve_stats.argtypes = [vp, vp, vp, vp, vp]
     lib.hmpc_set_timing.argtypes = [vp, i32]
     lib.hmpc_kernel_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    lib.hmpc_tick_times.argtypes = [vp, vp, vp, i32, C.POINTER(C.c_int)]
     lib.hmpc_launch_count.argtypes = [vp, i64p]
     lib.hmpc_hot_path_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), i64p]
     lib.hmpc_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]

@@ -203,6 +203,13 @@ class BatchMpc:
         _lib.check(self.lib.hmpc_kernel_times(self._h, C.byref(a), C.byref(b), C.byref(n)))
         return a.value, b.value, n.value
 
+    def tick_times(self, cap=4096):
+        """Per-tick (mpc_ms, sim_ms) numpy arrays of the most recent timed rollout (needs set_timing(True))."""
+        a, b, n = np.zeros(cap), np.zeros(cap), C.c_int()
+        _lib.check(self.lib.hmpc_tick_times(self._h, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), int(cap), C.byref(n)))
+        k = min(n.value, cap)
+        return a[:k], b[:k]
+
     def launch_count(self):
         n = C.c_int64()
         _lib.check(self.lib.hmpc_launch_count(self._h, C.byref(n)))

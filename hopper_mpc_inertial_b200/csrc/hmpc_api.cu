@@ -700,6 +700,21 @@ int hmpc_kernel_times(hmpc_handle* h, double* mpc_ms, double* sim_ms, int* n_tic
     return HMPC_OK;
 }
 
+int hmpc_tick_times(hmpc_handle* h, double* mpc_ms, double* sim_ms, int cap, int* n_ticks) {
+    if (int rc = check_handle(h)) return rc;
+    HMPC_CUDA(cudaStreamSynchronize(h->stream));
+    const int n = h->ev_ticks < cap ? h->ev_ticks : cap;
+    for (int t = 0; t < n; ++t) {
+        float m1 = 0, m2 = 0;
+        HMPC_CUDA(cudaEventElapsedTime(&m1, h->ev[3 * t], h->ev[3 * t + 1]));
+        HMPC_CUDA(cudaEventElapsedTime(&m2, h->ev[3 * t + 1], h->ev[3 * t + 2]));
+        if (mpc_ms) mpc_ms[t] = m1;
+        if (sim_ms) sim_ms[t] = m2;
+    }
+    if (n_ticks) *n_ticks = h->ev_ticks;
+    return HMPC_OK;
+}
+
 int hmpc_solve_stats(hmpc_handle* h, int32_t* nfac, int32_t* path, int32_t* n_infeasible, double* flops) {
     if (int rc = check_handle(h)) return rc;
     const size_t B = (size_t)h->cfg.batch;

@@ -41,11 +41,12 @@ def make_batch(B, idx0=0, seed=1234, N=10, n_ticks=100, N_run=None, mpc_factor=2
     """Scenario for hoppers idx0 .. idx0+B-1.
 
     Each hopper gets its own straight or curved reference (goal speed 0.2..1.0 x the reference's
-    0.4 m/s, random heading), its own gains (reference x logU(0.5,2)), its own entry point into the gait
+    0.4 m/s, random heading), its own gains (reference x logU(1/gain_spread, gain_spread); default spread 1.25, the
+    "hard" bench row and test_respawn use 2.0 = SURVEY 8(d)'s logU(0.5, 2)), its own entry point into the gait
     cycle (tick offset 0..phase_ticks-1, i.e. a uniformly random gait phase) and starts near its
-    reference state at that instant (position +-3 cm, height -2..+3 cm, roll/pitch +-0.05 rad, yaw
-    +-0.2 rad, velocity +-0.2 m/s, body rates +-0.3 rad/s) -- close enough that the height rows stay
-    feasible through the swing phases, as in the reference's own runs.
+    reference state at that instant (perturb = 1: position +-3 cm, height -2..+3 cm, roll/pitch +-0.05 rad, yaw
+    +-0.2 rad, velocity +-0.2 m/s, body rates +-0.3 rad/s; the default perturb = 0.5 halves these) -- close enough
+    that the height rows stay feasible through the swing phases, as in the reference's own runs.
     Returns numpy arrays in the SoA layout of include/hmpc.h:
     X0 (13,B), Qdiag (12,B), Rdiag (6,B), xref_tab, pf_tab, C_tab (uint64), pf_switch (uint8), C."""
     if t_p is None:

@@ -200,6 +200,10 @@ int hmpc_solve_stats(hmpc_handle* h, int32_t* nfac, int32_t* path, int32_t* n_in
  * of the solver kernel and of the simulator kernel over the most recent hmpc_rollout and its tick count. */
 int hmpc_set_timing(hmpc_handle* h, int enable);
 int hmpc_kernel_times(hmpc_handle* h, double* mpc_ms, double* sim_ms, int* n_ticks);
+/* The same per tick: mpc_ms / sim_ms are HOST arrays of at least cap doubles (either may be NULL); *n_ticks receives
+ * the tick count of the most recent timed hmpc_rollout.  Used for the p50 QP-solve latency of BASELINE.json's metric:
+ * one entry is the solver kernels' time for the WHOLE batch of that tick. */
+int hmpc_tick_times(hmpc_handle* h, double* mpc_ms_host, double* sim_ms_host, int cap, int* n_ticks);
 
 /* The warp-per-hopper hot path of this handle (hmpc_config.hot_path): resident warps (= hoppers in flight) per SM,
  * the cap on the order of the compact KKT system it keeps in shared memory, registers per thread, and how many
