@@ -1202,7 +1202,7 @@ __device__ inline SolveInfo admm_solve(const QpConst& c, Work& w, Sys& sys, cons
     __syncthreads();
     const int nF = w.cnt[0];
     sys.nF = nF; sys.ng = 0;
-    for (int r = tid; r < m; r += T) z[r] = fmin(fmax(A.row(r, w.x), w.lo[r]), w.hi[r]);
+    for (int r = tid; r < m; r += T) z[r] = A.row(r, w.x);     // OSQP: z = A x at a (warm or cold) start, no projection
     __syncthreads();
     info.nfac = 1;
     if (sys.factor(A, rv, sigma, 0.0, w.tmp)) { info.status = ST_NON_FINITE; return info; }

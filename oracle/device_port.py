@@ -274,7 +274,7 @@ def admm_solve(H, g, A, lo, hi, rho0=0.1, sigma=1e-6, alpha=1.6, max_iter=4000, 
     x = np.zeros(n) if x0 is None else np.array(x0, float)
     y = np.zeros(m) if y0 is None else np.array(y0, float)
     x = np.clip(np.where(fixed, lo[:n], x), lo[:n], hi[:n])
-    z = np.clip(A @ x, lo, hi)
+    z = A @ x                      # OSQP: z = A x at a (warm or cold) start, no projection
     cf = _factor(H, A, rv, sigma, fixed)
     info = dict(status=ST_MAX_ITER, iters=0, nfac=1, rho=rho, pri=np.inf, dua=np.inf)
     next_check = max_iter if fixed_iter else min(first_check, max_iter)

@@ -112,3 +112,19 @@ def test_live_reference_mpcontrol_through_shim(reference, dyn):
         minicvx.SOLVER_OPTS.clear(); minicvx.SOLVER_OPTS.update(old)
     U_or = OracleMpc(prm).mpcontrol(x_in, x_ref, pf, C, True)
     np.testing.assert_allclose(U_ref, U_or, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("tag,dyn", [("loop_ref_2f", "2f"), ("loop_ref_3f_curve", "3f")])
+def test_oracle_loop_matches_the_references_own_runner_golden(tag, dyn):
+    """tests/golden/loop_ref_*.npz: 12 ticks of the reference's unmodified Runner.run at N = 60 (oracle/make_loop_ref.py,
+    OSQP restated at eps 1e-5 + polish).  The oracle's exact-optimum loop -- what the GPU path is compared with --
+    agrees with it to 1e-3 in the applied controls and 1e-5 in the state (measured 2.6e-4 / 2.3e-6)."""
+    from oracle import hopper_oracle as ho
+    from oracle.closed_loop import closed_loop
+    from tests.conftest import golden
+    g = golden(f"{tag}.npz")
+    prm = ho.Params(dyn=dyn, N=int(g["N"]))
+    n = int(g["n_ticks"])
+    Xo, Uo = closed_loop(prm, g["X0"], g["xref_tab"], g["pf_tab"], g["C"], g["pf_switch"], n)
+    assert np.abs(Uo - g["U_log"]).max() < 1e-3
+    np.testing.assert_allclose(Xo, g["X_log"], rtol=0, atol=1e-5)
