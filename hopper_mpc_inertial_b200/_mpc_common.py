@@ -26,10 +26,19 @@ class MpcBase:
         self.f_max = np.array([352, 0, 206])
         self.f_min = -self.f_max
         self.n_x, self.n_u = 12, 6
-        self.Gd = np.zeros(12)
-        self.Gd[8] = -g * t
-        self.Q = np.eye(12)
-        np.fill_diagonal(self.Q, [50., 50., 2., 1., 1., 50., 1., 1., 1., 10., 10., 10.])
+        # constant parts of the continuous-time model and the per-stage discrete matrices, as public attributes like
+        # the reference's (mpc_cvx_euler_3f.py:24-33; 2f has no constant force block, mpc_cvx_euler_2f.py:24-32)
+        self.A = np.zeros((12, 12))
+        self.A[0:3, 6:9] = np.eye(3)
+        self.B = np.zeros((12, 6))
+        if self.DYN == "3f":
+            self.B[6:9, 0:3] = np.eye(3) / m
+        self.G = np.zeros(12)
+        self.G[8] = -g
+        self.Ad = np.zeros((N, 12, 12))
+        self.Bd = np.zeros((N, 12, 6))
+        self.Gd = self.G * t
+        self.Q = np.diag([50., 50., 2., 1., 1., 50., 1., 1., 1., 10., 10., 10.])
         self.R = np.eye(6) * 0.001
         self.x = _Value((N + 1, 12))
         self.u = _Value((N, 6))
@@ -40,8 +49,37 @@ class MpcBase:
         self._bm = None
         self._key = None
 
-    # the reference exposes Ad/Bd as attributes filled by gen_dt_dynamics; computed on demand here
+    # Q / R are the reference's public gain attributes (mpc_cvx_euler_3f.py:34-37).  The device path condenses with
+    # diagonal weights (hmpc_set_gains), so anything else is rejected at assignment time, not in the middle of a run.
+    @staticmethod
+    def _diag_only(M, n, name):
+        M = np.array(M, dtype=float)
+        if M.shape != (n, n):
+            raise ValueError(f"{name} must be a {n}x{n} matrix")
+        if np.any(M - np.diag(np.diag(M))):
+            raise ValueError(f"{name} must be diagonal: the GPU path condenses with diagonal weights only")
+        if np.any(np.diag(M) < 0):
+            raise ValueError(f"{name} must be positive semidefinite")
+        return M
+
+    @property
+    def Q(self):
+        return self._Q
+
+    @Q.setter
+    def Q(self, M):
+        self._Q = self._diag_only(M, 12, "Q")
+
+    @property
+    def R(self):
+        return self._R
+
+    @R.setter
+    def R(self, M):
+        self._R = self._diag_only(M, 6, "R")
+
     def gen_dt_dynamics(self, x, pf):
+        """Fills ``self.Ad`` (N, 12, 12) and ``self.Bd`` (N, 12, 6) like mpc_cvx_euler_3f.py:71-94 (on the GPU)."""
         bm = self._backend()
         dev = bm.device
         xg = torch.as_tensor(np.ascontiguousarray(x, dtype=float)[:, :, None], device=dev)
@@ -53,7 +91,7 @@ class MpcBase:
 
     def _backend(self):
         key = (float(self.t), int(self.N), float(self.m), float(self.g), float(self.mu),
-               self.Jinv.tobytes(), self.rh.tobytes(), float(self.f_max[2]))
+               self.Jinv.tobytes(), self.rh.tobytes(), float(self.f_max[2]), repr(sorted(self._overrides.items(), key=lambda kv: kv[0])))
         if self._bm is None or key != self._key:
             if self._bm is not None:
                 self._bm.close()
@@ -66,9 +104,8 @@ class MpcBase:
         return self._bm
 
     def _push_gains(self, bm):
-        Q, R = np.asarray(self.Q, float), np.asarray(self.R, float)
-        if np.any(Q - np.diag(np.diag(Q))) or np.any(R - np.diag(np.diag(R))):
-            raise NotImplementedError("the GPU path supports diagonal Q and R only")
+        # in-place edits (mpc.Q[0, 1] = ...) bypass the setters: validate again
+        Q, R = self._diag_only(self._Q, 12, "Q"), self._diag_only(self._R, 6, "R")
         qd = torch.as_tensor(np.diag(Q).copy()[:, None], device=bm.device).contiguous()
         rd = torch.as_tensor(np.diag(R).copy()[:, None], device=bm.device).contiguous()
         bm.set_gains(qd, rd)

@@ -894,7 +894,9 @@ __device__ inline int polish_verified(const QpConst& c, Work& w, Sys& sys, const
         // a trial that had no wrong-signed row (measured: fewer trials and fewer give-ups than doing both at
         // once).  w.side (interior-point scratch) holds the proposed change: 1 release, 2 / 3 activate lower / upper.
         int bad = (v[0] <= 1e-10 * scale) ? 0 : 1, anywrong = 0;
-        if (!(v[0] == v[0]) || !(v[2] == v[2])) bad = 2;
+        // v[] comes out of a block reduction: every thread sees the same value, no second reduction needed
+        const bool nonfinite = !(v[0] == v[0]) || !(v[2] == v[2]);
+        if (nonfinite) bad = 1;
         for (int r = tid; r < m; r += T) {
             const double ax = A.row(r, w.xp), lo = w.lo[r], hi = w.hi[r];
             const int cd = w.code[r];
@@ -926,7 +928,7 @@ __device__ inline int polish_verified(const QpConst& c, Work& w, Sys& sys, const
         }
         changed = __syncthreads_or(changed);
         PH_ADD(7, ph_v);
-        if (!changed || (bad & 2)) return 0;
+        if (!changed || nonfinite) return 0;
     }
     return 0;
 }

@@ -14,6 +14,7 @@ import torch
 
 from . import mpc_cvx_euler_2f, mpc_cvx_euler_3f, planner
 from .batch import cbits_from_C
+from .utils import H, L, R, quat2euler
 
 try:
     from tqdm import tqdm
@@ -24,31 +25,15 @@ except Exception:  # pragma: no cover
 np.set_printoptions(suppress=True, linewidth=np.nan)
 
 
-def _quat_rotm(q):
-    w, x, y, z = q
-    return np.array([
-        [w * w + x * x - y * y - z * z, 2 * (x * y - w * z), 2 * (x * z + w * y)],
-        [2 * (x * y + w * z), w * w - x * x + y * y - z * z, 2 * (y * z - w * x)],
-        [2 * (x * z - w * y), 2 * (y * z + w * x), w * w - x * x - y * y + z * z]])
-
-
 def convert(X_in):
     """SE(3) 13-state -> Euler 12-state on the host (robotrunner.py:19-28); used for the planner's
     end points only -- the per-tick conversion runs on the GPU (hmpc_convert)."""
     X_in = np.asarray(X_in, float)
     q = X_in[3:7]
-    Rm = _quat_rotm(q)
-    w, x, y, z = q
-    s = 2.0 / (q @ q)
-    m00, m10, m20 = 1 - s * (y * y + z * z), s * (x * y + w * z), s * (x * z - w * y)
-    m21, m22 = s * (y * z + w * x), 1 - s * (x * x + y * y)
-    cy = np.hypot(m00, m10)
+    Rm = H.T @ L(q) @ R(q).T @ H                  # rotation body -> world (robotrunner.py:22)
     x0 = np.zeros(12)
     x0[0:3] = X_in[0:3]
-    if cy > 4 * np.finfo(float).eps:
-        x0[3:6] = [np.arctan2(m21, m22), np.arctan2(-m20, cy), np.arctan2(m10, m00)]
-    else:
-        x0[3:6] = [np.arctan2(-(s * (y * z - w * x)), 1 - s * (x * x + z * z)), np.arctan2(-m20, cy), 0.0]
+    x0[3:6] = quat2euler(q)
     x0[6:9] = Rm @ X_in[7:10]
     x0[9:] = Rm @ X_in[10:13]
     return x0
@@ -78,6 +63,12 @@ class Runner:
         self.X_f = np.hstack([self.dist, 0, 0.27, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0]).T
         mu = 1
         mpc_dyn = {'2f': mpc_cvx_euler_2f, '3f': mpc_cvx_euler_3f}[dyn]
+        # the device integrates with h = sim_dt and runs mpc_factor steps per tick in the fused path: both follow
+        # this Runner's dt (robotrunner.py:48,154-164)
+        if not 1 <= self.mpc_factor <= 255:
+            raise ValueError("dt must give 1..255 simulator steps per MPC tick (mpc_dt / dt)")
+        mpc_kwargs.setdefault("sim_dt", float(self.dt))
+        mpc_kwargs.setdefault("mpc_factor", int(self.mpc_factor))
         self.mpc = mpc_dyn.Mpc(t=self.mpc_dt, N=self.N, m=self.m, g=self.g, mu=mu, Jinv=self.Jinv,
                                rh=self.rh, device=device, **mpc_kwargs)
         self.t_start = 0.5 * self.t_p * self.phi_switch

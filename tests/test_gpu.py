@@ -478,6 +478,29 @@ def test_runner_and_cli_dropin():
     assert r3.X_traj.shape == (101, 13)
 
 
+def test_runner_forwards_a_non_default_dt():
+    """Runner(dt=2e-3): the device integrates with h = dt and runs mpc_dt / dt = 10 steps per tick
+    (robotrunner.py:48,154-164); both loops agree with the oracle loop run with the same constants."""
+    from hopper_mpc_inertial_b200 import planner
+    from hopper_mpc_inertial_b200.robotrunner import Runner
+    dt, N, N_run = 2e-3, 10, 120
+    r = Runner(dt=dt, dyn="3f", curve=True, N_run=N_run, N=N, progress=False)
+    assert r.mpc_factor == 10
+    X_log, U_log = r.run_fused()
+    n_ticks = N_run // r.mpc_factor
+    xt, pt, C, sw = planner.mpc_tables(r.x_ref, r.pf_ref, n_ticks, N, r.mpc_factor, dt, r.mpc_dt, r.t_start)
+    prm = ho.Params(dyn="3f", N=N, sim_dt=dt, mpc_factor=r.mpc_factor)
+    Xo, Uo = closed_loop(prm, r.X_0, xt, pt, C, sw, n_ticks)
+    assert np.all(np.abs(U_log - Uo) <= 10 * u_tol(Uo))
+    np.testing.assert_allclose(X_log, Xo, rtol=0, atol=1e-6)
+    r2 = Runner(dt=dt, dyn="3f", curve=True, N_run=N_run, N=N, progress=False)
+    r2.run()
+    np.testing.assert_allclose(r2.X_traj[::r2.mpc_factor], X_log, rtol=0, atol=1e-9)
+    # and the default step really differs (the test would not notice a dropped override otherwise)
+    r3 = Runner(dt=1e-3, dyn="3f", curve=True, N_run=N_run, N=N, progress=False)
+    assert np.abs(r3.run_fused()[0][1] - X_log[1]).max() > 1e-4
+
+
 def test_sharded_run_equals_unsharded():
     """Sharding by hopper: two shards -- on two GPUs when the box has them, else two handles on one
     GPU -- reproduce the unsharded batch bit for bit (scenarios are keyed by the global hopper index)."""
