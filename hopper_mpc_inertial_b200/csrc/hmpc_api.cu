@@ -79,8 +79,9 @@ struct hmpc_handle {
     bool warp_ok = false;
     int warp_rounds = 0;
     int warp_grid = 0, warp_wpc = 1, warp_kcap = 0, warp_wdoubles = 0, warp_per_sm = 0, warp_regs = 0;
-    size_t warp_smem = 0, hstride = 0;
-    double* hws = nullptr;
+    size_t warp_smem = 0, pstride = 0;
+    double* prep = nullptr;       // [B][pstride] QP records the prep kernel hands to the solve kernel
+    int32_t* prep_flag = nullptr; // [B]
     int* defer_list = nullptr;    // [B] hoppers the warp kernel handed to the CTA kernel this tick
     int32_t* n_defer = nullptr;   // [1] accumulated deferrals of the most recent solve / rollout
 };
@@ -474,13 +475,15 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
             h->warp_smem = wbytes * best_wpc;
             const size_t want = ((size_t)B + best_wpc - 1) / best_wpc;
             h->warp_grid = (int)std::min<size_t>(want, (size_t)h->sm_count * (best_w / best_wpc));
-            h->hstride = ((n + 7) & ~(size_t)7) * ((n + 7) & ~(size_t)7);   // [ld][ld], ld = n rounded up to a tile
-            if ((e = cudaMalloc((void**)&h->hws, (size_t)h->warp_grid * best_wpc * h->hstride * 8)) != cudaSuccess) {
+            h->pstride = hmpc::prep_stride((int)N);
+            if ((e = cudaMalloc((void**)&h->prep, B * h->pstride * 8)) != cudaSuccess ||
+                (e = cudaMalloc((void**)&h->prep_flag, B * 4)) != cudaSuccess) {
                 hmpc_destroy(h);
-                return fail(HMPC_ERR_ALLOC, std::string("cudaMalloc warp workspace: ") + cudaGetErrorString(e));
+                return fail(HMPC_ERR_ALLOC, std::string("cudaMalloc QP records: ") + cudaGetErrorString(e));
             }
             h->warp_rounds = rounds;
-            if ((e = hmpc::warp_set_smem(rounds, best_wpc, smem_i)) != cudaSuccess) {
+            if ((e = hmpc::warp_set_smem(rounds, best_wpc, smem_i)) != cudaSuccess ||
+                (e = hmpc::prep_set_smem(smem_i)) != cudaSuccess) {
                 hmpc_destroy(h);
                 return fail(HMPC_ERR_CUDA, std::string("cudaFuncSetAttribute (warp kernel): ") + cudaGetErrorString(e));
             }
@@ -501,7 +504,7 @@ int hmpc_destroy(hmpc_handle* h) {
     cudaFree(h->Qd); cudaFree(h->Rd); cudaFree(h->Xsol); cudaFree(h->Usol); cudaFree(h->xin);
     cudaFree(h->U0); cudaFree(h->st_tmp); cudaFree(h->it_tmp); cudaFree(h->ws);
     cudaFree(h->code); cudaFree(h->valid); cudaFree(h->st_tick); cudaFree(h->nfac); cudaFree(h->path); cudaFree(h->ninf); cudaFree(h->flops); cudaFree(h->work_ctr);
-    cudaFree(h->hws); cudaFree(h->defer_list); cudaFree(h->n_defer);
+    cudaFree(h->prep); cudaFree(h->prep_flag); cudaFree(h->defer_list); cudaFree(h->n_defer);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     delete h;
     return HMPC_OK;
@@ -584,10 +587,11 @@ cudaError_t launch_mpc(hmpc_handle* h, const hmpc::QpConst& qc, const hmpc::MpcI
     const bool warp = h->warp_ok && hmpc::warp_path_applies(h->cfg, io.init);
     if (warp) {
         const hmpc::WarpLaunch wl{h->warp_grid, h->warp_wpc, h->warp_rounds, h->warp_smem, h->stream, h->cfg.batch, h->warp_kcap,
-                                  h->warp_wdoubles, h->hws, h->hstride, h->work_ctr, h->defer_list, h->work_ctr + 1};
+                                  h->warp_wdoubles, h->prep, h->pstride, h->prep_flag, h->work_ctr, h->defer_list, h->work_ctr + 1};
+        hmpc::prep_launch(wl, qc, io);
         hmpc::warp_launch(wl, qc, io);
         defer_stats_kernel<<<1, 1, 0, h->stream>>>(h->work_ctr, h->n_defer);
-        h->launches += 2;
+        h->launches += 3;
     }
     const hmpc::MpcLaunch l{h->mpc_grid, h->mpc_threads, h->mpc_smem, h->stream, h->cfg.batch, h->sm_count, h->ws,
                             h->work_ctr + 2, warp ? h->defer_list : nullptr, warp ? h->work_ctr + 1 : nullptr};

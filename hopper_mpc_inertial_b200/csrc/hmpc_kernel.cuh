@@ -82,10 +82,14 @@ struct WarpLaunch {
     size_t smem;            // dynamic shared memory per CTA
     cudaStream_t stream;
     int B, kcap, wdoubles;
-    double* hws;            // per-warp Hessian workspace
-    size_t hstride;
+    double* prep;           // per-hopper QP records (hmpc_warp.cuh: prep_stride), written by the prep kernel
+    size_t pstride;
+    int32_t* flags;         // per-hopper PREP_* flag
     int *work_ctr, *defer_list, *defer_cnt;
 };
+int prep_wdoubles(int N);
+cudaError_t prep_set_smem(int bytes);
+void prep_launch(const WarpLaunch&, const QpConst&, const MpcIo&);
 bool warp_wpc_supported(int rounds, int wpc);
 cudaError_t warp_set_smem(int rounds, int wpc, int bytes);
 cudaError_t warp_regs(int rounds, int wpc, int* regs);

@@ -83,6 +83,20 @@ __host__ __device__ inline size_t warp_work_doubles(int N, int kcap) {
     d += (5 * n + (size_t)kcap + 2 * m + N + 7) / 8;   // bytes: fr cpos idx fixed pin | grow | code side | stance
     return (d + 1) & ~(size_t)1;
 }
+// ------------------------------------------------------------------------------------------------
+// The per-hopper QP record the prep kernel leaves in HBM for the solve kernel (phase split: the condensing runs at
+// high occupancy in its own launch, the solve kernel's lock-step rounds then all do the same thing -- one trial):
+//   [0, hs)   compact Hessian over the non-fixed variables, [nf][ld] row-major, ld = nf rounded up to 8 (hs = ld_max^2)
+//   then      g [n -> 8],  hlo [N -> 8],  x_in [12 -> 16]
+// and one flag per hopper (PREP_*).
+// ------------------------------------------------------------------------------------------------
+enum { PREP_OK = 0, PREP_INVALID = 1, PREP_INFEASIBLE = 2 };
+__host__ __device__ inline size_t prep_hstride(int N) { const size_t l = (6 * (size_t)N + 7) & ~(size_t)7; return l * l; }
+__host__ __device__ inline size_t prep_stride(int N) {
+    return prep_hstride(N) + ((6 * (size_t)N + 7) & ~(size_t)7) + (((size_t)N + 7) & ~(size_t)7) + 16;
+}
+constexpr int kPrepKcap = 8;      // the prep kernel's per-warp slice: same carve, smallest factor (unused there)
+
 __device__ inline void wcarve(WWork& w, double* base, int N, int kcap) {
     const int n = 6 * N, m = 11 * N;
     double* p = base;
@@ -272,15 +286,10 @@ __device__ inline void wlinearize_all(const QpConst& c, WWork& w, int b, int B, 
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// load + time shift + linearise + condense for hopper b (warm tick).  Returns 1 (all lanes) when a height row
-// cannot be met (SURVEY App. D2).  Leaves Hc (global, compact), g, bounds, fixed / fr / cpos in place.
-// ------------------------------------------------------------------------------------------------
-__device__ inline int wcondense(const QpConst& c, WWork& w, int b, int B, const MpcIo& io, int lane) {
+// stance flags, box bounds, height-row scaling, fixed variables and the compact ordering of the non-fixed ones: all
+// functions of the contact schedule only.  Ends with a __syncwarp().
+__device__ inline void wload_sets(const QpConst& c, WWork& w, int b, const MpcIo& io, int lane) {
     const int N = c.N, n = 6 * N;
-    const size_t Bs = (size_t)B;
-    for (int i = lane; i < 12; i += 32) { w.xin[i] = io.x_in[i * Bs + b]; w.Qd[i] = io.Qd[i * Bs + b]; }
-    if (lane < 6) w.Rd[lane] = io.Rd[lane * Bs + b];
     {
         const uint64_t bits = io.Cbits[b];
         for (int k = lane; k < N; k += 32) w.stance[k] = (int8_t)((bits >> k) & 1ull);
@@ -294,10 +303,29 @@ __device__ inline int wcondense(const QpConst& c, WWork& w, int b, int B, const 
         if (cc == 1 && c.dyn == 2) { lo = 0.0; hi = 0.0; }
         w.blo[lane] = lo; w.bhi[lane] = hi;
     }
-    __syncwarp();
-    wlinearize_all(c, w, b, B, io, lane);
     for (int k = lane; k < N; k += 32) w.hinv[k] = (k >= 2) ? 1.0 / (double)(k - 1) : 0.0;
+    __syncwarp();
     for (int v = lane; v < n; v += 32) w.fixed[v] = (wbox_hi(w, v) - wbox_lo(w, v)) < 1e-12 ? 1 : 0;
+    __syncwarp();
+    // non-fixed variables, in order
+    w.nf = wcompact(0, n, n, w.fr, 0, lane, [&](int v) { return w.fixed[v] == 0; });
+    w.ld = (w.nf + 7) & ~7;
+    __syncwarp();
+    for (int i = lane; i < w.nf; i += 32) w.cpos[w.fr[i]] = (uint8_t)i;
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// load + time shift + linearise + condense for hopper b (warm tick).  Returns 1 (all lanes) when a height row
+// cannot be met (SURVEY App. D2).  Leaves Hc (global, compact), g, bounds, fixed / fr / cpos in place.
+// ------------------------------------------------------------------------------------------------
+__device__ inline int wcondense(const QpConst& c, WWork& w, int b, int B, const MpcIo& io, int lane) {
+    const int N = c.N, n = 6 * N;
+    const size_t Bs = (size_t)B;
+    for (int i = lane; i < 12; i += 32) { w.xin[i] = io.x_in[i * Bs + b]; w.Qd[i] = io.Qd[i * Bs + b]; }
+    if (lane < 6) w.Rd[lane] = io.Rd[lane * Bs + b];
+    wload_sets(c, w, b, io, lane);
+    wlinearize_all(c, w, b, B, io, lane);
     __syncwarp();
     // prefix sums of cos / sin (same summation order as condense())
     for (int i = lane; i <= N; i += 32) {
@@ -305,11 +333,7 @@ __device__ inline int wcondense(const QpConst& c, WWork& w, int b, int B, const 
         for (int k = 0; k < i; ++k) { pc += w.cz[k]; ps += w.sz[k]; }
         w.PC[i] = pc; w.PS[i] = ps;
     }
-    // non-fixed variables, in order
-    w.nf = wcompact(0, n, n, w.fr, 0, lane, [&](int v) { return w.fixed[v] == 0; });
-    w.ld = (w.nf + 7) & ~7;
     __syncwarp();
-    for (int i = lane; i < w.nf; i += 32) w.cpos[w.fr[i]] = (uint8_t)i;
     const double dt = c.dt, gdt = -c.g * dt;
     const double zc = dt * dt / c.m;
     int infeasible = 0;
@@ -511,15 +535,16 @@ __device__ inline void wmatvec(WWork& w, int lane) {
     const double* hp = w.Hc + g * ld + 2 * t;
 #pragma unroll 1
     for (int I = 0; I < ntf; ++I) {
+        // all tiles of the block row are requested from L2 before the first product (ntf <= 8)
+        d2 h[8];
+#pragma unroll
+        for (int K = 0; K < 8; ++K) h[K] = (K < ntf) ? ld2(hp + 8 * K) : d2{0.0, 0.0};
         double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;            // two chains: even / odd column tiles
-        int K = 0;
-#pragma unroll 1
-        for (; K + 1 < ntf; K += 2) {
-            const d2 h0 = ld2(hp + 8 * K), h1 = ld2(hp + 8 * K + 8);
-            tile_mac(a0, a1, h0, vec_b(w.xc + 8 * K, lane));
-            tile_mac(b0, b1, h1, vec_b(w.xc + 8 * K + 8, lane));
+#pragma unroll
+        for (int K = 0; K < 8; K += 2) {
+            if (K < ntf) tile_mac(a0, a1, h[K], vec_b(w.xc + 8 * K, lane));
+            if (K + 1 < ntf) tile_mac(b0, b1, h[K + 1], vec_b(w.xc + 8 * K + 8, lane));
         }
-        if (K < ntf) tile_mac(a0, a1, ld2(hp + 8 * K), vec_b(w.xc + 8 * K, lane));
         const int i = 8 * I + g;
         if (t == 0 && i < nf) w.hx[w.fr[i]] = a0 + b0;
         hp += 8 * ld;
@@ -528,53 +553,63 @@ __device__ inline void wmatvec(WWork& w, int lane) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// 8x8 diagonal block starting at pivot j0 of the system, in place in shared memory: signed Cholesky  C = V S V'
-// of the tile D (row-major, lower triangle), S = +1 for pivots < nF (variables), -1 for the active rows, then the
-// inverse  W = V^-1  (lower triangular, zeros above the diagonal) into Wt.  When the first active-row pivot lies in
-// this block, the diagonal of the remaining (Schur complement) rows is scaled by 1 + eps at that point
-// (hmpc_qp.cuh: LinSys::factor).  Lane l holds entries (l >> 3, l & 7) and (4 + (l >> 3), l & 7).
+// 8x8 diagonal block of the system, in place in registers: signed Cholesky  C = V S V'  of the tile D (row-major,
+// lower triangle; the strict upper triangle is never read as data), then the inverse  W = V^-1  (lower triangular,
+// zeros above the diagonal) into Wt.  Lane l holds entries (l >> 3, l & 7) and (4 + (l >> 3), l & 7).
+//   MIXED = false: all eight pivots have the same sign sgn (+1 variables, -1 active rows; a block of rows is the
+//                  plain Cholesky factorisation of -C);
+//   MIXED = true : pivots 0 .. jrel-1 are variables (+), jrel .. 7 active rows (-), 0 < jrel < 8, and the diagonal of
+//                  the remaining (Schur complement) rows is scaled by 1 + eps once the variables are eliminated
+//                  (hmpc_qp.cuh: LinSys::factor).
+// The eight elimination steps are unrolled: which register holds column j / row j is then known at compile time, and
+// one step costs five 64-bit shuffles, one reciprocal square root and a handful of FMAs (profiles/README.md: the
+// rolled loop spent 1300 instructions per block, a third of the kernel's instruction stream).
 // Returns nonzero when a pivot has the wrong sign or is not finite.  Ends with a __syncwarp().
 // ------------------------------------------------------------------------------------------------
-__device__ inline int wdiag8(double* D, double* Wt, int j0, int nF, double eps, int lane) {
+template <bool MIXED>
+__device__ __forceinline__ int wdiag8(const double* D, double* Wt, int jrel, double sgn, double eps, int lane) {
     const int kk = lane & 7, i0 = lane >> 3, i1 = i0 + 4;
+    const int rowsrc = lane & 24, colsrc = 8 * (kk & 3);   // lanes holding (i0, 0) / (kk mod 4, 0): + j gives column j
+    const bool lowk = kk < 4;
     int bad = 0;
     // W starts as the identity and receives the row operations of the elimination (forward substitution on I):
     // after pivot j, row j of W is final and rows i > j have  W(i, 0..j) -= V(i, j) W(j, 0..j)
-    double w0 = (i0 == kk) ? 1.0 : 0.0, w1 = (i1 == kk) ? 1.0 : 0.0;     // W(i0, kk), W(i1, kk) in registers
+    double w0 = (i0 == kk) ? 1.0 : 0.0, w1 = (i1 == kk) ? 1.0 : 0.0;     // W(i0, kk), W(i1, kk)
     double c0 = D[8 * i0 + kk], c1 = D[8 * i1 + kk];                      // C(i0, kk), C(i1, kk)
-#pragma unroll 1
+    if (!MIXED) { c0 *= sgn; c1 *= sgn; }
+#pragma unroll
     for (int j = 0; j < 8; ++j) {
-        if (j0 + j == nF && j > 0) {            // all variables eliminated: regularise the rows' Schur complement
-            if (i0 == kk && kk >= j) c0 *= 1.0 + eps;
-            if (i1 == kk && kk >= j) c1 *= 1.0 + eps;
+        double s = 1.0;
+        if (MIXED) {
+            if (j == jrel) {            // all variables eliminated: regularise the rows' Schur complement
+                if (i0 == kk && kk >= j) c0 *= 1.0 + eps;
+                if (i1 == kk && kk >= j) c1 *= 1.0 + eps;
+            }
+            s = (j < jrel) ? 1.0 : -1.0;
         }
-        const double s = (j0 + j < nF) ? 1.0 : -1.0;
-        // column j of C lives in the lanes with kk == j: lane 8 r + j holds rows r (c0) and r + 4 (c1)
-        const double piv = (j < 4) ? __shfl_sync(kFullMask, c0, 9 * j) : __shfl_sync(kFullMask, c1, 9 * j - 32);
-        const double ap = s * piv;
+        // pivot C(j, j): lane 8 (j mod 4) + j, register c0 for j < 4 and c1 otherwise
+        const double piv = __shfl_sync(kFullMask, j < 4 ? c0 : c1, 8 * (j & 3) + j);
+        const double ap = MIXED ? s * piv : piv;
         const bool ok = (ap > 0.0) && (ap < 1e30);
         if (!ok) bad = 1;
         const double rsq = fast_rsqrt(ok ? ap : 1.0);
-        // V(i, j) for this lane's two rows, V(kk, j) for its column
-        const double cj0 = __shfl_sync(kFullMask, c0, 8 * i0 + j), cj1 = __shfl_sync(kFullMask, c1, 8 * i0 + j);
-        const double ck0 = __shfl_sync(kFullMask, c0, 8 * (kk & 3) + j), ck1 = __shfl_sync(kFullMask, c1, 8 * (kk & 3) + j);
-        const double vi0 = (i0 == j) ? ap * rsq : s * cj0 * rsq, vi1 = (i1 == j) ? ap * rsq : s * cj1 * rsq;
-        const double vk = s * (kk < 4 ? ck0 : ck1) * rsq;
+        const double srs = MIXED ? s * rsq : rsq;
+        // V(i, j) = S_j C(i, j) / sqrt(|C(j, j)|) for this lane's two rows and for its column
+        const double vi0 = __shfl_sync(kFullMask, c0, rowsrc + j) * srs, vi1 = __shfl_sync(kFullMask, c1, rowsrc + j) * srs;
+        const double ck0 = __shfl_sync(kFullMask, c0, colsrc + j), ck1 = __shfl_sync(kFullMask, c1, colsrc + j);
+        const double vk = (lowk ? ck0 : ck1) * (MIXED ? rsq : srs);     // S_j V(kk, j)
         // row j of W, scaled: W(j, kk) / V(j, j)
-        const double wj = ((j < 4) ? __shfl_sync(kFullMask, w0, 8 * j + kk) : __shfl_sync(kFullMask, w1, 8 * (j - 4) + kk)) * rsq;
-        if (kk == j) { c0 = vi0; c1 = vi1; }                                   // column j of V
-        else if (kk > j) {                                                     // rank-1 update of the trailing part
-            if (i0 >= kk) c0 = fma(-s * vi0, vk, c0);
-            if (i1 >= kk) c1 = fma(-s * vi1, vk, c1);
-        }
-        if (kk <= j) {
+        const double wj = __shfl_sync(kFullMask, j < 4 ? w0 : w1, 8 * (j & 3) + kk) * rsq;
+        if (kk > j) {                               // rank-1 update of the trailing part (upper entries: don't care)
+            c0 = fma(-vi0, vk, c0);
+            c1 = fma(-vi1, vk, c1);
+        } else {
             w0 = (i0 == j) ? wj : (i0 > j ? fma(-vi0, wj, w0) : w0);
             w1 = (i1 == j) ? wj : (i1 > j ? fma(-vi1, wj, w1) : w1);
         }
     }
     Wt[8 * i0 + kk] = w0;
     Wt[8 * i1 + kk] = w1;
-    (void)D;
     __syncwarp();
     return bad;
 }
@@ -619,10 +654,23 @@ __device__ inline int wfactor(const QpConst& c, WWork& w, const AOp& A, int nF, 
         const double s0 = (j0 < nF) ? 1.0 : -1.0, s1 = (j0 + 1 < nF) ? 1.0 : -1.0;
         const double* Lj = L + tile_off(J, 0) + fo;                  // tiles (J, K), K = 0 .. J
         const bool scaled = (J > Jb) || (J == Jb && !mixed);        // diagonal regularised here (else inside wdiag8)
+        // Hessian rows of this lane's two columns (block column J made of variables only: plain gather)
+        const bool jvars = 8 * J + 8 <= nF;
+        const double* hc0 = w.Hc + (jvars ? (int)w.idx[j0] * w.ld : 0);
+        const double* hc1 = w.Hc + (jvars ? (int)w.idx[j0 + 1] * w.ld : 0);
         d2 bw = d2{0.0, 0.0};
 #pragma unroll 1
         for (int I = J; I < nt; ++I) {
             const double* Li = L + tile_off(I, 0) + fo;              // tiles (I, K)
+            // K(I, J) first: the gather from the L2-resident Hessian is in flight while the tile products run
+            const int i = 8 * I + g;
+            double k0, k1;
+            if (8 * I + 8 <= nF) {                                   // variables x variables (H is stored symmetric)
+                const int ri = (int)w.idx[i];
+                k0 = hc0[ri]; k1 = hc1[ri];
+            } else {
+                k0 = wentry(c, w, A, nF, nk, i, j0); k1 = wentry(c, w, A, nF, nk, i, j0 + 1);
+            }
             double a0 = 0.0, a1 = 0.0;
             const int kplain = J < Jb ? J : Jb;
 #pragma unroll 1
@@ -649,8 +697,6 @@ __device__ inline int wfactor(const QpConst& c, WWork& w, const AOp& A, int nF, 
                 }
             }
             // C = K - acc
-            const int i = 8 * I + g;
-            double k0 = wentry(c, w, A, nF, nk, i, j0), k1 = wentry(c, w, A, nF, nk, i, j0 + 1);
             if (I == J) {
                 if (i >= nk) { if (ondiag0) k0 = -1.0; if (ondiag1) k1 = -1.0; }          // past the end: unit pivots
                 else if (scaled && i >= nF) { if (ondiag0) k0 *= 1.0 + eps; if (ondiag1) k1 *= 1.0 + eps; }
@@ -659,8 +705,11 @@ __device__ inline int wfactor(const QpConst& c, WWork& w, const AOp& A, int nF, 
             if (I == J) {                                            // diagonal tile -> W_J
                 st2(scratch + fo, c0, c1);
                 __syncwarp();
-                bad |= wdiag8(scratch, L + tile_off(J, J), 8 * J, nF, eps, lane);
-                bw = ld2(L + tile_off(J, J) + fo);
+                double* Wt = L + tile_off(J, J);
+                const int jrel = nF - 8 * J;                         // first active-row pivot inside this tile
+                if (jrel > 0 && jrel < 8) bad |= wdiag8<true>(scratch, Wt, jrel, 1.0, eps, lane);
+                else bad |= wdiag8<false>(scratch, Wt, 0, jrel >= 8 ? 1.0 : -1.0, eps, lane);
+                bw = ld2(Wt + fo);
             } else {                                                 // panel: V(I,J) = C(I,J) W_J' S_J
                 double d0 = 0.0, d1 = 0.0;
                 tile_mac(d0, d1, d2{c0, c1}, bw);
@@ -811,10 +860,12 @@ __device__ inline int wtrial(const QpConst& c, WWork& w, const AOp& A, int kcap,
         // ---- pass 1: multipliers of pinned variables, scales ----
         if (!hx_current) { wmatvec(w, lane); info.flops += flops_matvec(n); }
         double s_stat = 0.0, s_scale = 0.0, s_mult = 0.0;
+        int notfinite = 0;                                // fmax() drops NaNs: test the gradient entries themselves
         for (int i = lane; i < n; i += 32) {
             if (w.fixed[i]) continue;                     // eliminated a priori: no Hessian row, multiplier unused
             const double aty = A.colT(i, mul);            // mul[i] == 0 on box rows at this point
             const double G = w.hx[i] + w.g[i] + aty;
+            if (!(fabs(G) < 1e300)) notfinite = 1;
             s_scale = fmax(s_scale, fmax(fabs(w.hx[i]), fmax(fabs(w.g[i]), fabs(aty))));
             if (!w.pin[i]) s_stat = fmax(s_stat, fabs(G));
             else { mul[i] = -G; s_mult = fmax(s_mult, fabs(G)); }
@@ -826,7 +877,7 @@ __device__ inline int wtrial(const QpConst& c, WWork& w, const AOp& A, int kcap,
         const double stol = tol * fmax(scale, s_mult);
         // ---- pass 2: per-row verdicts and the refined active set ----
         int bad = (s_stat <= 1e-10 * scale) ? 0 : 1, anywrong = 0;
-        const int nonfinite = (!(s_stat == s_stat) || !(s_mult == s_mult)) ? 1 : 0;
+        const int nonfinite = __any_sync(kFullMask, notfinite) || !(s_stat == s_stat) || !(s_mult == s_mult);
         for (int r = lane; r < m; r += 32) {
             const bool apriori = (r < n) && w.fixed[r];
             const int cd = w.code[r];
@@ -881,12 +932,40 @@ __device__ inline int wpolish(const QpConst& c, WWork& w, const AOp& A, int kcap
 // One warm tick of hopper b by one warp.  Returns 1 when the hopper is done (outputs and handle state written),
 // 0 when it has to take the CTA kernel (nothing written).
 // ------------------------------------------------------------------------------------------------
-// wbegin: load, time shift, linearise, condense, warm start.  Returns 0 when the hopper must take the CTA kernel.
-__device__ inline int wbegin(const QpConst& c, WWork& w, int b, int B, const MpcIo& io, int lane) {
+// wprep (prep kernel): load, time shift, linearise, condense hopper b and leave its QP record in HBM.
+__device__ inline void wprep(const QpConst& c, WWork& w, double* rec, int32_t* flag, int b, int B, const MpcIo& io, int lane) {
+    const int N = c.N, n = 6 * N;
+    if (!io.valid[b]) { if (lane == 0) *flag = PREP_INVALID; return; }
+    w.Hc = rec;
+    const int infeasible = wcondense(c, w, b, B, io, lane);
+    double* rg = rec + prep_hstride(N);
+    double* rh = rg + ((n + 7) & ~7);
+    double* rx = rh + ((N + 7) & ~7);
+    for (int i = lane; i < n; i += 32) rg[i] = w.g[i];
+    for (int k = lane; k < N; k += 32) rh[k] = w.hlo[k];
+    if (lane < 12) rx[lane] = w.xin[lane];
+    if (lane == 0) *flag = infeasible ? PREP_INFEASIBLE : PREP_OK;
+}
+// wfetch (solve kernel): take hopper b's record, rebuild the index sets, warm start.  Returns 0 when the hopper must
+// take the CTA kernel (no valid previous tick / infeasible height row).
+__device__ inline int wfetch(const QpConst& c, WWork& w, double* rec, const int32_t* flag, int b, int B, const MpcIo& io, int lane) {
     const int N = c.N, n = 6 * N, m = 11 * N;
     const size_t Bs = (size_t)B;
-    if (!io.valid[b]) { HMPC_EMUL_COUNT(4); return 0; }
-    if (wcondense(c, w, b, B, io, lane)) { HMPC_EMUL_COUNT(5); return 0; }
+    const int f = *flag;
+    if (f == PREP_INVALID) { HMPC_EMUL_COUNT(4); return 0; }
+    if (f == PREP_INFEASIBLE) { HMPC_EMUL_COUNT(5); return 0; }
+    w.Hc = rec;
+    wload_sets(c, w, b, io, lane);
+#ifndef HMPC_HOST_EMUL
+    // the record was written by another kernel long ago: pull the Hessian into L2 while the rest is set up
+    for (int o = 16 * lane; o < w.nf * w.ld; o += 16 * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + o));
+#endif
+    const double* rg = rec + prep_hstride(N);
+    const double* rh = rg + ((n + 7) & ~7);
+    const double* rx = rh + ((N + 7) & ~7);
+    for (int i = lane; i < n; i += 32) w.g[i] = rg[i];
+    for (int k = lane; k < N; k += 32) w.hlo[k] = rh[k];
+    if (lane < 12) w.xin[lane] = rx[lane];
     // warm start: stage k starts from the previous tick's stage k+1, the last two stages keep their own previous
     // pattern (mpc_hopper in hmpc_mpc.cuh)
     for (int i = lane; i < n; i += 32) {
@@ -985,8 +1064,8 @@ __device__ inline void wfinish(const QpConst& c, WWork& w, int b, int B, const M
 // its interior point (same QP, same verified polish afterwards).
 constexpr int kDeferWarmFailed = 1 << 30;     // flag bit in a deferral-list entry
 template <int SLOTS>
-__device__ inline int mpc_hopper_warp(const QpConst& c, WWork& w, int kcap, int b, int B, const MpcIo& io, int lane) {
-    if (!wbegin(c, w, b, B, io, lane)) return 0;
+__device__ inline int mpc_hopper_warp(const QpConst& c, WWork& w, double* rec, const int32_t* flag, int kcap, int b, int B, const MpcIo& io, int lane) {
+    if (!wfetch(c, w, rec, flag, b, B, io, lane)) return 0;
     AOp A{c.N, 6 * c.N, c.dyn == 3 ? 1 : 0, c.mu, w.stance, w.hinv};
     WInfo info{0, c.condense_flops};
     for (int trial = 0; trial <= c.retries; ++trial) {
@@ -1017,41 +1096,58 @@ inline bool warp_path_applies(const hmpc_config& cfg, int init) {
 
 #ifndef HMPC_HOST_EMUL
 // ------------------------------------------------------------------------------------------------
-// Persistent kernel: WPC independent warps per CTA, hoppers handed out one at a time (the solve times differ).
-// hws: per-warp Hessian workspace [grid * WPC][hstride] doubles.  Deferred hoppers are appended to defer_list.
+// Prep kernel: one warp per hopper, plain grid.  Small per-warp slice and no factor: many warps per SM hide the HBM
+// latency of the loads and the dependent arithmetic of the condensing.
+// ------------------------------------------------------------------------------------------------
+template <int WPC>
+__global__ void __launch_bounds__(32 * WPC)
+mpc_prep_kernel(QpConst c, int B, int wdoubles, double* __restrict__ prep, size_t pstride, int32_t* __restrict__ flags, MpcIo io) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int b = blockIdx.x * WPC + wid;
+    if (b >= B) return;
+    WWork w;
+    wcarve(w, smem + (size_t)wid * wdoubles, c.N, kPrepKcap);
+    wprep(c, w, prep + (size_t)b * pstride, flags + b, b, B, io, lane);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Solve kernel, free-running form: WPC independent warps per CTA, hoppers handed out one at a time (the solve times
+// differ).  Deferred hoppers are appended to defer_list.
 // ------------------------------------------------------------------------------------------------
 template <int SLOTS, int WPC, int MIN_CTAS>
 __global__ void __launch_bounds__(32 * WPC, MIN_CTAS)
-mpc_warp_kernel(QpConst c, int B, int kcap, int wdoubles, double* __restrict__ hws, size_t hstride,
-                int* __restrict__ work_ctr, int* __restrict__ defer_list, int* __restrict__ defer_cnt, MpcIo io) {
+mpc_warp_kernel(QpConst c, int B, int kcap, int wdoubles, double* __restrict__ prep, size_t pstride,
+                const int32_t* __restrict__ flags, int* __restrict__ work_ctr, int* __restrict__ defer_list,
+                int* __restrict__ defer_cnt, MpcIo io) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     WWork w;
     wcarve(w, smem + (size_t)wid * wdoubles, c.N, kcap);
-    w.Hc = hws + ((size_t)blockIdx.x * WPC + wid) * hstride;
     for (;;) {
         int b = 0;
         if (lane == 0) b = atomicAdd(work_ctr, 1);
         b = __shfl_sync(kFullMask, b, 0);
         if (b >= B) break;
-        const int done = mpc_hopper_warp<SLOTS>(c, w, kcap, b, B, io, lane);
+        const int done = mpc_hopper_warp<SLOTS>(c, w, prep + (size_t)b * pstride, flags + b, kcap, b, B, io, lane);
         __syncwarp();
         if (done <= 0 && lane == 0) defer_list[atomicAdd(defer_cnt, 1)] = b | (done < 0 ? kDeferWarmFailed : 0);
     }
 }
 
-// Lock-step variant: the WPC warps of a CTA still own one hopper each, but start every active-set trial together
-// (one CTA barrier per round), so that the warps sharing an SM execute the same code at the same time and share its
-// instruction fetches.  A warp whose hopper is finished fetches and condenses the next one while the others wait.
+// Lock-step form (default): the WPC warps of a CTA still own one hopper each, but start every active-set trial
+// together (one CTA barrier per round), so that the warps sharing an SM execute the same code at the same time and
+// share its instruction fetches.  A warp whose hopper is finished stores it and fetches the next record; since the
+// condensing moved to the prep kernel a round is one trial for every warp.
 template <int SLOTS, int WPC, int MIN_CTAS>
 __global__ void __launch_bounds__(32 * WPC, MIN_CTAS)
-mpc_warp_rounds_kernel(QpConst c, int B, int kcap, int wdoubles, double* __restrict__ hws, size_t hstride,
-                       int* __restrict__ work_ctr, int* __restrict__ defer_list, int* __restrict__ defer_cnt, MpcIo io) {
+mpc_warp_rounds_kernel(QpConst c, int B, int kcap, int wdoubles, double* __restrict__ prep, size_t pstride,
+                       const int32_t* __restrict__ flags, int* __restrict__ work_ctr, int* __restrict__ defer_list,
+                       int* __restrict__ defer_cnt, MpcIo io) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     WWork w;
     wcarve(w, smem + (size_t)wid * wdoubles, c.N, kcap);
-    w.Hc = hws + ((size_t)blockIdx.x * WPC + wid) * hstride;
     AOp A{c.N, 6 * c.N, c.dyn == 3 ? 1 : 0, c.mu, w.stance, w.hinv};
     bool have = false, exhausted = false;
     int b = 0, trial = 0;
@@ -1061,7 +1157,7 @@ mpc_warp_rounds_kernel(QpConst c, int B, int kcap, int wdoubles, double* __restr
             if (lane == 0) b = atomicAdd(work_ctr, 1);
             b = __shfl_sync(kFullMask, b, 0);
             if (b >= B) { exhausted = true; break; }
-            if (wbegin(c, w, b, B, io, lane)) { have = true; trial = 0; info.nfac = 0; info.flops = c.condense_flops; }
+            if (wfetch(c, w, prep + (size_t)b * pstride, flags + b, b, B, io, lane)) { have = true; trial = 0; info.nfac = 0; info.flops = c.condense_flops; }
             else if (lane == 0) defer_list[atomicAdd(defer_cnt, 1)] = b;
         }
         if (__syncthreads_and(!have)) break;

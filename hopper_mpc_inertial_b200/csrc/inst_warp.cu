@@ -51,10 +51,22 @@ cudaError_t warp_regs(int rounds, int wpc, int* regs) {
     return e;
 }
 
+// prep kernel: 4 warps per CTA, one hopper per warp
+constexpr int kPrepWpc = 4;
+int prep_wdoubles(int N) { return (int)warp_work_doubles(N, kPrepKcap); }
+cudaError_t prep_set_smem(int bytes) {
+    return cudaFuncSetAttribute(mpc_prep_kernel<kPrepWpc>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+void prep_launch(const WarpLaunch& l, const QpConst& qc, const MpcIo& io) {
+    const int wd = prep_wdoubles(qc.N);
+    mpc_prep_kernel<kPrepWpc><<<(l.B + kPrepWpc - 1) / kPrepWpc, 32 * kPrepWpc, (size_t)wd * 8 * kPrepWpc, l.stream>>>(
+        qc, l.B, wd, l.prep, l.pstride, l.flags, io);
+}
+
 void warp_launch(const WarpLaunch& l, const QpConst& qc, const MpcIo& io) {
 #define CALL(K, W, M)                                                                                     \
-    K<2, W, M><<<l.grid, 32 * W, l.smem, l.stream>>>(qc, l.B, l.kcap, l.wdoubles, l.hws, l.hstride,       \
-                                                     l.work_ctr, l.defer_list, l.defer_cnt, io)
+    K<2, W, M><<<l.grid, 32 * W, l.smem, l.stream>>>(qc, l.B, l.kcap, l.wdoubles, l.prep, l.pstride,      \
+                                                     l.flags, l.work_ctr, l.defer_list, l.defer_cnt, io)
     HMPC_WARP_DISPATCH(l.rounds, l.wpc, CALL)
 #undef CALL
 }

@@ -144,14 +144,20 @@ int emul_solve(const hmpc_config* cfg, const double* Qd, const double* Rd, const
     g_emul_warp_done = 0;
     if (warp_path_applies(*cfg, init)) {
         const int kcap = warp_kcap(*cfg);
-        std::vector<double> wsm(warp_work_doubles(N, kcap) + 8), hc((size_t)(n + 8) * (n + 8) + 8);
+        std::vector<double> wsm(warp_work_doubles(N, kcap) + 8), psm(warp_work_doubles(N, kPrepKcap) + 8), rec(prep_stride(N) + 8);
         for (int b = 0; b < B; ++b) {
             int done = 0;
+            int32_t flag = -1;
+            // prep kernel (its own per-warp slice), then the solve kernel on the record it left
+            run_warp([&](int lane) {
+                WWork ww;
+                wcarve(ww, psm.data(), N, kPrepKcap);
+                wprep(c, ww, rec.data(), &flag, b, B, io, lane);
+            });
             run_warp([&](int lane) {
                 WWork ww;
                 wcarve(ww, wsm.data(), N, kcap);
-                ww.Hc = hc.data();
-                const int d = mpc_hopper_warp<2>(c, ww, kcap, b, B, io, lane);
+                const int d = mpc_hopper_warp<2>(c, ww, rec.data(), &flag, kcap, b, B, io, lane);
                 if (lane == 0) done = d;
             });
             deferred[b] = done > 0 ? 0 : 1;

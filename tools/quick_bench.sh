@@ -4,7 +4,7 @@ tag=$1; shift
 envs=()
 while [ "$1" != "--" ] && [ $# -gt 0 ]; do envs+=("$1"); shift; done
 shift
-env "${envs[@]}" python bench.py --steps 6 --warmup 5 --no-cpu-baseline --no-extra-configs "$@" > gpurun_out/qb_$tag.json 2> gpurun_out/qb_$tag.err
+env "${envs[@]}" python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extra-configs "$@" > gpurun_out/qb_$tag.json 2> gpurun_out/qb_$tag.err
 python - "$tag" <<'PY'
 import json, sys
 tag = sys.argv[1]
