@@ -26,7 +26,7 @@ HOT_PATH = {"auto": 0, "cta": 1}
 SYMBOLS = [
     "hmpc_default_config", "hmpc_create", "hmpc_destroy", "hmpc_set_stream", "hmpc_synchronize",
     "hmpc_set_gains", "hmpc_convert", "hmpc_rk4", "hmpc_linearize", "hmpc_condense", "hmpc_solve",
-    "hmpc_rollout", "hmpc_solve_stats", "hmpc_set_timing", "hmpc_kernel_times", "hmpc_tick_times", "hmpc_launch_count", "hmpc_hot_path_info", "hmpc_measure_fp64_peak", "hmpc_last_error",
+    "hmpc_rollout", "hmpc_plan_set", "hmpc_plan_tables", "hmpc_rollout_planned", "hmpc_solve_stats", "hmpc_set_timing", "hmpc_kernel_times", "hmpc_tick_times", "hmpc_launch_count", "hmpc_hot_path_info", "hmpc_measure_fp64_peak", "hmpc_last_error",
     "hmpc_abi_version",
 ]
 
@@ -46,6 +46,12 @@ class HmpcConfig(C.Structure):
         ("eps_abs", C.c_double), ("eps_rel", C.c_double), ("rho0", C.c_double), ("sigma", C.c_double),
         ("alpha", C.c_double), ("kkt_eps", C.c_double), ("polish_tol", C.c_double), ("ipm_tol", C.c_double),
     ]
+
+
+class HmpcPlanConfig(C.Structure):
+    """Mirror of ``hmpc_plan_config`` (include/hmpc.h)."""
+    _fields_ = [("N_run", C.c_int32), ("n_sim", C.c_int32), ("max_tick", C.c_int32), ("reserved", C.c_int32),
+                ("t_p", C.c_double), ("curve_psi1", C.c_double), ("curve_psi2", C.c_double)]
 
 
 class HmpcError(RuntimeError):
@@ -80,6 +86,9 @@ def load():
     lib.hmpc_condense.argtypes = [vp] + [vp] * 10
     lib.hmpc_solve.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]
     lib.hmpc_rollout.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]
+    lib.hmpc_plan_set.argtypes = [vp, C.POINTER(HmpcPlanConfig), vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.hmpc_plan_tables.argtypes = [vp, i32, i32, vp, vp, vp, vp]
+    lib.hmpc_rollout_planned.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
     lib.hmpc_solve_stats.argtypes = [vp, vp, vp, vp, vp]
     lib.hmpc_set_timing.argtypes = [vp, i32]
     lib.hmpc_kernel_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]

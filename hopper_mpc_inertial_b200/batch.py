@@ -180,6 +180,48 @@ class BatchMpc:
                                          _ptr(out["status"]), _ptr(out["iters"])))
         return out
 
+    # -- device-side planner (robotrunner.py:166-230 for a batch; include/hmpc.h: hmpc_plan_*) -----------------
+    def plan_set(self, x0, xf, curve, tick_offset, gt):
+        """x0, xf (12,B) float64, curve, tick_offset (B,) int32 device tensors (kept referenced by the handle);
+        ``gt`` = planner.global_tables(...) (host numpy: what depends on the common clock only)."""
+        B = self.B
+        self._chk(x0, (12, B)); self._chk(xf, (12, B))
+        self._chk(curve, (B,), torch.int32); self._chk(tick_offset, (B,), torch.int32)
+        pc = _lib.HmpcPlanConfig()
+        pc.N_run, pc.n_sim, pc.max_tick = int(gt["N_run"]), int(gt["n_sim"]), int(gt["max_tick"])
+        pc.t_p, pc.curve_psi1, pc.curve_psi2 = float(gt["t_p"]), float(gt["curve_psi1"]), float(gt["curve_psi2"])
+        tabs = [np.ascontiguousarray(gt["sin_tab"], dtype=np.float64), np.ascontiguousarray(gt["pf_idx"], dtype=np.int32),
+                np.ascontiguousarray(gt["cmask"], dtype=np.uint64), np.ascontiguousarray(gt["sw_glob"], dtype=np.uint8)]
+        if tabs[0].shape[0] < pc.n_sim or tabs[1].shape[0] < pc.n_sim or tabs[2].shape[0] < pc.max_tick or tabs[3].shape[0] < pc.max_tick:
+            raise ValueError("global tables shorter than n_sim / max_tick")
+        _lib.check(self.lib.hmpc_plan_set(self._h, C.byref(pc), _ptr(x0), _ptr(xf), _ptr(curve), _ptr(tick_offset),
+                                          *[t.ctypes.data_as(C.c_void_p) for t in tabs]))
+        self._plan_keep = (x0, xf, curve, tick_offset)
+        self._plan_max_tick = pc.max_tick
+
+    def plan_tables(self, tick0, n_ticks):
+        """The tables ``rollout`` takes, generated on the device: dict(xref_tab, pf_tab, C_tab, pf_switch)."""
+        N, B = self.N, self.B
+        out = dict(xref_tab=self.empty(n_ticks + N, 12, B), pf_tab=self.empty(n_ticks + N + 1, 3, B),
+                   C_tab=self.empty(max(n_ticks, 1), B, dtype=torch.int64), pf_switch=self.empty(max(n_ticks, 1), B, dtype=torch.uint8))
+        _lib.check(self.lib.hmpc_plan_tables(self._h, int(tick0), int(n_ticks), _ptr(out["xref_tab"]), _ptr(out["pf_tab"]),
+                                             _ptr(out["C_tab"]), _ptr(out["pf_switch"])))
+        return out
+
+    def rollout_planned(self, X, tick0=0, n_ticks=1, init=True, log=False, out=None):
+        """``rollout`` with every tick's reference window generated on the device (no tables)."""
+        B = self.B
+        self._chk(X, (13, B))
+        if out is None:
+            out = dict(status=self.empty(B, dtype=torch.int32), iters=self.empty(B, dtype=torch.int32))
+            if log:
+                out["X_log"] = self.empty(n_ticks + 1, 13, B)
+                out["U_log"] = self.empty(n_ticks, 6, B)
+        _lib.check(self.lib.hmpc_rollout_planned(self._h, _ptr(X), int(tick0), int(n_ticks), 1 if init else 0,
+                                                 _ptr(out.get("X_log")), _ptr(out.get("U_log")),
+                                                 _ptr(out["status"]), _ptr(out["iters"])))
+        return out
+
     def solve_stats(self):
         """Per-hopper (nfac, path, n_infeasible) of the last solve / accumulated over the last rollout."""
         nf = self.empty(self.B, dtype=torch.int32)

@@ -24,6 +24,7 @@
 #include "hmpc_mpc.cuh"
 #include "hmpc_kernel.cuh"
 #include "hmpc_warp.cuh"
+#include "hmpc_plan.cuh"
 
 namespace {
 
@@ -77,11 +78,19 @@ struct hmpc_handle {
     int64_t launches = 0;
     // warp-per-hopper warm path (hmpc_warp.cuh): geometry, per-warp Hessian workspace, deferral list
     bool warp_ok = false;
-    int warp_rounds = 0;
+    int warp_rounds = 0, warp_group = 0;
     int warp_grid = 0, warp_wpc = 1, warp_kcap = 0, warp_wdoubles = 0, warp_per_sm = 0, warp_regs = 0;
     size_t warp_smem = 0, pstride = 0;
     double* prep = nullptr;       // [B][pstride] QP records the prep kernel hands to the solve kernel
     int32_t* prep_flag = nullptr; // [B]
+    // device-side planner (hmpc_plan.cuh): global tables owned by the handle, per-hopper arrays owned by the caller
+    bool plan_ok = false;
+    hmpc::PlanConst plan;
+    double* plan_sin = nullptr; int32_t* plan_pfidx = nullptr; uint64_t* plan_cmask = nullptr; uint8_t* plan_sw = nullptr;
+    double* win_xref = nullptr;   // [N+1][12][B] reference window of the current tick (hmpc_rollout_planned)
+    double* win_pf = nullptr;     // [N+1][3][B]
+    uint64_t* win_C = nullptr;    // [B]
+    uint8_t* win_sw = nullptr;    // [B]
     int* defer_list = nullptr;    // [B] hoppers the warp kernel handed to the CTA kernel this tick
     int32_t* n_defer = nullptr;   // [1] accumulated deferrals of the most recent solve / rollout
 };
@@ -482,6 +491,8 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
                 return fail(HMPC_ERR_ALLOC, std::string("cudaMalloc QP records: ") + cudaGetErrorString(e));
             }
             h->warp_rounds = rounds;
+            h->warp_group = best_wpc;
+            if (const char* ev = getenv("HMPC_WARP_GROUP")) { const int v = atoi(ev); if (v >= 1 && v <= best_wpc) h->warp_group = v; }
             if ((e = hmpc::warp_set_smem(rounds, best_wpc, smem_i)) != cudaSuccess ||
                 (e = hmpc::prep_set_smem(smem_i)) != cudaSuccess) {
                 hmpc_destroy(h);
@@ -504,6 +515,8 @@ int hmpc_destroy(hmpc_handle* h) {
     cudaFree(h->Qd); cudaFree(h->Rd); cudaFree(h->Xsol); cudaFree(h->Usol); cudaFree(h->xin);
     cudaFree(h->U0); cudaFree(h->st_tmp); cudaFree(h->it_tmp); cudaFree(h->ws);
     cudaFree(h->code); cudaFree(h->valid); cudaFree(h->st_tick); cudaFree(h->nfac); cudaFree(h->path); cudaFree(h->ninf); cudaFree(h->flops); cudaFree(h->work_ctr);
+    cudaFree(h->plan_sin); cudaFree(h->plan_pfidx); cudaFree(h->plan_cmask); cudaFree(h->plan_sw);
+    cudaFree(h->win_xref); cudaFree(h->win_pf); cudaFree(h->win_C); cudaFree(h->win_sw);
     cudaFree(h->prep); cudaFree(h->prep_flag); cudaFree(h->defer_list); cudaFree(h->n_defer);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     delete h;
@@ -586,7 +599,7 @@ cudaError_t launch_mpc(hmpc_handle* h, const hmpc::QpConst& qc, const hmpc::MpcI
     if (e != cudaSuccess) return e;
     const bool warp = h->warp_ok && hmpc::warp_path_applies(h->cfg, io.init);
     if (warp) {
-        const hmpc::WarpLaunch wl{h->warp_grid, h->warp_wpc, h->warp_rounds, h->warp_smem, h->stream, h->cfg.batch, h->warp_kcap,
+        const hmpc::WarpLaunch wl{h->warp_grid, h->warp_wpc, h->warp_rounds, h->warp_group, h->warp_smem, h->stream, h->cfg.batch, h->warp_kcap,
                                   h->warp_wdoubles, h->prep, h->pstride, h->prep_flag, h->work_ctr, h->defer_list, h->work_ctr + 1};
         hmpc::prep_launch(wl, qc, io);
         hmpc::warp_launch(wl, qc, io);
@@ -631,14 +644,14 @@ int hmpc_solve(hmpc_handle* h, const double* x_in, const double* x_ref, const do
     return HMPC_OK;
 }
 
-int hmpc_rollout(hmpc_handle* h, double* X, const double* xref_tab, const double* pf_tab,
+namespace {
+// One closed-loop run.  planned = false: rows of the caller's tables; planned = true: every tick writes its own window
+// (N+1 reference / footstep rows, contact mask, switch step) with the device planner first.
+int rollout_impl(hmpc_handle* h, bool planned, double* X, const double* xref_tab, const double* pf_tab,
                  const uint64_t* C_tab, const uint8_t* pf_switch, int tick0, int n_ticks, int init,
                  double* X_log, double* U_log, int32_t* status, int32_t* iters) {
-    if (int rc = check_handle(h)) return rc;
-    if (!X || !xref_tab || !pf_tab || !C_tab || tick0 < 0 || n_ticks < 0)
-        return fail(HMPC_ERR_BAD_ARG, "bad argument");
     const size_t B = (size_t)h->cfg.batch;
-    const int Bi = h->cfg.batch;
+    const int Bi = h->cfg.batch, N = h->cfg.N;
     int32_t* st = status ? status : h->st_tmp;
     int32_t* it = iters ? iters : h->it_tmp;
     HMPC_CUDA(cudaMemsetAsync(st, 0, B * 4, h->stream));
@@ -664,22 +677,104 @@ int hmpc_rollout(hmpc_handle* h, double* X, const double* xref_tab, const double
     ++h->launches;
     if (X_log) HMPC_CUDA(cudaMemcpyAsync(X_log, X, 13 * B * 8, cudaMemcpyDeviceToDevice, h->stream));
     for (int t = 0; t < n_ticks; ++t) {
-        const size_t row = (size_t)(tick0 + t);
-        hmpc::MpcIo io = make_io(h, h->xin, xref_tab + row * 12 * B, pf_tab + row * 3 * B, C_tab + row * B,
-                                 (init && t == 0) ? 1 : 0, 1, nullptr, nullptr, h->U0, st, it);
+        const double *xr, *pf;
+        const uint64_t* Cm;
+        const uint8_t* sw;
+        if (planned) {
+            hmpc::plan_rows_kernel<<<dim3(sim_grid, N + 1), 128, 0, h->stream>>>(h->plan, Bi, tick0 + t, N + 1, N + 1, h->win_xref, h->win_pf);
+            hmpc::plan_masks_kernel<<<dim3(sim_grid, 1), 128, 0, h->stream>>>(h->plan, Bi, tick0 + t, 1, h->win_pf, h->win_C, h->win_sw);
+            h->launches += 2;
+            xr = h->win_xref; pf = h->win_pf; Cm = h->win_C; sw = h->win_sw;
+        } else {
+            const size_t row = (size_t)(tick0 + t);
+            xr = xref_tab + row * 12 * B; pf = pf_tab + row * 3 * B; Cm = C_tab + row * B;
+            sw = pf_switch ? pf_switch + row * B : nullptr;
+        }
+        hmpc::MpcIo io = make_io(h, h->xin, xr, pf, Cm, (init && t == 0) ? 1 : 0, 1, nullptr, nullptr, h->U0, st, it);
         if (h->timing) HMPC_CUDA(cudaEventRecord(h->ev[3 * t], h->stream));
         HMPC_CUDA(launch_mpc(h, qc, io));
         if (h->timing) HMPC_CUDA(cudaEventRecord(h->ev[3 * t + 1], h->stream));
         hmpc::sim_kernel<<<sim_grid, 128, 0, h->stream>>>(
-            sc, Bi, X, h->U0, pf_tab + row * 3 * B, pf_tab + (row + 1) * 3 * B,
-            pf_switch ? pf_switch + row * B : nullptr, h->cfg.mpc_factor, h->xin,
+            sc, Bi, X, h->U0, pf, pf + 3 * B, sw, h->cfg.mpc_factor, h->xin,
             X_log ? X_log + (size_t)(t + 1) * 13 * B : nullptr, U_log ? U_log + (size_t)t * 6 * B : nullptr,
-            nullptr, respawn ? h->st_tick : nullptr, respawn ? xref_tab + (row + 1) * 12 * B : nullptr);
+            nullptr, respawn ? h->st_tick : nullptr, respawn ? xr + 12 * B : nullptr);
         if (h->timing) HMPC_CUDA(cudaEventRecord(h->ev[3 * t + 2], h->stream));
         ++h->launches;
     }
     HMPC_CUDA(cudaGetLastError());
     return HMPC_OK;
+}
+}  // namespace
+
+int hmpc_rollout(hmpc_handle* h, double* X, const double* xref_tab, const double* pf_tab,
+                 const uint64_t* C_tab, const uint8_t* pf_switch, int tick0, int n_ticks, int init,
+                 double* X_log, double* U_log, int32_t* status, int32_t* iters) {
+    if (int rc = check_handle(h)) return rc;
+    if (!X || !xref_tab || !pf_tab || !C_tab || tick0 < 0 || n_ticks < 0)
+        return fail(HMPC_ERR_BAD_ARG, "bad argument");
+    return rollout_impl(h, false, X, xref_tab, pf_tab, C_tab, pf_switch, tick0, n_ticks, init, X_log, U_log, status, iters);
+}
+
+int hmpc_plan_set(hmpc_handle* h, const hmpc_plan_config* pc, const double* x0, const double* xf, const int32_t* curve,
+                  const int32_t* tick_offset, const double* sin_tab_host, const int32_t* pf_idx_host,
+                  const uint64_t* cmask_host, const uint8_t* sw_glob_host) {
+    if (int rc = check_handle(h)) return rc;
+    if (!pc || !x0 || !xf || !curve || !tick_offset || !sin_tab_host || !pf_idx_host || !cmask_host || !sw_glob_host)
+        return fail(HMPC_ERR_BAD_ARG, "null argument");
+    if (pc->N_run < 2 || pc->n_sim < 1 || pc->max_tick < 1 || !(pc->t_p > 0.0)) return fail(HMPC_ERR_BAD_ARG, "bad plan config");
+    const size_t B = (size_t)h->cfg.batch, N = (size_t)h->cfg.N;
+    h->plan_ok = false;
+    cudaFree(h->plan_sin); cudaFree(h->plan_pfidx); cudaFree(h->plan_cmask); cudaFree(h->plan_sw);
+    h->plan_sin = nullptr; h->plan_pfidx = nullptr; h->plan_cmask = nullptr; h->plan_sw = nullptr;
+    cudaError_t e;
+    if ((e = cudaMalloc((void**)&h->plan_sin, (size_t)pc->n_sim * 8)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&h->plan_pfidx, (size_t)pc->n_sim * 4)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&h->plan_cmask, (size_t)pc->max_tick * 8)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&h->plan_sw, (size_t)pc->max_tick)) != cudaSuccess)
+        return fail(HMPC_ERR_ALLOC, std::string("cudaMalloc plan tables: ") + cudaGetErrorString(e));
+    if (!h->win_xref) {
+        if ((e = cudaMalloc((void**)&h->win_xref, (N + 1) * 12 * B * 8)) != cudaSuccess ||
+            (e = cudaMalloc((void**)&h->win_pf, (N + 1) * 3 * B * 8)) != cudaSuccess ||
+            (e = cudaMalloc((void**)&h->win_C, B * 8)) != cudaSuccess || (e = cudaMalloc((void**)&h->win_sw, B)) != cudaSuccess)
+            return fail(HMPC_ERR_ALLOC, std::string("cudaMalloc plan windows: ") + cudaGetErrorString(e));
+    }
+    // the host tables may be pageable: synchronous copies, ordered before later work on the handle's stream
+    HMPC_CUDA(cudaStreamSynchronize(h->stream));
+    HMPC_CUDA(cudaMemcpy(h->plan_sin, sin_tab_host, (size_t)pc->n_sim * 8, cudaMemcpyHostToDevice));
+    HMPC_CUDA(cudaMemcpy(h->plan_pfidx, pf_idx_host, (size_t)pc->n_sim * 4, cudaMemcpyHostToDevice));
+    HMPC_CUDA(cudaMemcpy(h->plan_cmask, cmask_host, (size_t)pc->max_tick * 8, cudaMemcpyHostToDevice));
+    HMPC_CUDA(cudaMemcpy(h->plan_sw, sw_glob_host, (size_t)pc->max_tick, cudaMemcpyHostToDevice));
+    hmpc::PlanConst& P = h->plan;
+    P.N = h->cfg.N; P.mpc_factor = h->cfg.mpc_factor; P.N_run = pc->N_run; P.t_ref = pc->N_run + h->cfg.N * h->cfg.mpc_factor;
+    P.n_sim = pc->n_sim; P.max_tick = pc->max_tick; P.dt = h->cfg.sim_dt; P.amp = pc->t_p / 4; P.T = (double)pc->N_run;
+    P.curve_psi1 = pc->curve_psi1; P.curve_psi2 = pc->curve_psi2;
+    P.sin_tab = h->plan_sin; P.pf_idx = h->plan_pfidx; P.cmask = h->plan_cmask; P.sw_glob = h->plan_sw;
+    P.x0 = x0; P.xf = xf; P.curve = curve; P.off = tick_offset;
+    h->plan_ok = true;
+    return HMPC_OK;
+}
+
+int hmpc_plan_tables(hmpc_handle* h, int tick0, int n_ticks, double* xref_tab, double* pf_tab, uint64_t* C_tab,
+                     uint8_t* pf_switch) {
+    if (int rc = check_handle(h)) return rc;
+    if (!h->plan_ok) return fail(HMPC_ERR_BAD_ARG, "hmpc_plan_set has not been called");
+    if (!xref_tab || !pf_tab || !C_tab || !pf_switch || tick0 < 0 || n_ticks < 0) return fail(HMPC_ERR_BAD_ARG, "bad argument");
+    const int Bi = h->cfg.batch, N = h->cfg.N, grid = (Bi + 127) / 128;
+    const int nrows = n_ticks + N + 1;
+    hmpc::plan_rows_kernel<<<dim3(grid, std::min(nrows, 64)), 128, 0, h->stream>>>(h->plan, Bi, tick0, nrows, nrows - 1, xref_tab, pf_tab);
+    if (n_ticks > 0)
+        hmpc::plan_masks_kernel<<<dim3(grid, std::min(n_ticks, 64)), 128, 0, h->stream>>>(h->plan, Bi, tick0, n_ticks, pf_tab, C_tab, pf_switch);
+    h->launches += 2;
+    HMPC_CUDA(cudaGetLastError());
+    return HMPC_OK;
+}
+
+int hmpc_rollout_planned(hmpc_handle* h, double* X, int tick0, int n_ticks, int init, double* X_log, double* U_log,
+                         int32_t* status, int32_t* iters) {
+    if (int rc = check_handle(h)) return rc;
+    if (!h->plan_ok) return fail(HMPC_ERR_BAD_ARG, "hmpc_plan_set has not been called");
+    if (!X || tick0 < 0 || n_ticks < 0) return fail(HMPC_ERR_BAD_ARG, "bad argument");
+    return rollout_impl(h, true, X, nullptr, nullptr, nullptr, nullptr, tick0, n_ticks, init, X_log, U_log, status, iters);
 }
 
 int hmpc_set_timing(hmpc_handle* h, int enable) {

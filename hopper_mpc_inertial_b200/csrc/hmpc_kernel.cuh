@@ -79,6 +79,7 @@ void mpc_launch_wide_gmem(const MpcLaunch&, const QpConst&, const MpcIo&);
 // the warp-per-hopper warm-path kernel (hmpc_warp.cuh, instantiated in inst_warp.cu)
 struct WarpLaunch {
     int grid, wpc, rounds;  // CTAs, warps per CTA, 1: lock-step rounds kernel
+    int group;              // rounds kernel: warps per lock-step group (named barrier)
     size_t smem;            // dynamic shared memory per CTA
     cudaStream_t stream;
     int B, kcap, wdoubles;

@@ -398,22 +398,27 @@ __device__ inline int wcondense(const QpConst& c, WWork& w, int b, int B, const 
 #pragma unroll
             for (int j = 0; j < 6; ++j)
                 MB[6 * i + j] = M3[3 * i] * Bwb[j] + M3[3 * i + 1] * Bwb[6 + j] + M3[3 * i + 2] * Bwb[12 + j];
+        // compact positions of the two stages' variables (-1: fixed), read once per block
+        int pa[6], pb[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            pa[r] = w.fixed[6 * a + r] ? -1 : (int)w.cpos[6 * a + r];
+            pb[r] = w.fixed[6 * bb + r] ? -1 : (int)w.cpos[6 * bb + r];
+        }
         // fully unrolled so that MB / Bva / Bvb stay in registers; fixed rows and columns are skipped by predicate
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
-            const int vi = 6 * a + r;
-            if (w.fixed[vi]) continue;
-            const int ci = w.cpos[vi];
+            const int ci = pa[r];
+            if (ci < 0) continue;
 #pragma unroll
             for (int cc = 0; cc < 6; ++cc) {
-                const int vj = 6 * bb + cc;
-                if (vi < vj || w.fixed[vj]) continue;        // a == b: the lower half only, mirrored below
+                const int cj = pb[cc];
+                if (cj < 0 || (a == bb && r < cc)) continue;          // a == b: the lower half only, mirrored below
                 double v = Bwa[r] * MB[cc] + Bwa[6 + r] * MB[6 + cc] + Bwa[12 + r] * MB[12 + cc];
                 if (r < 3 && cc < 3)
                     v += Bva[r] * dv[0] * Bvb[cc] + Bva[3 + r] * dv[1] * Bvb[3 + cc] + Bva[6 + r] * dv[2] * Bvb[6 + cc];
                 v *= 2.0;
                 if (a == bb && r == cc && a != N - 1) v += 2.0 * w.Rd[r];
-                const int cj = w.cpos[vj];
                 Hc[ci * nf + cj] = v;
                 Hc[cj * nf + ci] = v;
             }
@@ -1099,8 +1104,11 @@ inline bool warp_path_applies(const hmpc_config& cfg, int init) {
 // Prep kernel: one warp per hopper, plain grid.  Small per-warp slice and no factor: many warps per SM hide the HBM
 // latency of the loads and the dependent arithmetic of the condensing.
 // ------------------------------------------------------------------------------------------------
+#ifndef HMPC_PREP_MINB
+#define HMPC_PREP_MINB 4
+#endif
 template <int WPC>
-__global__ void __launch_bounds__(32 * WPC)
+__global__ void __launch_bounds__(32 * WPC, HMPC_PREP_MINB)
 mpc_prep_kernel(QpConst c, int B, int wdoubles, double* __restrict__ prep, size_t pstride, int32_t* __restrict__ flags, MpcIo io) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1119,7 +1127,7 @@ template <int SLOTS, int WPC, int MIN_CTAS>
 __global__ void __launch_bounds__(32 * WPC, MIN_CTAS)
 mpc_warp_kernel(QpConst c, int B, int kcap, int wdoubles, double* __restrict__ prep, size_t pstride,
                 const int32_t* __restrict__ flags, int* __restrict__ work_ctr, int* __restrict__ defer_list,
-                int* __restrict__ defer_cnt, MpcIo io) {
+                int* __restrict__ defer_cnt, int /*group: rounds kernel only*/, MpcIo io) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     WWork w;
@@ -1139,13 +1147,23 @@ mpc_warp_kernel(QpConst c, int B, int kcap, int wdoubles, double* __restrict__ p
 // together (one CTA barrier per round), so that the warps sharing an SM execute the same code at the same time and
 // share its instruction fetches.  A warp whose hopper is finished stores it and fetches the next record; since the
 // condensing moved to the prep kernel a round is one trial for every warp.
+// AND-reduction of pred over the `nthreads` threads that use named barrier `id` (a lock-step group of warps)
+__device__ __forceinline__ bool group_all(int id, int nthreads, bool pred) {
+    int r;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 q, %3, 0;\n\tbar.red.and.pred p, %1, %2, q;\n\tselp.s32 %0, 1, 0, p;\n\t}"
+                 : "=r"(r) : "r"(id), "r"(nthreads), "r"((int)pred) : "memory");
+    return r != 0;
+}
 template <int SLOTS, int WPC, int MIN_CTAS>
 __global__ void __launch_bounds__(32 * WPC, MIN_CTAS)
 mpc_warp_rounds_kernel(QpConst c, int B, int kcap, int wdoubles, double* __restrict__ prep, size_t pstride,
                        const int32_t* __restrict__ flags, int* __restrict__ work_ctr, int* __restrict__ defer_list,
-                       int* __restrict__ defer_cnt, MpcIo io) {
+                       int* __restrict__ defer_cnt, int gw, MpcIo io) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // lock-step groups of gw warps, each on its own named barrier (the last group takes what is left of the CTA)
+    const int grp = wid / gw, bar_id = 1 + grp;
+    const int bar_threads = 32 * ((grp + 1) * gw <= WPC ? gw : WPC - grp * gw);
     WWork w;
     wcarve(w, smem + (size_t)wid * wdoubles, c.N, kcap);
     AOp A{c.N, 6 * c.N, c.dyn == 3 ? 1 : 0, c.mu, w.stance, w.hinv};
@@ -1160,7 +1178,7 @@ mpc_warp_rounds_kernel(QpConst c, int B, int kcap, int wdoubles, double* __restr
             if (wfetch(c, w, prep + (size_t)b * pstride, flags + b, b, B, io, lane)) { have = true; trial = 0; info.nfac = 0; info.flops = c.condense_flops; }
             else if (lane == 0) defer_list[atomicAdd(defer_cnt, 1)] = b;
         }
-        if (__syncthreads_and(!have)) break;
+        if (group_all(bar_id, bar_threads, !have)) break;
         if (have) {
             const int r = wtrial<SLOTS>(c, w, A, kcap, info, lane);
             if (r > 0) { wfinish(c, w, b, B, io, info, lane); have = false; }

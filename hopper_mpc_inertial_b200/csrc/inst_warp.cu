@@ -66,7 +66,7 @@ void prep_launch(const WarpLaunch& l, const QpConst& qc, const MpcIo& io) {
 void warp_launch(const WarpLaunch& l, const QpConst& qc, const MpcIo& io) {
 #define CALL(K, W, M)                                                                                     \
     K<2, W, M><<<l.grid, 32 * W, l.smem, l.stream>>>(qc, l.B, l.kcap, l.wdoubles, l.prep, l.pstride,      \
-                                                     l.flags, l.work_ctr, l.defer_list, l.defer_cnt, io)
+                                                     l.flags, l.work_ctr, l.defer_list, l.defer_cnt, l.group, io)
     HMPC_WARP_DISPATCH(l.rounds, l.wpc, CALL)
 #undef CALL
 }

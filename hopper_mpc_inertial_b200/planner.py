@@ -114,6 +114,46 @@ def _parabola(y0, y1, y2, T, k):
     return y0 * (1 - s) * (1 - 2 * s) + y1 * 4 * s * (1 - s) + y2 * s * (2 * s - 1)
 
 
+def global_tables(N_run, N, max_tick, mpc_factor=20, dt=1e-3, mpc_dt=0.02, t_start=0.5 * T_P * PHI_SWITCH, t_p=T_P,
+                  phi_switch=PHI_SWITCH, step_adjustment=STEP_ADJUSTMENT, n_sim=None):
+    """Everything in the planner that depends only on the common clock, not on the hopper (the host half of the
+    device-side planner, include/hmpc.h: hmpc_plan_set):
+      sin_tab (n_sim,)   sine of the height wave at simulator step k           (robotrunner.py:210)
+      pf_idx (n_sim,)    simulator index whose reference xy is the footstep in force at step k  (:214-224)
+      Cglob (max_tick,N) contact flags of the MPC window of global tick j, cmask the same as bit masks (:97-102,172-180)
+      sw_glob (max_tick,) simulator step inside tick j at which the footstep index changes (mpc_factor = never)
+    with the reference's running float sums."""
+    t_ref = N_run + N * mpc_factor
+    if n_sim is None:
+        n_sim = t_ref
+    k = np.arange(n_sim).astype(float)
+    sin_tab = np.sin(2 * np.pi / t_p * (k * dt) + np.pi * 3 / 2)
+    cmap = gait_map(n_sim, dt, t_start, 0.0, t_p, phi_switch)
+    edges = np.zeros(n_sim, dtype=np.int64)
+    edges[1:] = (cmap[:-1] == 1) & (cmap[1:] == 0)
+    period = int(round(t_p / dt))
+    idx_pf = np.hstack((0, np.arange(period, t_ref - 1, period) + step_adjustment, t_ref - 1))
+    kf = np.minimum(np.cumsum(edges), idx_pf.shape[0] - 1)
+    pf_idx = idx_pf[kf]                                   # (n_sim,) sim index whose xy is the footstep
+    # switch step inside each tick: pf_ref[20 (off+j) + i] == pf_tab[j] if i < sw else pf_tab[j+1]
+    sw_glob = np.full(max_tick, mpc_factor, dtype=np.uint8)
+    for J in range(max_tick):
+        base = J * mpc_factor
+        if base + mpc_factor > n_sim:
+            break
+        d = pf_idx[base:base + mpc_factor] != pf_idx[base]
+        if d.any():
+            sw_glob[J] = np.argmax(d)
+    # MPC contact windows from the run clock t_k (robotrunner.py:97)
+    tk = run_clock(max_tick * mpc_factor, dt, t_start)
+    Cglob = gait_map(N, mpc_dt, tk[::mpc_factor], 0.0, t_p, phi_switch)      # (max_tick, N)
+    w = (np.uint64(1) << np.arange(N, dtype=np.uint64))
+    cmask = ((Cglob != 0).astype(np.uint64) * w).sum(axis=-1).astype(np.uint64)
+    s45 = np.sin(45 * np.pi / 180)
+    return dict(sin_tab=sin_tab, pf_idx=pf_idx.astype(np.int32), sw_glob=sw_glob, Cglob=Cglob, cmask=cmask,
+                curve_psi1=-0.4 * s45, curve_psi2=-s45, n_sim=n_sim, max_tick=max_tick, N_run=N_run, t_p=t_p)
+
+
 def batch_tables(x0, xf, curve, tick_offset, N_run, n_ticks, N, mpc_factor=20, dt=1e-3, mpc_dt=0.02,
                  t_start=0.5 * T_P * PHI_SWITCH, t_p=T_P, phi_switch=PHI_SWITCH,
                  step_adjustment=STEP_ADJUSTMENT):
@@ -162,36 +202,18 @@ def batch_tables(x0, xf, curve, tick_offset, N_run, n_ticks, N, mpc_factor=20, d
     r0[..., 6:9] = np.where((rows == t_ref - 1)[..., None], xf[None, :, 6:9], vel)   # last row keeps xf's
     xref_tab = r0[:-1]
 
-    # common clocks: 1 kHz contact map from t_start (planner) and the run clock t_k (robotrunner.py:97)
+    # everything that depends only on the common clock
     n_need = min(int(rows.max()) + 1, t_ref)
-    cmap = gait_map(n_need, dt, t_start, 0.0, t_p, phi_switch)
-    edges = np.zeros(n_need, dtype=np.int64)
-    edges[1:] = (cmap[:-1] == 1) & (cmap[1:] == 0)
-    period = int(round(t_p / dt))
-    idx_pf = np.hstack((0, np.arange(period, t_ref - 1, period) + step_adjustment, t_ref - 1))
-    kf = np.minimum(np.cumsum(edges), idx_pf.shape[0] - 1)
-    pf_idx = idx_pf[kf]                                   # (n_need,) sim index whose xy is the footstep
+    gt = global_tables(N_run, N, max_tick, mpc_factor, dt, mpc_dt, t_start, t_p, phi_switch, step_adjustment, n_sim=n_need)
+    pf_idx, sw_glob = gt["pf_idx"], gt["sw_glob"]
     sel = pf_idx[np.minimum(rows, n_need - 1)]            # (R,B)
     pf_tab = np.zeros(rows.shape + (3,))
     pf_tab[..., 0:2] = ref_rows(sel)[..., 0:2]
-    # switch step inside each tick: pf_ref[20 (off+j) + i] == pf_tab[j] if i < sw else pf_tab[j+1]
-    sw_glob = np.full(max_tick, mpc_factor, dtype=np.uint8)
-    for J in range(max_tick):
-        base = J * mpc_factor
-        if base + mpc_factor > n_need:
-            break
-        d = pf_idx[base:base + mpc_factor] != pf_idx[base]
-        if d.any():
-            sw_glob[J] = np.argmax(d)
     jj = off[None, :] + np.arange(n_ticks)[:, None]       # (n_ticks,B) global tick index
     sw = sw_glob[jj]
     sw[np.all(pf_tab[:n_ticks] == pf_tab[1:n_ticks + 1], axis=-1)] = mpc_factor
-    # MPC contact windows from the run clock
-    tk = run_clock(max_tick * mpc_factor, dt, t_start)
-    Cglob = gait_map(N, mpc_dt, tk[::mpc_factor], 0.0, t_p, phi_switch)      # (max_tick, N)
-    C = Cglob[jj]                                                             # (n_ticks,B,N)
-    w = (np.uint64(1) << np.arange(N, dtype=np.uint64))
-    C_tab = ((C != 0).astype(np.uint64) * w).sum(axis=-1).astype(np.uint64)
+    C = gt["Cglob"][jj]                                                       # (n_ticks,B,N)
+    C_tab = gt["cmask"][jj]
     return dict(xref_tab=np.ascontiguousarray(xref_tab.transpose(0, 2, 1)),
                 pf_tab=np.ascontiguousarray(pf_tab.transpose(0, 2, 1)),
                 C_tab=C_tab, pf_switch=sw, C=C)

@@ -37,7 +37,7 @@ def _uniforms(seed, idx0, count, k):
 
 def make_batch(B, idx0=0, seed=1234, N=10, n_ticks=100, N_run=None, mpc_factor=20, dt=1e-3, mpc_dt=0.02,
                randomize_gains=True, phase_ticks=None, t_p=None, z_base=(0.30, 0.45), gain_spread=1.25,
-               dyn="3f", perturb=0.5, speed_range=(0.2, 1.0), curve_prob=0.5):
+               dyn="3f", perturb=0.5, speed_range=(0.2, 1.0), curve_prob=0.5, tables=True):
     """Scenario for hoppers idx0 .. idx0+B-1.
 
     Each hopper gets its own straight or curved reference (goal speed 0.2..1.0 x the reference's
@@ -100,9 +100,19 @@ def make_batch(B, idx0=0, seed=1234, N=10, n_ticks=100, N_run=None, mpc_factor=2
     xfp[:, 0] = p_xy0[:, 0] + dist * np.cos(heading)
     xfp[:, 1] = p_xy0[:, 1] + dist * np.sin(heading)
     xfp[:, 2] = zb
-    tabs = planner.batch_tables(x0p, xfp, curve, off, N_run, n_ticks, N, mpc_factor, dt, mpc_dt,
-                                t_start=0.5 * t_p * planner.PHI_SWITCH, t_p=t_p,
-                                step_adjustment=int(round(planner.STEP_ADJUSTMENT * t_p / planner.T_P)))
+    # tables=False: only the entry row is built here (for the initial states); the device planner generates the
+    # rest (BatchMpc.plan_set / plan_tables / rollout_planned with out["plan"])
+    t_start = 0.5 * t_p * planner.PHI_SWITCH
+    step_adj = int(round(planner.STEP_ADJUSTMENT * t_p / planner.T_P))
+    tabs = planner.batch_tables(x0p, xfp, curve, off, N_run, n_ticks if tables else 0, N, mpc_factor, dt, mpc_dt,
+                                t_start=t_start, t_p=t_p, step_adjustment=step_adj)
+    if not tables:
+        tabs = dict(xref_tab=tabs["xref_tab"][:1])
+    plan = dict(x0=np.ascontiguousarray(x0p.T), xf=np.ascontiguousarray(xfp.T), curve=curve.astype(np.int32),
+                tick_offset=off.astype(np.int32),
+                global_args=dict(N_run=N_run, N=N, max_tick=int(phase_ticks) + n_ticks, mpc_factor=mpc_factor, dt=dt,
+                                 mpc_dt=mpc_dt, t_start=t_start, t_p=t_p, phi_switch=planner.PHI_SWITCH,
+                                 step_adjustment=step_adj))
 
     # initial simulator state: the reference state at the hopper's entry tick plus a perturbation
     r = tabs["xref_tab"][0]                       # (12,B) reference row at the entry tick
@@ -122,6 +132,7 @@ def make_batch(B, idx0=0, seed=1234, N=10, n_ticks=100, N_run=None, mpc_factor=2
     v_b = np.einsum("bji,bj->bi", R, v_w)
     X0 = np.concatenate([pos, q, v_b, w_b], axis=1)
     out = dict(X0=np.ascontiguousarray(X0.T), Qdiag=np.ascontiguousarray((Q_REF[None] * gq).T),
-               Rdiag=np.ascontiguousarray((R_REF[None] * gr).T), curve=curve, tick_offset=off, t_p=t_p, _x0p=x0p, _xfp=xfp)
+               Rdiag=np.ascontiguousarray((R_REF[None] * gr).T), curve=curve, tick_offset=off, t_p=t_p, _x0p=x0p, _xfp=xfp,
+               plan=plan)
     out.update(tabs)
     return out

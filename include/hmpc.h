@@ -189,6 +189,40 @@ int hmpc_rollout(hmpc_handle* h, double* X, const double* xref_tab, const double
                  const uint64_t* C_tab, const uint8_t* pf_switch, int tick0, int n_ticks, int init,
                  double* X_log, double* U_log, int32_t* status, int32_t* iters);
 
+/* ---- the caller side of the path on the device: path_plan_init / path_plan_grab / gait_map ------------------------
+ * (robotrunner.py:166-230).  Every hopper follows the reference's planner between its own start x0 and goal xf,
+ * optionally with the --curve profile, and enters the run at its own tick.  What depends only on the common clock is
+ * passed as small HOST tables (computed with the reference's summation order, planner.global_tables in the Python
+ * package); the per-hopper rows are generated on the device, bit-identical to the numpy planner. */
+typedef struct hmpc_plan_config {
+    int32_t N_run;        /* simulator steps of the run (robotrunner.py:183) */
+    int32_t n_sim;        /* entries of sin_tab / pf_idx (N_run + N * mpc_factor) */
+    int32_t max_tick;     /* entries of cmask / sw_glob */
+    int32_t reserved;
+    double t_p;           /* gait period (robotrunner.py:43); the height wave has amplitude t_p / 4 (:207) */
+    double curve_psi1, curve_psi2;   /* yaw knots of --curve: -0.4 sin(45 deg), -sin(45 deg) (robotrunner.py:197) */
+} hmpc_plan_config;
+
+/* x0, xf [12][B] (device), curve, tick_offset [B] int32 (device); HOST tables: sin_tab [n_sim] = sin(2 pi / t_p (k dt)
+ * + 3 pi / 2) (robotrunner.py:210), pf_idx [n_sim] = simulator index whose reference xy is the footstep in force at
+ * step k (:214-224), cmask [max_tick] = contact mask of global tick j (gait_map on the run clock, :97-102,172-180),
+ * sw_glob [max_tick] = simulator step inside tick j at which the footstep changes (mpc_factor = never).  The
+ * per-hopper arrays are referenced, not copied: they must stay alive while the plan is in use. */
+int hmpc_plan_set(hmpc_handle* h, const hmpc_plan_config* pc, const double* x0, const double* xf, const int32_t* curve,
+                  const int32_t* tick_offset, const double* sin_tab_host, const int32_t* pf_idx_host,
+                  const uint64_t* cmask_host, const uint8_t* sw_glob_host);
+
+/* path_plan_grab for ticks [tick0, tick0 + n_ticks): the tables hmpc_rollout takes, written by the device:
+ * xref_tab [n_ticks+N][12][B], pf_tab [n_ticks+N+1][3][B], C_tab [n_ticks][B], pf_switch [n_ticks][B] (uint8). */
+int hmpc_plan_tables(hmpc_handle* h, int tick0, int n_ticks, double* xref_tab, double* pf_tab, uint64_t* C_tab,
+                     uint8_t* pf_switch);
+
+/* hmpc_rollout without tables: every tick generates its own reference window (N+1 rows), footsteps, contact mask
+ * and switch step on the device just before the solve (about 1.4 KB written per hopper-tick instead of table rows
+ * read).  Same results as hmpc_rollout on the tables of hmpc_plan_tables, bit for bit. */
+int hmpc_rollout_planned(hmpc_handle* h, double* X, int tick0, int n_ticks, int init, double* X_log, double* U_log,
+                         int32_t* status, int32_t* iters);
+
 /* Per-hopper statistics of the most recent hmpc_solve (or accumulated over the most recent
  * hmpc_rollout): nfac [B] = matrix factorisations, path [B] = HMPC_PATH_* of the last solve,
  * n_infeasible [B] = ticks flagged HMPC_PRIMAL_INFEASIBLE (device int32 arrays), flops [B] = algorithmic

@@ -11,7 +11,7 @@ _ROOT = os.path.dirname(os.path.dirname(_HERE))
 _SO = os.path.join(_HERE, "libhmpc_emul.so")
 _DEPS = [os.path.join(_HERE, "emul.cpp"), os.path.join(_HERE, "fake_cuda", "cuda_runtime.h"),
          os.path.join(_ROOT, "include", "hmpc.h")] + \
-        [os.path.join(_ROOT, "hopper_mpc_inertial_b200", "csrc", f) for f in ("hmpc_sim.cuh", "hmpc_qp.cuh", "hmpc_mpc.cuh", "hmpc_warp.cuh")]
+        [os.path.join(_ROOT, "hopper_mpc_inertial_b200", "csrc", f) for f in ("hmpc_sim.cuh", "hmpc_qp.cuh", "hmpc_mpc.cuh", "hmpc_warp.cuh", "hmpc_plan.cuh")]
 _lib = None
 
 
@@ -125,3 +125,22 @@ class EmulMpc:
                              _p(np.ascontiguousarray(pf, float)), int(nsteps), _p(x))
         assert rc == 0
         return (X, x) if convert else X
+
+
+def plan_tables(x0, xf, curve, off, gt, N, n_ticks, tick0=0, mpc_factor=20, dt=1e-3):
+    """The device planner (csrc/hmpc_plan.cuh) run on the host: same outputs as BatchMpc.plan_tables (numpy)."""
+    x0 = np.ascontiguousarray(x0, float); xf = np.ascontiguousarray(xf, float)
+    B = x0.shape[1]
+    curve = np.ascontiguousarray(curve, np.int32); off = np.ascontiguousarray(off, np.int32)
+    sin_tab = np.ascontiguousarray(gt["sin_tab"], float); pf_idx = np.ascontiguousarray(gt["pf_idx"], np.int32)
+    cmask = np.ascontiguousarray(gt["cmask"], np.uint64); sw = np.ascontiguousarray(gt["sw_glob"], np.uint8)
+    xr = np.zeros((n_ticks + N, 12, B)); pf = np.zeros((n_ticks + N + 1, 3, B))
+    Ct = np.zeros((max(n_ticks, 1), B), np.uint64); ps = np.zeros((max(n_ticks, 1), B), np.uint8)
+    lib = load()
+    lib.emul_plan_tables.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                     C.c_double] + [C.c_void_p] * 8 + [C.c_int, C.c_int] + [C.c_void_p] * 4
+    rc = lib.emul_plan_tables(B, int(N), int(mpc_factor), float(dt), int(gt["N_run"]), int(gt["n_sim"]), int(gt["max_tick"]),
+                              float(gt["t_p"]), float(gt["curve_psi1"]), float(gt["curve_psi2"]), _p(x0), _p(xf), _p(curve), _p(off),
+                              _p(sin_tab), _p(pf_idx), _p(cmask), _p(sw), int(tick0), int(n_ticks), _p(xr), _p(pf), _p(Ct), _p(ps))
+    assert rc == 0
+    return dict(xref_tab=xr, pf_tab=pf, C_tab=Ct, pf_switch=ps)

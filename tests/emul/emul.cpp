@@ -15,6 +15,7 @@
 #include "../../hopper_mpc_inertial_b200/csrc/hmpc_sim.cuh"
 #include "../../hopper_mpc_inertial_b200/csrc/hmpc_mpc.cuh"
 #include "../../hopper_mpc_inertial_b200/csrc/hmpc_warp.cuh"
+#include "../../hopper_mpc_inertial_b200/csrc/hmpc_plan.cuh"
 
 using namespace hmpc;
 
@@ -202,6 +203,39 @@ int emul_condense(const hmpc_config* cfg, const double* Qd, const double* Rd, co
         for (int e = 0; e < n * n; ++e) H[(size_t)e * B + b] = sym_at(w.H, n, e / n, e % n);
         for (int i = 0; i < n; ++i) g[(size_t)i * B + b] = w.g[i];
         for (int r = 0; r < m; ++r) { lo[(size_t)r * B + b] = w.lo[r]; hi[(size_t)r * B + b] = w.hi[r]; }
+    }
+    return 0;
+}
+
+// device planner (hmpc_plan.cuh): rows [row0, row0 + nrows) of the MPC-rate tables for every hopper, then the contact
+// masks / switch steps of ticks [row0, row0 + n_ticks); same layout as hmpc_plan_tables.  All pointers HOST memory.
+int emul_plan_tables(int B, int N, int mpc_factor, double dt, int N_run, int n_sim, int max_tick, double t_p, double psi1,
+                     double psi2, const double* x0, const double* xf, const int32_t* curve, const int32_t* off,
+                     const double* sin_tab, const int32_t* pf_idx, const uint64_t* cmask, const uint8_t* sw_glob,
+                     int row0, int n_ticks, double* xref_tab, double* pf_tab, uint64_t* C_tab, uint8_t* pf_switch) {
+    PlanConst P;
+    P.N = N; P.mpc_factor = mpc_factor; P.N_run = N_run; P.t_ref = N_run + N * mpc_factor; P.n_sim = n_sim;
+    P.max_tick = max_tick; P.dt = dt; P.amp = t_p / 4; P.T = (double)N_run; P.curve_psi1 = psi1; P.curve_psi2 = psi2;
+    P.sin_tab = sin_tab; P.pf_idx = pf_idx; P.cmask = cmask; P.sw_glob = sw_glob;
+    P.x0 = x0; P.xf = xf; P.curve = curve; P.off = off;
+    const int nrows = n_ticks + N + 1;
+    for (int b = 0; b < B; ++b) {
+        PlanHopper h;
+        plan_load(P, b, B, h);
+        for (int r = 0; r < nrows; ++r) {
+            double xr[12], pf[3];
+            plan_table_row(P, h, off[b], row0 + r, xr, pf);
+            if (r < nrows - 1) for (int q = 0; q < 12; ++q) xref_tab[((size_t)r * 12 + q) * B + b] = xr[q];
+            for (int q = 0; q < 3; ++q) pf_tab[((size_t)r * 3 + q) * B + b] = pf[q];
+        }
+        for (int t = 0; t < n_ticks; ++t) {       // plan_masks_kernel
+            int j = off[b] + row0 + t;
+            if (j >= max_tick) j = max_tick - 1;
+            C_tab[(size_t)t * B + b] = cmask[j];
+            bool same = true;
+            for (int q = 0; q < 3; ++q) same = same && (pf_tab[((size_t)t * 3 + q) * B + b] == pf_tab[((size_t)(t + 1) * 3 + q) * B + b]);
+            pf_switch[(size_t)t * B + b] = same ? (uint8_t)mpc_factor : sw_glob[j];
+        }
     }
     return 0;
 }

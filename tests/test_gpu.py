@@ -478,6 +478,56 @@ def test_runner_and_cli_dropin():
     assert r3.X_traj.shape == (101, 13)
 
 
+def _plan_set(bm, sc, dev="cuda:0"):
+    from hopper_mpc_inertial_b200 import planner
+    p = sc["plan"]
+    gt = planner.global_tables(**p["global_args"])
+    bm.plan_set(T(p["x0"], dev), T(p["xf"], dev), T(p["curve"], dev), T(p["tick_offset"], dev), gt)
+
+
+@pytest.mark.parametrize("dyn,N", [("3f", 10), ("2f", 10), ("3f", 20)])
+def test_device_planner_tables_are_bit_identical(dyn, N):
+    """path_plan_init / path_plan_grab / gait_map generated on the device (hmpc_plan_tables) against
+    the numpy planner (planner.batch_tables, itself pinned to the reference's path_plan_init by planner.npz)."""
+    B, n_ticks = 777, 37
+    sc = scenarios.make_batch(B, N=N, n_ticks=n_ticks, seed=11, dyn=dyn)
+    bm = mk(B, dyn, N)
+    _plan_set(bm, sc)
+    tabs = bm.plan_tables(0, n_ticks)
+    assert np.array_equal(tabs["xref_tab"].cpu().numpy(), sc["xref_tab"])
+    assert np.array_equal(tabs["pf_tab"].cpu().numpy(), sc["pf_tab"])
+    assert np.array_equal(tabs["C_tab"].cpu().numpy().view(np.uint64), sc["C_tab"])
+    assert np.array_equal(tabs["pf_switch"].cpu().numpy(), sc["pf_switch"])
+    late = bm.plan_tables(9, 3)
+    assert np.array_equal(late["xref_tab"].cpu().numpy(), sc["xref_tab"][9:9 + 3 + N])
+    assert np.array_equal(late["pf_tab"].cpu().numpy(), sc["pf_tab"][9:9 + 3 + N + 1])
+
+
+def test_planned_rollout_equals_table_rollout():
+    """hmpc_rollout_planned (reference window generated per tick on the device, nothing uploaded) reproduces
+    hmpc_rollout on the host-built tables bit for bit, respawns included."""
+    B, N, n_ticks = 512, 10, 24
+    sc = scenarios.make_batch(B, N=N, n_ticks=n_ticks, seed=3, gain_spread=2.0, perturb=1.0)
+    res = []
+    for planned in (False, True):
+        bm = mk(B, "3f", N, on_infeasible="respawn")
+        bm.set_gains(T(sc["Qdiag"]), T(sc["Rdiag"]))
+        X = T(sc["X0"]).clone()
+        if planned:
+            _plan_set(bm, sc)
+            out = bm.rollout_planned(X, 0, 10, True, log=True)
+            out2 = bm.rollout_planned(X, 10, n_ticks - 10, False, log=True)     # resumed mid-run
+        else:
+            args = (T(sc["xref_tab"]), T(sc["pf_tab"]), cb64(sc["C_tab"]), T(sc["pf_switch"]))
+            out = bm.rollout(X, *args, 0, 10, True, log=True)
+            out2 = bm.rollout(X, *args, 10, n_ticks - 10, False, log=True)
+        torch.cuda.synchronize()
+        res.append((X.cpu().numpy(), out["U_log"].cpu().numpy(), out2["U_log"].cpu().numpy(), bm.solve_stats()[2].cpu().numpy()))
+    for a, b in zip(res[0], res[1]):
+        assert np.array_equal(a, b)
+    assert res[0][3].sum() > 0        # the scenario does exercise the respawn path
+
+
 def test_runner_forwards_a_non_default_dt():
     """Runner(dt=2e-3): the device integrates with h = dt and runs mpc_dt / dt = 10 steps per tick
     (robotrunner.py:48,154-164); both loops agree with the oracle loop run with the same constants."""

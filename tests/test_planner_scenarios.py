@@ -91,3 +91,27 @@ def test_shard_ranges_partition_the_batch():
             assert all(rs[i][1] == rs[i + 1][0] for i in range(world - 1))
             sizes = [hi - lo for lo, hi in rs]
             assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.parametrize("dyn,N,n_ticks", [("3f", 10, 40), ("2f", 10, 12), ("3f", 20, 25)])
+def test_device_planner_source_is_bit_identical_to_the_numpy_planner(dyn, N, n_ticks):
+    """csrc/hmpc_plan.cuh compiled for the host (tests/emul) against planner.batch_tables: every generated row,
+    contact mask and switch step equal bit for bit; the GPU run of the same source is checked in
+    tests/test_gpu.py."""
+    from tests import emul
+    sc = scenarios.make_batch(96, N=N, n_ticks=n_ticks, seed=5, dyn=dyn)
+    p = sc["plan"]
+    gt = planner.global_tables(**p["global_args"])
+    out = emul.plan_tables(p["x0"], p["xf"], p["curve"], p["tick_offset"], gt, N, n_ticks)
+    assert np.array_equal(out["xref_tab"], sc["xref_tab"])
+    assert np.array_equal(out["pf_tab"], sc["pf_tab"])
+    assert np.array_equal(out["C_tab"], sc["C_tab"])
+    assert np.array_equal(out["pf_switch"], sc["pf_switch"])
+    # a window starting later in the run (what hmpc_rollout_planned generates per tick)
+    out5 = emul.plan_tables(p["x0"], p["xf"], p["curve"], p["tick_offset"], gt, N, 1, tick0=5)
+    assert np.array_equal(out5["xref_tab"], sc["xref_tab"][5:5 + N + 1])
+    assert np.array_equal(out5["pf_tab"], sc["pf_tab"][5:5 + N + 2])
+    assert np.array_equal(out5["C_tab"][0], sc["C_tab"][5]) and np.array_equal(out5["pf_switch"][0], sc["pf_switch"][5])
+    # tables=False builds the same initial states without the tables
+    sc2 = scenarios.make_batch(96, N=N, n_ticks=n_ticks, seed=5, dyn=dyn, tables=False)
+    assert np.array_equal(sc2["X0"], sc["X0"]) and "pf_tab" not in sc2
