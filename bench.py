@@ -207,6 +207,16 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # product arm
 # ------------------------------------------------------------------------------------------------
+def plan_on_device(bm, sc, dev):
+    """Hand the scenario's per-hopper planner scalars to the device-side planner (hmpc_plan_set)."""
+    import torch
+    from hopper_mpc_inertial_b200 import planner
+    p = sc["plan"]
+    gt = planner.global_tables(**p["global_args"])
+    T = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
+    bm.plan_set(T(p["x0"]), T(p["xf"]), T(p["curve"]), T(p["tick_offset"]), gt)
+
+
 def quick_run(args, dev, local, B, W, K, tag, **scenario_kw):
     """A secondary configuration measured in the same process: W warm-up ticks (first = init), K timed ticks with the
     tables resident in HBM.  Returns a small record (steps/s, ms per tick, solver statistics)."""
@@ -214,12 +224,14 @@ def quick_run(args, dev, local, B, W, K, tag, **scenario_kw):
     from hopper_mpc_inertial_b200 import scenarios
     from hopper_mpc_inertial_b200.batch import BatchMpc
     N = args.horizon
-    sc = scenarios.make_batch(B, N=N, n_ticks=W + K + 1, dyn=args.dyn, **scenario_kw)
+    sc = scenarios.make_batch(B, N=N, n_ticks=W + K + 1, dyn=args.dyn, tables=False, **scenario_kw)
     bm = BatchMpc(B, dyn=args.dyn, N=N, device=local, solver=args.solver, precision=args.precision,
                   on_infeasible="respawn", sqp_sweeps=args.sqp_sweeps, hot_path=args.hot_path)
     T = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
     bm.set_gains(T(sc["Qdiag"]), T(sc["Rdiag"]))
-    xr, pf, Cd, sw = T(sc["xref_tab"]), T(sc["pf_tab"]), T(np.ascontiguousarray(sc["C_tab"]).view(np.int64)), T(sc["pf_switch"])
+    plan_on_device(bm, sc, dev)
+    tabs = bm.plan_tables(0, W + K + 1)               # the MPC-rate tables, generated on the device
+    xr, pf, Cd, sw = tabs["xref_tab"], tabs["pf_tab"], tabs["C_tab"], tabs["pf_switch"]
     X = T(sc["X0"]).clone()
     bm.rollout(X, xr, pf, Cd, sw, 0, W, True)
     torch.cuda.synchronize()
@@ -257,17 +269,19 @@ def run_b200(args):
     n_ticks = W + K
     idx0 = rank * B                                   # contiguous global hopper range of this rank
 
-    # ---- synthetic scenario for this shard (host, numpy), tables resident in HBM ----
-    sc = scenarios.make_batch(B, idx0=idx0, N=N, n_ticks=n_ticks + 1, dyn=args.dyn)
+    # ---- synthetic scenario for this shard: per-hopper scalars on the host (numpy, keyed by the global hopper index),
+    # the MPC-rate tables generated by the device-side planner (bit-identical to planner.batch_tables), resident in HBM;
+    # the e2e leg uploads the same tables from pinned host memory tick by tick ----
+    sc = scenarios.make_batch(B, idx0=idx0, N=N, n_ticks=n_ticks + 1, dyn=args.dyn, tables=False)
     bm = BatchMpc(B, dyn=args.dyn, N=N, device=local, solver=args.solver, precision=args.precision,
                   on_infeasible="respawn", sqp_sweeps=args.sqp_sweeps, hot_path=args.hot_path)
     T = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
     bm.set_gains(T(sc["Qdiag"]), T(sc["Rdiag"]))
-    xref_h = torch.from_numpy(np.ascontiguousarray(sc["xref_tab"])).pin_memory()
-    pf_h = torch.from_numpy(np.ascontiguousarray(sc["pf_tab"])).pin_memory()
-    C_h = torch.from_numpy(np.ascontiguousarray(sc["C_tab"]).view(np.int64)).pin_memory()
-    sw_h = torch.from_numpy(np.ascontiguousarray(sc["pf_switch"])).pin_memory()
-    xref_d, pf_d, C_d, sw_d = xref_h.to(dev), pf_h.to(dev), C_h.to(dev), sw_h.to(dev)
+    plan_on_device(bm, sc, dev)
+    tabs = bm.plan_tables(0, n_ticks + 1)
+    xref_d, pf_d, C_d, sw_d = tabs["xref_tab"], tabs["pf_tab"], tabs["C_tab"], tabs["pf_switch"]
+    pin = lambda t: torch.empty(t.shape, dtype=t.dtype).pin_memory().copy_(t)
+    xref_h, pf_h, C_h, sw_h = pin(xref_d), pin(pf_d), pin(C_d), pin(sw_d)
     X = T(sc["X0"]).clone()
 
     def barrier():
@@ -382,6 +396,40 @@ def run_b200(args):
     barrier()
     e2e_state_matches = bool(torch.equal(X, X_res))      # the two paths computed the same closed loop
     e2e_ms = sharding.max_over_ranks(f0.elapsed_time(f1), dev)
+    # ---- timed region 3 (e2e, device planner): nothing to upload -- every tick generates its own reference window on
+    # the GPU from the per-hopper scalars set once (hmpc_rollout_planned); results are downloaded as above ----
+    bm_e2e = bm
+    bm = BatchMpc(B, dyn=args.dyn, N=N, device=local, solver=args.solver, precision=args.precision, on_infeasible="respawn",
+                  sqp_sweeps=args.sqp_sweeps, hot_path=args.hot_path)
+    bm.set_gains(T(sc["Qdiag"]), T(sc["Rdiag"]))
+    plan_on_device(bm, sc, dev)
+    Xp = T(sc["X0"]).clone()
+    bm.rollout_planned(Xp, 0, W, True)
+
+    def planned_run(t0, count):
+        for rb in res:
+            rb["read"].record(main)
+        for i in range(count):
+            rb = res[i % 2]
+            bm.rollout_planned(Xp, t0 + i, 1, False, log=True, out=o2)
+            main.wait_event(rb["read"])
+            rb["u"].copy_(o2["U_log"][0], non_blocking=True)
+            rb["X"].copy_(Xp, non_blocking=True)
+            rb["st"].copy_(o2["status"], non_blocking=True)
+            rb["done"].record(main)
+            download(rb)
+        main.wait_stream(cs)
+
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    planned_run(W, K)
+    g1.record()
+    barrier()
+    planned_state_matches = bool(torch.equal(Xp, X_res))
+    planned_ms = sharding.max_over_ranks(g0.elapsed_time(g1), dev)
+    bm.close()
+    bm = bm_e2e
     clocks = sampler.stop()
     # NCCL is used for exactly one thing: gathering logged results after the run (here the final states)
     Xg = sharding.gather_hoppers(X, B * world, dst=0)
@@ -415,6 +463,11 @@ def run_b200(args):
     # window 15 N, contact mask 1, previous trajectory (p, yaw of N stages) 4 N read; trajectory 12 (N+1),
     # inputs 6 N + 6 written; warm start: inputs 6 N read, active-set codes 11 N bytes read + written; 4 int32 stats
     bytes_tick = 8 * (12 + 18 + 15 * N + 1 + 4 * N + 12 * (N + 1) + 6 * N + 6 + 6 * N) + 2 * m_rows + 6 * 4
+    if hot["warps_per_sm"]:
+        # phase split: the prep kernel writes and the solve kernel reads the per-hopper QP record (compact Hessian over
+        # the nf = 6N - 3 N_swing non-fixed variables, N_swing ~ N/2, rows padded to 8; gradient; height bounds; x_in)
+        nfree = 6 * N - 3 * (N // 2) if args.dyn == "3f" else 5 * N - 2 * (N // 2)
+        bytes_tick += 2 * 8 * (nfree * ((nfree + 7) // 8 * 8) + 6 * N + N + 12)
     mpc_s = mpc_ms * 1e-3 / max(nt, 1)
     ach_gbs = bytes_tick * B / mpc_s / 1e9
     fp64_peak = bm.measure_fp64_peak()
@@ -427,7 +480,7 @@ def run_b200(args):
     # The solver kernels' arithmetic runs on the FP64 pipe (DMMA.8x8x4 tensor-core tiles + DFMA): that is the roofline
     # the kernel is measured against.  It is far from it: the binding resource is instruction issue / fetch (ncu, see
     # profiles/README.md: issue slots ~25 % busy, top stalls no_instruction / long_scoreboard / wait), not FP64 and not HBM.
-    kname = "mpc_warp_rounds_kernel + mpc_kernel (deferred hoppers)" if hot["warps_per_sm"] else "mpc_kernel"
+    kname = "mpc_prep_kernel + mpc_warp_rounds_kernel + mpc_kernel (deferred hoppers)" if hot["warps_per_sm"] else "mpc_kernel"
     roofline = {"bound": "tensor", "pipe": "FP64 (DMMA.8x8x4 tensor-core tiles and DFMA share the FP64 pipe)", "kernel": kname,
                 "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak if fp64_peak else None,
                 "traffic": (prof["mpc_kernel_dram_bytes_per_hopper"] * B) if "mpc_kernel_dram_bytes_per_hopper" in prof else None,
@@ -436,6 +489,7 @@ def run_b200(args):
                                "tools/micro/dmma.cu measures the same 37 TFLOP/s through DMMA",
                 "algorithmic_flops_per_launch": flops / max(nt, 1), "algorithmic_flops_per_hopper_tick": flops / max(nt, 1) / B,
                 "avg_launch_ms": mpc_s * 1e3, "share_of_step": mpc_ms / ms,
+                "launches_per_step": "prep + solve + deferred-list kernel (timed together with CUDA events around the three launches)",
                 "binding_resource": "instruction issue / fetch, not FP64 and not HBM: see profiles/README.md (ncu issue-slot "
                                     "utilisation and stall breakdown of the same command)"}
     roofline_hbm = {"bound": "hbm", "kernel": kname, "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
@@ -461,6 +515,11 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / K, "same_ticks_as_value": True, "final_state_equals_resident_run": e2e_state_matches,
                     "overlap": "double-buffered: uploads of tick t+1 / downloads of tick t-1 on a copy stream"},
+            "e2e_device_planner": {"value": n_hop * K / (planned_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(d2h),
+                                   "ms_per_step": planned_ms / K, "final_state_equals_resident_run": planned_state_matches,
+                                   "note": "hmpc_rollout_planned: reference rows, footsteps, contact masks generated per tick on the GPU "
+                                           "from per-hopper planner scalars uploaded once (SURVEY 8 row f1); the headline e2e above "
+                                           "uploads host-built windows every tick"},
             "gpu_launches": int(launches_all),
             "clocks": clocks, "log_gather": gather_info,
             "roofline": roofline, "roofline_hbm": roofline_hbm, "p50_qp_solve_us": p50,
