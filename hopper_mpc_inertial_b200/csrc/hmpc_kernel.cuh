@@ -27,6 +27,8 @@ mpc_kernel(QpConst c, int B, int sm_count, double* __restrict__ ws, int* __restr
     LinSys<F> sys{n, 0, 0, reinterpret_cast<F*>(w.Lm), reinterpret_cast<F*>(w.dinv), w.H, w.idx, w.grow};
     // CTAs are dealt to the SMs round-robin, so the CTAs sharing an SM differ in blockIdx.x / #SMs
     sys.solver_warp = blockIdx.x / sm_count;
+    // horizons beyond N = 10 (256-thread CTAs): tensor-core tiles, all warps of the CTA (LinSys::factor_tiled)
+    sys.tiled = (THREADS == 256 && sizeof(F) == 8 && tiled_factor_applies(c.N)) ? 1 : 0;
     // dynamic distribution of hoppers over the persistent CTAs (solve times differ: warm active-set path
     // vs interior-point path); results do not depend on the order
     // list mode: only the hoppers the warp kernel deferred (hmpc_warp.cuh), in any order

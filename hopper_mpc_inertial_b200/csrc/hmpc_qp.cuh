@@ -31,6 +31,7 @@
 #include <stdint.h>
 
 #include "hmpc_sim.cuh"   // mat3_vec / mat3T_vec
+#include "hmpc_tile.cuh"  // FP64 tensor-core tile primitives
 
 namespace hmpc {
 
@@ -106,17 +107,28 @@ __host__ __device__ inline int kkt_max(int N) { return 7 * N + 2; }
 // i >= j, of an order-k matrix sits at tri_off(j, k) + (i - j).
 __host__ __device__ inline int tri_off(int j, int k) { return j * k - (j * (j - 1)) / 2; }
 // fsize: bytes per factor entry (8: FP64 factor, 4: FP32 factor)
+// Horizons beyond the 128-thread kernels (6N > 64) keep the FP64 factor as a lower block triangle of 8x8 tiles for the
+// tensor-core path (LinSys::factor_tiled): room for both layouts.
+__host__ __device__ inline bool tiled_factor_applies(int N, int fsize = 8) { return 6 * N > 64 && fsize == 8; }
+__host__ __device__ inline size_t tiled_factor_doubles(int N) {
+    const size_t nt = ((size_t)kkt_max(N) + 7) / 8;
+    return (nt * (nt + 1) / 2) * 64;
+}
 __host__ __device__ inline size_t mat_doubles(int N, int fsize = 8) {
     const size_t n = 6 * (size_t)N, kk = (size_t)kkt_max(N);
-    return n * (n + 1) / 2 + (kk * (kk + 1) / 2 * (size_t)fsize + 7) / 8;
+    size_t f = (kk * (kk + 1) / 2 * (size_t)fsize + 7) / 8;
+    if (tiled_factor_applies(N, fsize) && tiled_factor_doubles(N) > f) f = tiled_factor_doubles(N);
+    return n * (n + 1) / 2 + f;
 }
+// compact-system vectors: padded to whole tiles for the tiled path
+__host__ __device__ inline int kkt_vec(int N) { return kkt_max(N) + (6 * N > 64 ? 8 : 0); }
 __host__ __device__ inline size_t work_vec_doubles(int N) {
     const int n = 6 * N, m = 11 * N;
     size_t d = 0;
     // linearisation (cfree, gp, pfw, Qd, Rd, PC, PS alias the last three m-vectors: dead once condense() returns)
     d += 2 * N + 9 * N + 18 * N + 12 + 12 * (N + 1) + N;
     d += n + 2 * m;           // g lo hi
-    d += 3 * n + (N > 14 ? N - 14 : 0) + 4 * kkt_max(N);   // x xp tmp(+pad) | xt rhs sc dinv
+    d += 3 * n + (N > 14 ? N - 14 : 0) + 4 * kkt_vec(N);   // x xp tmp(+pad) | xt rhs sc dinv
     d += kNumMVec * m;
     d += 48;                  // red
     d += (n + kkt_max(N) + 4 + 1) / 2;          // int32: idx grow cnt
@@ -135,7 +147,7 @@ __device__ inline void carve(Work& w, double* base, int N) {
     w.g = take(n); w.lo = take(m); w.hi = take(m);
     // tmp | xt | rhs | sc are contiguous: together they are the 4-column panel scratch of LinSys::factor
     w.x = take(n); w.xp = take(n); w.tmp = take(n + (N > 14 ? N - 14 : 0));   // pad: 4 (kkt_max - 4) panel entries
-    w.xt = take(kk); w.rhs = take(kk); w.sc = take(kk); w.dinv = take(kk);
+    { const int kv = kkt_vec(N); w.xt = take(kv); w.rhs = take(kv); w.sc = take(kv); w.dinv = take(kv); }
     for (int i = 0; i < kNumMVec; ++i) w.mv[i] = take(m);
     // condense-only scratch on top of the solvers' last three m-vectors: 12(N+1) + 4N + 3N + 18 + 2(N+1) <= 33N
     w.cfree = w.mv[kNumMVec - 3]; w.gp = w.cfree + 12 * (N + 1); w.pfw = w.gp + 4 * N;
@@ -568,6 +580,7 @@ struct LinSys {
     const int *idx, *grow;
     double flops = 0.0;   // algorithmic FLOPs of factor/solve since the last reset (same value in all threads)
     int solver_warp = 0;  // which warp of the CTA runs the substitutions
+    int tiled = 0;        // 1: FP64 tensor-core tiles, all warps of the CTA (factor_tiled / solve_tiled; wide kernels)
 
     __device__ inline double entry(const AOp& A, const double* wts, double dadd, double eps, int i, int j) const {
         if (i < nF) {   // i >= j
@@ -589,6 +602,9 @@ struct LinSys {
     // Returns nonzero (same value in all threads) when a pivot has the wrong sign or is not finite.
     // P: scratch of at least 4 (nk - 4) doubles (the pre-scaled panel, see below).
     __device__ inline int factor(const AOp& A, const double* wts, double dadd, double eps, double* scratch) {
+#ifndef HMPC_HOST_EMUL
+        if (sizeof(F) == 8 && tiled) return factor_tiled(A, wts, dadd, eps, scratch);
+#endif
         PH_T0(ph_f);
         F* P = reinterpret_cast<F*>(scratch);
         const int tid = threadIdx.x, T = blockDim.x, nk = nF + ng;
@@ -677,6 +693,9 @@ struct LinSys {
     // (lane, lane+32, lane+64) in registers and the pivot entry is broadcast with a shuffle, so the dependency
     // chain per column is one shuffle and one FMA.
     __device__ inline void solve(const double* b, double* out, double* scratch) {
+#ifndef HMPC_HOST_EMUL
+        if (sizeof(F) == 8 && tiled) { solve_tiled(b, out, scratch); return; }
+#endif
         F* sc = reinterpret_cast<F*>(scratch);
         const int tid = threadIdx.x, T = blockDim.x, nk = nF + ng;
         const int LS = T < 32 ? T : 32;
@@ -744,6 +763,194 @@ struct LinSys {
         __syncthreads();
         PH_ADD(5, ph_s);
     }
+
+#ifndef HMPC_HOST_EMUL
+    // --------------------------------------------------------------------------------------------
+    // Tiled path (horizons N >= 11, 256-thread CTA): the same signed Cholesky  K = V S V'  as the warp kernel
+    // (hmpc_warp.cuh: wfactor), in 8x8 tiles through the FP64 tensor core (mma.sync.m8n8k4.f64), with the tile rows of
+    // a block column dealt to the warps of the CTA.  Storage: lower block triangle of row-major 8x8 tiles
+    // (tile_off), diagonal tiles hold W_J = V(J,J)^-1.  Left-looking per block column J:
+    //   phase A  every warp accumulates  C(I,J) = K(I,J) - sum_{K<J} V(I,K) S_K V(J,K)'  for its tiles I in
+    //            registers; the owner of I == J factorises the diagonal tile and publishes W_J       | barrier
+    //   phase B  V(I,J) = C(I,J) W_J' S_J  from the registers                                         | barrier
+    // so a factorisation of order nk costs 2 nk/8 CTA barriers instead of one per pivot column, the summation runs
+    // on the tensor core, and nothing is read-modify-written in the (L2-resident) factor storage.
+    // --------------------------------------------------------------------------------------------
+    static constexpr int kMaxOwn = 8;     // tile rows per warp and block column: nt <= 64 with 8 warps
+    __device__ inline int factor_tiled(const AOp& A, const double* wts, double dadd, double eps, double* scratch) {
+        PH_T0(ph_f);
+        const int tid = threadIdx.x, T = blockDim.x, nk = nF + ng, nt = (nk + 7) >> 3;
+        const int lane = tid & 31, wid = tid >> 5, nw = T >> 5;
+        const int g = lane >> 2, t = lane & 3, fo = 8 * g + 2 * t;
+        double* L = reinterpret_cast<double*>(Lm);
+        flops += flops_factor(nk);
+        // ---- assemble K tile by tile (a warp per tile, a lane per entry pair) ----
+        {
+            const int ntile = nt * (nt + 1) / 2;
+            for (int tl = wid; tl < ntile; tl += nw) {
+                int I = (int)((sqrtf(8.0f * (float)tl + 1.0f) - 1.0f) * 0.5f);
+                while ((I + 1) * (I + 2) / 2 <= tl) ++I;
+                while (I * (I + 1) / 2 > tl) --I;
+                const int J = tl - I * (I + 1) / 2;
+                const int i = 8 * I + g, j = 8 * J + 2 * t;
+                double k0 = 0.0, k1 = 0.0;
+                if (i < nk) {
+                    if (j <= i) k0 = entry(A, wts, dadd, eps, i, j);
+                    if (j + 1 <= i) k1 = entry(A, wts, dadd, eps, i, j + 1);
+                } else {                                       // past the end: unit pivots (negative block)
+                    if (j == i) k0 = -1.0;
+                    if (j + 1 == i) k1 = -1.0;
+                }
+                st2(L + tl * 64 + fo, k0, k1);
+            }
+        }
+        __syncthreads();
+        const int Jb = nF >> 3;                                          // tile of the first active-row pivot
+        const bool mixed = (nF & 7) != 0;                                // ... which also holds variables
+        const double mv0 = (8 * Jb + 2 * t < nF) ? 1.0 : 0.0, mv1 = (8 * Jb + 2 * t + 1 < nF) ? 1.0 : 0.0;
+        const bool ondiag0 = (2 * t == g), ondiag1 = (2 * t + 1 == g);
+        int bad = 0;
+#pragma unroll 1
+        for (int J = 0; J < nt; ++J) {
+            const int j0 = 8 * J + 2 * t;
+            const double s0 = (j0 < nF) ? 1.0 : -1.0, s1 = (j0 + 1 < nF) ? 1.0 : -1.0;
+            const double* Lj = L + tile_off(J, 0) + fo;                  // tiles (J, K), K = 0 .. J
+            const bool scaled = (J > Jb) || (J == Jb && !mixed);        // diagonal regularised here (else inside wdiag8)
+            const int kplain = J < Jb ? J : Jb;
+            double c0[kMaxOwn], c1[kMaxOwn];
+            // ---- phase A ----
+#pragma unroll
+            for (int q = 0; q < kMaxOwn; ++q) {
+                const int I = J + wid + q * nw;
+                c0[q] = 0.0; c1[q] = 0.0;
+                if (I < nt) {
+                    const double* Li = L + tile_off(I, 0) + fo;          // tiles (I, K)
+                    const int i = 8 * I + g;
+                    d2 kk = ld2(Li + 64 * J);                            // K(I, J) as assembled
+                    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;      // two accumulator chains
+                    int K = 0;
+#pragma unroll 2
+                    for (; K + 1 < kplain; K += 2) {                     // variables: +
+                        tile_mac(a0, a1, ld2(Li + 64 * K), ld2(Lj + 64 * K));
+                        tile_mac(b0, b1, ld2(Li + 64 * K + 64), ld2(Lj + 64 * K + 64));
+                    }
+                    if (K < kplain) tile_mac(a0, a1, ld2(Li + 64 * K), ld2(Lj + 64 * K));
+                    a0 += b0; a1 += b1;
+                    if (J > Jb && mixed) {                               // variable columns of the mixed tile
+                        const d2 b = ld2(Lj + 64 * Jb);
+                        tile_mac(a0, a1, ld2(Li + 64 * Jb), d2{b.x * mv0, b.y * mv1});
+                    }
+                    if (scaled && I == J) {                              // the Schur complement's diagonal
+                        if (ondiag0) a0 *= 1.0 + eps;
+                        if (ondiag1) a1 *= 1.0 + eps;
+                    }
+                    if (J > Jb) {
+                        if (mixed) {                                     // row columns of the mixed tile: -
+                            const d2 b = ld2(Lj + 64 * Jb);
+                            tile_mac(a0, a1, ld2(Li + 64 * Jb), d2{b.x * (mv0 - 1.0), b.y * (mv1 - 1.0)});
+                        }
+                        double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
+                        int K2 = Jb + (mixed ? 1 : 0);
+#pragma unroll 2
+                        for (; K2 + 1 < J; K2 += 2) {                    // active-row columns: -
+                            tile_mac(e0, e1, ld2(Li + 64 * K2), ld2(Lj + 64 * K2));
+                            tile_mac(f0, f1, ld2(Li + 64 * K2 + 64), ld2(Lj + 64 * K2 + 64));
+                        }
+                        if (K2 < J) tile_mac(e0, e1, ld2(Li + 64 * K2), ld2(Lj + 64 * K2));
+                        a0 -= e0 + f0; a1 -= e1 + f1;
+                    }
+                    if (I == J && scaled && i >= nF && i < nk) {
+                        if (ondiag0) kk.x *= 1.0 + eps;
+                        if (ondiag1) kk.y *= 1.0 + eps;
+                    }
+                    c0[q] = kk.x - a0; c1[q] = kk.y - a1;
+                }
+            }
+            if (wid == 0) {                                              // owner of the diagonal tile (q = 0)
+                double* dsc = scratch;                                   // one tile of shared memory
+                st2(dsc + fo, c0[0], c1[0]);
+                __syncwarp();
+                double* Wt = L + tile_off(J, J);
+                const int jrel = nF - 8 * J;                             // first active-row pivot inside this tile
+                if (jrel > 0 && jrel < 8) bad |= wdiag8<true>(dsc, Wt, jrel, 1.0, eps, lane);
+                else bad |= wdiag8<false>(dsc, Wt, 0, jrel >= 8 ? 1.0 : -1.0, eps, lane);
+            }
+            __syncthreads();
+            // ---- phase B ----
+            const d2 bw = ld2(L + tile_off(J, J) + fo);
+#pragma unroll
+            for (int q = 0; q < kMaxOwn; ++q) {
+                const int I = J + wid + q * nw;
+                if (I < nt && I > J) {
+                    double d0 = 0.0, d1 = 0.0;
+                    tile_mac(d0, d1, d2{c0[q], c1[q]}, bw);
+                    st2(L + tile_off(I, J) + fo, s0 * d0, s1 * d1);
+                }
+            }
+            __syncthreads();
+        }
+        bad = __syncthreads_or(bad);
+        PH_ADD(4, ph_f);
+        return bad;
+    }
+
+    // Substitutions with the tiled factor, column-oriented so that every step is a batch of independent
+    // tile-times-vector products dealt to the warps:
+    //   forward   z_J = W_J b_J,            b_I -= V(I,J) z_J   (I > J)
+    //   backward  x_I = W_I' (S z)_I,       z_J -= V(I,J)' x_I  (J < I)
+    // scratch: at least 8 ceil(nk / 8) doubles of shared memory.  Ends with a __syncthreads().
+    __device__ inline void solve_tiled(const double* b, double* out, double* scratch) {
+        PH_T0(ph_s);
+        const int tid = threadIdx.x, T = blockDim.x, nk = nF + ng, nt = (nk + 7) >> 3;
+        const int lane = tid & 31, wid = tid >> 5, nw = T >> 5;
+        const int g = lane >> 2, t = lane & 3, fo = 8 * g + 2 * t;
+        const double* L = reinterpret_cast<const double*>(Lm);
+        double* v = scratch;
+        flops += flops_solve(nk);
+        __syncthreads();
+        for (int i = tid; i < 8 * nt; i += T) v[i] = i < nk ? b[i] : 0.0;
+        __syncthreads();
+#pragma unroll 1
+        for (int J = 0; J < nt; ++J) {
+            if (wid == 0) {
+                double z0 = 0.0, z1 = 0.0;
+                tile_mac(z0, z1, ld2(L + tile_off(J, J) + fo), vec_b(v + 8 * J, lane));
+                __syncwarp();
+                if (t == 0) v[8 * J + g] = z0;
+            }
+            __syncthreads();
+            for (int I = J + 1 + wid; I < nt; I += nw) {
+                double a0 = 0.0, a1 = 0.0;
+                tile_mac(a0, a1, ld2(L + tile_off(I, J) + fo), vec_b(v + 8 * J, lane));
+                if (t == 0) v[8 * I + g] -= a0;
+            }
+            __syncthreads();
+        }
+        for (int i = nF + tid; i < 8 * nt; i += T) v[i] = -v[i];          // S z
+        __syncthreads();
+#pragma unroll 1
+        for (int I = nt - 1; I >= 0; --I) {
+            if (wid == 0) {
+                const double* Wt = L + tile_off(I, I);
+                double x0 = 0.0, x1 = 0.0;
+                tile_mac(x0, x1, d2{Wt[8 * (2 * t) + g], Wt[8 * (2 * t + 1) + g]}, vec_b(v + 8 * I, lane));
+                __syncwarp();
+                if (t == 0) v[8 * I + g] = x0;
+            }
+            __syncthreads();
+            for (int J = wid; J < I; J += nw) {
+                const double* Tt = L + tile_off(I, J);                    // A = V(I,J)': A[g][2t + h] = T[2t + h][g]
+                double a0 = 0.0, a1 = 0.0;
+                tile_mac(a0, a1, d2{Tt[8 * (2 * t) + g], Tt[8 * (2 * t + 1) + g]}, vec_b(v + 8 * I, lane));
+                if (t == 0) v[8 * J + g] -= a0;
+            }
+            __syncthreads();
+        }
+        for (int i = tid; i < nk; i += T) out[i] = v[i];
+        __syncthreads();
+        PH_ADD(5, ph_s);
+    }
+#endif  // HMPC_HOST_EMUL
 };
 
 // out = H x for the symmetric H of order n (packed lower triangle); every row is split into two halves

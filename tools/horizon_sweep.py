@@ -11,7 +11,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from hopper_mpc_inertial_b200 import scenarios          # noqa: E402
+from hopper_mpc_inertial_b200 import planner, scenarios          # noqa: E402
 from hopper_mpc_inertial_b200.batch import BatchMpc     # noqa: E402
 
 
@@ -19,12 +19,15 @@ def T(a, dev):
     return torch.as_tensor(np.ascontiguousarray(a), device=dev)
 
 
-def run(dyn, N, B, warm=3, ticks=8):
-    sc = scenarios.make_batch(B, N=N, n_ticks=warm + ticks, dyn=dyn)
-    bm = BatchMpc(B, dyn=dyn, N=N, on_infeasible="respawn")
+def run(dyn, N, B, warm=3, ticks=8, precision="fp64"):
+    sc = scenarios.make_batch(B, N=N, n_ticks=warm + ticks, dyn=dyn, tables=False)
+    bm = BatchMpc(B, dyn=dyn, N=N, on_infeasible="respawn", precision=precision)
     dev = bm.device
     bm.set_gains(T(sc["Qdiag"], dev), T(sc["Rdiag"], dev))
-    args = (T(sc["xref_tab"], dev), T(sc["pf_tab"], dev), T(sc["C_tab"].view(np.int64), dev), T(sc["pf_switch"], dev))
+    p = sc["plan"]                                       # tables from the device-side planner
+    bm.plan_set(T(p["x0"], dev), T(p["xf"], dev), T(p["curve"], dev), T(p["tick_offset"], dev), planner.global_tables(**p["global_args"]))
+    tabs = bm.plan_tables(0, warm + ticks)
+    args = (tabs["xref_tab"], tabs["pf_tab"], tabs["C_tab"], tabs["pf_switch"])
     X = T(sc["X0"], dev).clone()
     bm.rollout(X, *args, 0, warm, True)
     torch.cuda.synchronize()
@@ -55,11 +58,11 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--horizons", type=int, nargs="+", default=[10, 20, 40])
+    ap.add_argument("--dyns", nargs="+", default=["3f", "2f"])
     a = ap.parse_args()
     rows = []
     for N in a.horizons:
-        for dyn in ("3f", "2f"):
-            B = a.batch if N <= 20 else min(a.batch, 8192)      # N = 40 runs from the L2-resident workspace
-            r = run(dyn, N, B)
+        for dyn in a.dyns:
+            r = run(dyn, N, a.batch)
             rows.append(r)
             print(json.dumps(r), flush=True)
