@@ -776,7 +776,71 @@ struct LinSys {
     // so a factorisation of order nk costs 2 nk/8 CTA barriers instead of one per pivot column, the summation runs
     // on the tensor core, and nothing is read-modify-written in the (L2-resident) factor storage.
     // --------------------------------------------------------------------------------------------
-    static constexpr int kMaxOwn = 8;     // tile rows per warp and block column: nt <= 64 with 8 warps
+    // K(i, j) of the compact system for the tile position of this lane; i < j (above the diagonal) is never used
+    __device__ __forceinline__ double entry_or_pad(const AOp& A, const double* wts, double dadd, double eps, int nk, int i, int j) const {
+        if (i >= nk) return i == j ? -1.0 : 0.0;              // past the end: unit pivots (negative block)
+        if (j > i) return 0.0;
+        return entry(A, wts, dadd, eps, i, j);
+    }
+    // C(I,J) = K(I,J) - sum_{K<J} V(I,K) S_K V(J,K)'  for one tile, by one warp.  The operand tiles come from the
+    // (L2-resident) factor storage: kBatch tile pairs are requested before the first product so that the latency of a
+    // whole batch overlaps (measured: one pair at a time left the tensor core waiting 150-190 cycles per product).
+    // Variable columns accumulate in (av0, av1), active-row columns in (ar0, ar1); the regularisation of the Schur
+    // complement's diagonal sits between the two.
+    static constexpr int kBatch = 6;
+    __device__ __forceinline__ void tile_column(const AOp& A, const double* wts, double dadd, double eps, const double* L,
+                                                int nk, int I, int J, int lane, double& c0, double& c1) const {
+        const int g = lane >> 2, t = lane & 3, fo = 8 * g + 2 * t;
+        const int Jb = nF >> 3;
+        const bool mixed = (nF & 7) != 0;
+        const int i = 8 * I + g, j0 = 8 * J + 2 * t;
+        // K(I, J) first: its gather is in flight while the products run
+        double k0, k1;
+        if (!wts && 8 * I + 8 <= nF) {                       // variables x variables, no weights: branch-free gather
+            const int vi = idx[i], va = idx[j0], vb = idx[j0 + 1];
+            const int lo0 = vi < va ? vi : va, hi0 = vi < va ? va : vi, lo1 = vi < vb ? vi : vb, hi1 = vi < vb ? vb : vi;
+            k0 = H[tri_off(lo0, n) + (hi0 - lo0)];
+            k1 = H[tri_off(lo1, n) + (hi1 - lo1)];
+            if (i == j0) k0 += dadd;
+            if (i == j0 + 1) k1 += dadd;
+        } else {
+            k0 = entry_or_pad(A, wts, dadd, eps, nk, i, j0);
+            k1 = entry_or_pad(A, wts, dadd, eps, nk, i, j0 + 1);
+        }
+        const double* Li = L + tile_off(I, 0) + fo;
+        const double* Lj = L + tile_off(J, 0) + fo;
+        const double mv0 = (8 * Jb + 2 * t < nF) ? 1.0 : 0.0, mv1 = (8 * Jb + 2 * t + 1 < nF) ? 1.0 : 0.0;
+        double av0 = 0.0, av1 = 0.0, ar0 = 0.0, ar1 = 0.0;
+#pragma unroll 1
+        for (int K0 = 0; K0 < J; K0 += kBatch) {
+            d2 a[kBatch], b[kBatch];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const int K = K0 + u < J ? K0 + u : J - 1;   // clamped: a harmless repeat load past the end
+                a[u] = ld2(Li + 64 * K);
+                b[u] = ld2(Lj + 64 * K);
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const int K = K0 + u;
+                if (K >= J) break;
+                if (K < Jb) tile_mac(av0, av1, a[u], b[u]);
+                else if (K > Jb || !mixed) tile_mac(ar0, ar1, a[u], b[u]);
+                else {                                       // the tile that holds both kinds of columns
+                    tile_mac(av0, av1, a[u], d2{b[u].x * mv0, b[u].y * mv1});
+                    tile_mac(ar0, ar1, a[u], d2{b[u].x * (1.0 - mv0), b[u].y * (1.0 - mv1)});
+                }
+            }
+        }
+        const bool scaled = (J > Jb) || (J == Jb && !mixed);  // diagonal regularised here (else inside wdiag8)
+        if (I == J && scaled) {
+            const bool ondiag0 = (2 * t == g), ondiag1 = (2 * t + 1 == g);
+            if (ondiag0) { av0 *= 1.0 + eps; if (i >= nF && i < nk) k0 *= 1.0 + eps; }
+            if (ondiag1) { av1 *= 1.0 + eps; if (i >= nF && i < nk) k1 *= 1.0 + eps; }
+        }
+        c0 = k0 - (av0 - ar0);
+        c1 = k1 - (av1 - ar1);
+    }
     __device__ inline int factor_tiled(const AOp& A, const double* wts, double dadd, double eps, double* scratch) {
         PH_T0(ph_f);
         const int tid = threadIdx.x, T = blockDim.x, nk = nF + ng, nt = (nk + 7) >> 3;
@@ -784,108 +848,42 @@ struct LinSys {
         const int g = lane >> 2, t = lane & 3, fo = 8 * g + 2 * t;
         double* L = reinterpret_cast<double*>(Lm);
         flops += flops_factor(nk);
-        // ---- assemble K tile by tile (a warp per tile, a lane per entry pair) ----
-        {
-            const int ntile = nt * (nt + 1) / 2;
-            for (int tl = wid; tl < ntile; tl += nw) {
-                int I = (int)((sqrtf(8.0f * (float)tl + 1.0f) - 1.0f) * 0.5f);
-                while ((I + 1) * (I + 2) / 2 <= tl) ++I;
-                while (I * (I + 1) / 2 > tl) --I;
-                const int J = tl - I * (I + 1) / 2;
-                const int i = 8 * I + g, j = 8 * J + 2 * t;
-                double k0 = 0.0, k1 = 0.0;
-                if (i < nk) {
-                    if (j <= i) k0 = entry(A, wts, dadd, eps, i, j);
-                    if (j + 1 <= i) k1 = entry(A, wts, dadd, eps, i, j + 1);
-                } else {                                       // past the end: unit pivots (negative block)
-                    if (j == i) k0 = -1.0;
-                    if (j + 1 == i) k1 = -1.0;
-                }
-                st2(L + tl * 64 + fo, k0, k1);
-            }
-        }
-        __syncthreads();
-        const int Jb = nF >> 3;                                          // tile of the first active-row pivot
-        const bool mixed = (nF & 7) != 0;                                // ... which also holds variables
-        const double mv0 = (8 * Jb + 2 * t < nF) ? 1.0 : 0.0, mv1 = (8 * Jb + 2 * t + 1 < nF) ? 1.0 : 0.0;
-        const bool ondiag0 = (2 * t == g), ondiag1 = (2 * t + 1 == g);
+        __syncthreads();                                                 // the previous factor is no longer in use
         int bad = 0;
 #pragma unroll 1
         for (int J = 0; J < nt; ++J) {
             const int j0 = 8 * J + 2 * t;
             const double s0 = (j0 < nF) ? 1.0 : -1.0, s1 = (j0 + 1 < nF) ? 1.0 : -1.0;
-            const double* Lj = L + tile_off(J, 0) + fo;                  // tiles (J, K), K = 0 .. J
-            const bool scaled = (J > Jb) || (J == Jb && !mixed);        // diagonal regularised here (else inside wdiag8)
-            const int kplain = J < Jb ? J : Jb;
-            double c0[kMaxOwn], c1[kMaxOwn];
-            // ---- phase A ----
-#pragma unroll
-            for (int q = 0; q < kMaxOwn; ++q) {
-                const int I = J + wid + q * nw;
-                c0[q] = 0.0; c1[q] = 0.0;
-                if (I < nt) {
-                    const double* Li = L + tile_off(I, 0) + fo;          // tiles (I, K)
-                    const int i = 8 * I + g;
-                    d2 kk = ld2(Li + 64 * J);                            // K(I, J) as assembled
-                    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;      // two accumulator chains
-                    int K = 0;
-#pragma unroll 2
-                    for (; K + 1 < kplain; K += 2) {                     // variables: +
-                        tile_mac(a0, a1, ld2(Li + 64 * K), ld2(Lj + 64 * K));
-                        tile_mac(b0, b1, ld2(Li + 64 * K + 64), ld2(Lj + 64 * K + 64));
-                    }
-                    if (K < kplain) tile_mac(a0, a1, ld2(Li + 64 * K), ld2(Lj + 64 * K));
-                    a0 += b0; a1 += b1;
-                    if (J > Jb && mixed) {                               // variable columns of the mixed tile
-                        const d2 b = ld2(Lj + 64 * Jb);
-                        tile_mac(a0, a1, ld2(Li + 64 * Jb), d2{b.x * mv0, b.y * mv1});
-                    }
-                    if (scaled && I == J) {                              // the Schur complement's diagonal
-                        if (ondiag0) a0 *= 1.0 + eps;
-                        if (ondiag1) a1 *= 1.0 + eps;
-                    }
-                    if (J > Jb) {
-                        if (mixed) {                                     // row columns of the mixed tile: -
-                            const d2 b = ld2(Lj + 64 * Jb);
-                            tile_mac(a0, a1, ld2(Li + 64 * Jb), d2{b.x * (mv0 - 1.0), b.y * (mv1 - 1.0)});
-                        }
-                        double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
-                        int K2 = Jb + (mixed ? 1 : 0);
-#pragma unroll 2
-                        for (; K2 + 1 < J; K2 += 2) {                    // active-row columns: -
-                            tile_mac(e0, e1, ld2(Li + 64 * K2), ld2(Lj + 64 * K2));
-                            tile_mac(f0, f1, ld2(Li + 64 * K2 + 64), ld2(Lj + 64 * K2 + 64));
-                        }
-                        if (K2 < J) tile_mac(e0, e1, ld2(Li + 64 * K2), ld2(Lj + 64 * K2));
-                        a0 -= e0 + f0; a1 -= e1 + f1;
-                    }
-                    if (I == J && scaled && i >= nF && i < nk) {
-                        if (ondiag0) kk.x *= 1.0 + eps;
-                        if (ondiag1) kk.y *= 1.0 + eps;
-                    }
-                    c0[q] = kk.x - a0; c1[q] = kk.y - a1;
-                }
-            }
-            if (wid == 0) {                                              // owner of the diagonal tile (q = 0)
-                double* dsc = scratch;                                   // one tile of shared memory
-                st2(dsc + fo, c0[0], c1[0]);
+            // ---- phase A: warp 0 owns the diagonal tile (its 8 sequential pivots are the long pole of the block
+            // column) and only joins the others when many tile rows are left; warps 1.. share the rows below ----
+            if (wid == 0) {
+                double c0, c1;
+                PH_T0(ph_k);
+                tile_column(A, wts, dadd, eps, L, nk, J, J, lane, c0, c1);
+                PH_ADD(11, ph_k);
+                PH_T0(ph_d);
+                st2(scratch + fo, c0, c1);
                 __syncwarp();
                 double* Wt = L + tile_off(J, J);
                 const int jrel = nF - 8 * J;                             // first active-row pivot inside this tile
-                if (jrel > 0 && jrel < 8) bad |= wdiag8<true>(dsc, Wt, jrel, 1.0, eps, lane);
-                else bad |= wdiag8<false>(dsc, Wt, 0, jrel >= 8 ? 1.0 : -1.0, eps, lane);
+                if (jrel > 0 && jrel < 8) bad |= wdiag8<true>(scratch, Wt, jrel, 1.0, eps, lane);
+                else bad |= wdiag8<false>(scratch, Wt, 0, jrel >= 8 ? 1.0 : -1.0, eps, lane);
+                PH_ADD(12, ph_d);
+            } else {
+                for (int I = J + wid; I < nt; I += nw - 1) {             // rows J+1 .. nt-1 over warps 1 .. nw-1
+                    double c0, c1;
+                    tile_column(A, wts, dadd, eps, L, nk, I, J, lane, c0, c1);
+                    st2(L + tile_off(I, J) + fo, c0, c1);                // C(I,J) parks where V(I,J) will live
+                }
             }
             __syncthreads();
-            // ---- phase B ----
+            // ---- phase B: V(I,J) = C(I,J) W_J' S_J ----
             const d2 bw = ld2(L + tile_off(J, J) + fo);
-#pragma unroll
-            for (int q = 0; q < kMaxOwn; ++q) {
-                const int I = J + wid + q * nw;
-                if (I < nt && I > J) {
-                    double d0 = 0.0, d1 = 0.0;
-                    tile_mac(d0, d1, d2{c0[q], c1[q]}, bw);
-                    st2(L + tile_off(I, J) + fo, s0 * d0, s1 * d1);
-                }
+            for (int I = J + 1 + wid; I < nt; I += nw) {
+                double* Tt = L + tile_off(I, J) + fo;
+                double d0 = 0.0, d1 = 0.0;
+                tile_mac(d0, d1, ld2(Tt), bw);
+                st2(Tt, s0 * d0, s1 * d1);
             }
             __syncthreads();
         }
