@@ -272,6 +272,12 @@ hmpc::QpConst make_qp_const(const hmpc_config& cfg) {
     c.eps_abs = cfg.eps_abs; c.eps_rel = cfg.eps_rel; c.rho0 = cfg.rho0; c.sigma = cfg.sigma;
     c.alpha = cfg.alpha; c.kkt_eps = cfg.kkt_eps; c.polish_tol = cfg.polish_tol; c.ipm_tol = cfg.ipm_tol;
     c.condense_flops = hmpc::flops_condense(cfg.N);
+    c.work_mul = 1; c.work_add = 0;
+    if (const char* ev = getenv("HMPC_WORK_PERM")) {      // stress test: "mul,add" permutes the order the hoppers are taken in
+        int mul = 1, add = 0;
+        auto gcd = [](long long a, long long b) { while (b) { const long long r = a % b; a = b; b = r; } return a; };
+        if (sscanf(ev, "%d,%d", &mul, &add) >= 1 && mul >= 1 && add >= 0 && gcd(mul, cfg.batch) == 1) { c.work_mul = mul; c.work_add = add; }
+    }
     c.max_refine = 6;
     c.stagnation = 0.25;
     if (cfg.precision == HMPC_FP32) {   // FP32 factor: more refinement sweeps, regularisation / IPM tolerance at FP32 scale

@@ -62,7 +62,13 @@ struct QpConst {
     double eps_abs, eps_rel, rho0, sigma, alpha, kkt_eps, polish_tol, ipm_tol;
     double condense_flops;   // flops_condense(N), precomputed on the host
     double stagnation;       // refinement stops when the residual shrinks by less than this factor
+    // order in which the persistent kernels take the hoppers: ticket i -> hopper (i * work_mul + work_add) mod B
+    // (1, 0 = in order).  Results never depend on it; the stress test permutes it (HMPC_WORK_PERM, tests/test_gpu.py).
+    int work_mul, work_add;
 };
+__device__ __forceinline__ int work_item(const QpConst& c, int i, int B) {
+    return (int)(((long long)i * c.work_mul + c.work_add) % B);
+}
 
 // ------------------------------------------------------------------------------------------------
 // shared-memory carve-up (all doubles unless noted)

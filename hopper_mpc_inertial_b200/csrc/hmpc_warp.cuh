@@ -982,8 +982,9 @@ __global__ void __launch_bounds__(32 * WPC, HMPC_PREP_MINB)
 mpc_prep_kernel(QpConst c, int B, int wdoubles, double* __restrict__ prep, size_t pstride, int32_t* __restrict__ flags, MpcIo io) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int b = blockIdx.x * WPC + wid;
-    if (b >= B) return;
+    const int ticket = blockIdx.x * WPC + wid;
+    if (ticket >= B) return;
+    const int b = work_item(c, ticket, B);
     WWork w;
     wcarve(w, smem + (size_t)wid * wdoubles, c.N, kPrepKcap);
     wprep(c, w, prep + (size_t)b * pstride, flags + b, b, B, io, lane);
@@ -1007,6 +1008,7 @@ mpc_warp_kernel(QpConst c, int B, int kcap, int wdoubles, double* __restrict__ p
         if (lane == 0) b = atomicAdd(work_ctr, 1);
         b = __shfl_sync(kFullMask, b, 0);
         if (b >= B) break;
+        b = work_item(c, b, B);
         const int done = mpc_hopper_warp<SLOTS>(c, w, prep + (size_t)b * pstride, flags + b, kcap, b, B, io, lane);
         __syncwarp();
         if (done <= 0 && lane == 0) defer_list[atomicAdd(defer_cnt, 1)] = b | (done < 0 ? kDeferWarmFailed : 0);
@@ -1045,6 +1047,7 @@ mpc_warp_rounds_kernel(QpConst c, int B, int kcap, int wdoubles, double* __restr
             if (lane == 0) b = atomicAdd(work_ctr, 1);
             b = __shfl_sync(kFullMask, b, 0);
             if (b >= B) { exhausted = true; break; }
+            b = work_item(c, b, B);
             if (wfetch(c, w, prep + (size_t)b * pstride, flags + b, b, B, io, lane)) { have = true; trial = 0; info.nfac = 0; info.flops = c.condense_flops; }
             else if (lane == 0) defer_list[atomicAdd(defer_cnt, 1)] = b;
         }

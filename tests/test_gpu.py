@@ -528,6 +528,35 @@ def test_planned_rollout_equals_table_rollout():
     assert res[0][3].sum() > 0        # the scenario does exercise the respawn path
 
 
+def test_work_order_stress_is_bit_identical(monkeypatch):
+    """Race / stale-state stress (compute-sanitizer is closed on this pool): the same closed loop is repeated with the
+    hoppers handed to the persistent warps / CTAs in 24 different orders (HMPC_WORK_PERM: ticket i -> hopper
+    (i mul + add) mod B, so every hopper meets other neighbours, other shared-memory slices and another position in
+    its lock-step group); states, controls, statuses and factorisation counts must be bit-identical every time."""
+    B, N, n_ticks = 1531, 10, 7                     # a prime batch: every multiplier is a permutation
+    sc = scenarios.make_batch(B, N=N, n_ticks=n_ticks, seed=17, gain_spread=2.0, perturb=1.0)
+    args = None
+    ref = None
+    rng = np.random.default_rng(0)
+    perms = [(1, 0)] + [(int(m), int(a)) for m, a in zip(rng.integers(2, B, 23), rng.integers(0, B, 23))]
+    for mul, add in perms:
+        monkeypatch.setenv("HMPC_WORK_PERM", f"{mul},{add}")
+        bm = mk(B, "3f", N, on_infeasible="respawn")
+        bm.set_gains(T(sc["Qdiag"]), T(sc["Rdiag"]))
+        if args is None:
+            args = (T(sc["xref_tab"]), T(sc["pf_tab"]), cb64(sc["C_tab"]), T(sc["pf_switch"]))
+        X = T(sc["X0"]).clone()
+        out = bm.rollout(X, *args, 0, n_ticks, True, log=True)
+        torch.cuda.synchronize()
+        got = (X.cpu().numpy(), out["U_log"].cpu().numpy(), out["status"].cpu().numpy(), bm.solve_stats()[0].cpu().numpy())
+        bm.close()
+        if ref is None:
+            ref = got
+        else:
+            for a, b in zip(ref, got):
+                assert np.array_equal(a, b), (mul, add)
+
+
 def test_runner_forwards_a_non_default_dt():
     """Runner(dt=2e-3): the device integrates with h = dt and runs mpc_dt / dt = 10 steps per tick
     (robotrunner.py:48,154-164); both loops agree with the oracle loop run with the same constants."""
