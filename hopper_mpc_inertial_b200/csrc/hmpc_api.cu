@@ -498,7 +498,7 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
             }
             h->warp_rounds = rounds;
             h->warp_group = best_wpc;
-            if (const char* ev = getenv("HMPC_WARP_GROUP")) { const int v = atoi(ev); if (v >= 1 && v <= best_wpc) h->warp_group = v; }
+            if (const char* ev = getenv("HMPC_WARP_GROUP")) { const int v = atoi(ev); if (abs(v) >= 1 && abs(v) <= best_wpc) h->warp_group = v; }
             if ((e = hmpc::warp_set_smem(rounds, best_wpc, smem_i)) != cudaSuccess ||
                 (e = hmpc::prep_set_smem(smem_i)) != cudaSuccess) {
                 hmpc_destroy(h);

@@ -669,8 +669,11 @@ __device__ inline void wpolish_init(const QpConst& c, WWork& w, int lane) {
 }
 // One trial: 1 = verified optimum (w.xp, w.mul, w.code), 0 = active set updated, try again, -1 = give up,
 // -2 = the system does not fit this kernel's factor storage.
-template <int SLOTS>
-__device__ inline int wtrial(const QpConst& c, WWork& w, const AOp& A, int kcap, WInfo& info, int lane) {
+struct NoSync { __device__ __forceinline__ void operator()() const {} };
+// mid: called exactly once per trial by every lane, after the factorisation (lock-step kernel: a group barrier that
+// re-aligns the warps of the SM before the refinement / verification code; NoSync elsewhere)
+template <int SLOTS, class Sync = NoSync>
+__device__ inline int wtrial(const QpConst& c, WWork& w, const AOp& A, int kcap, WInfo& info, int lane, Sync mid = Sync()) {
     const int N = c.N, n = 6 * N, m = 11 * N;
     const double tol = c.polish_tol;
     double* mul = w.mul;
@@ -690,10 +693,12 @@ __device__ inline int wtrial(const QpConst& c, WWork& w, const AOp& A, int kcap,
         const int ng = wcompact(n, m - n, kcap, w.grow, n, lane, [&](int r) { return w.code[r] != 0; });
         __syncwarp();
         const int nk = nF + ng;
-        if (nk > kcap) { HMPC_EMUL_COUNT(6); return -2; }     // too large for this kernel, not a failed attempt
+        if (nk > kcap) { HMPC_EMUL_COUNT(6); mid(); return -2; }     // too large for this kernel, not a failed attempt
         ++info.nfac;
         info.flops += flops_factor(nk);
-        if (wfactor(c, w, A, nF, ng, c.kkt_eps, lane)) return -1;
+        const int fbad = wfactor(c, w, A, nF, ng, c.kkt_eps, lane);
+        mid();
+        if (fbad) return -1;
         double prev = 1e300;
         bool hx_current = false;
         for (int k = 0; k < c.max_refine; ++k) {
@@ -1034,6 +1039,8 @@ mpc_warp_rounds_kernel(QpConst c, int B, int kcap, int wdoubles, double* __restr
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     // lock-step groups of gw warps, each on its own named barrier (the last group takes what is left of the CTA)
+    const int midsync = gw < 0;        // experiment switch: negative group size = one more barrier after the factorisation
+    if (gw < 0) gw = -gw;
     const int grp = wid / gw, bar_id = 1 + grp;
     const int bar_threads = 32 * ((grp + 1) * gw <= WPC ? gw : WPC - grp * gw);
     WWork w;
@@ -1052,8 +1059,10 @@ mpc_warp_rounds_kernel(QpConst c, int B, int kcap, int wdoubles, double* __restr
             else if (lane == 0) defer_list[atomicAdd(defer_cnt, 1)] = b;
         }
         if (group_all(bar_id, bar_threads, !have)) break;
+        auto mid = [&]() { if (midsync) group_all(bar_id, bar_threads, true); };
+        if (!have) mid();
         if (have) {
-            const int r = wtrial<SLOTS>(c, w, A, kcap, info, lane);
+            const int r = wtrial<SLOTS>(c, w, A, kcap, info, lane, mid);
             if (r > 0) { wfinish(c, w, b, B, io, info, lane); have = false; }
             else if (r < 0 || ++trial > c.retries) {
                 if (lane == 0) defer_list[atomicAdd(defer_cnt, 1)] = b | (r == -2 ? 0 : kDeferWarmFailed);
