@@ -222,6 +222,19 @@ class BatchMpc:
                                                  _ptr(out["status"]), _ptr(out["iters"])))
         return out
 
+    def set_contact_gate(self, mode="off", gate_tab=None, gate_glob=None, leg_max=0.0):
+        """Contact gate of the applied control (include/hmpc.h: hmpc_set_contact_gate; robotrunner.py:99,111).
+        ``mode``: "off" (the reference as shipped), "schedule" (U[0] * s at every simulator step; ``gate_tab`` (T,B)
+        int32 device tensor of per-tick step masks for ``rollout`` and / or ``gate_glob`` (max_tick,) host uint32 array
+        for ``rollout_planned``, see planner.gate_masks / global_tables), "detect" (leg reach <= ``leg_max``)."""
+        m = _lib.GATE[mode]
+        if gate_tab is not None:
+            self._chk(gate_tab, (gate_tab.shape[0], self.B), torch.int32)
+        gg = None if gate_glob is None else np.ascontiguousarray(gate_glob, dtype=np.uint32)
+        _lib.check(self.lib.hmpc_set_contact_gate(self._h, m, _ptr(gate_tab), None if gg is None else gg.ctypes.data_as(C.c_void_p),
+                                                  0 if gg is None else int(gg.shape[0]), float(leg_max)))
+        self._gate_keep = gate_tab
+
     def solve_stats(self):
         """Per-hopper (nfac, path, n_infeasible) of the last solve / accumulated over the last rollout."""
         nf = self.empty(self.B, dtype=torch.int32)

@@ -74,6 +74,7 @@ struct hmpc_handle {
     int mpc_grid = 0;
     size_t mpc_smem = 0;
     bool mats_in_smem = false;
+    int wide_ctas = 1;               // L2-workspace kernel (long horizons): resident CTAs per SM it is compiled for
     double* ws = nullptr;     // per-CTA matrix workspace when the matrices do not fit in shared memory
     int64_t launches = 0;
     // warp-per-hopper warm path (hmpc_warp.cuh): geometry, per-warp Hessian workspace, deferral list
@@ -92,6 +93,12 @@ struct hmpc_handle {
     uint64_t* win_C = nullptr;    // [B]
     uint8_t* win_sw = nullptr;    // [B]
     int* defer_list = nullptr;    // [B] hoppers the warp kernel handed to the CTA kernel this tick
+    // contact gate of the simulator (hmpc_set_contact_gate)
+    int gate_mode = HMPC_GATE_OFF;
+    const uint32_t* gate_tab = nullptr;   // caller's [T][B] masks (table flavour)
+    uint32_t* gate_glob = nullptr;        // device copy of the common-clock masks (planned flavour)
+    int gate_max_tick = 0;
+    double leg_max = 0.0;
     int32_t* n_defer = nullptr;   // [1] accumulated deferrals of the most recent solve / rollout
 };
 
@@ -105,7 +112,7 @@ sim_kernel(SimConst c, int B, double* __restrict__ X, const double* __restrict__
            const double* __restrict__ pfa, const double* __restrict__ pfb,
            const uint8_t* __restrict__ sw, int nsteps, double* __restrict__ xin_out,
            double* __restrict__ Xlog, double* __restrict__ Ulog, double* __restrict__ Xsteps,
-           const int32_t* __restrict__ st_tick, const double* __restrict__ xref_next) {
+           const int32_t* __restrict__ st_tick, const double* __restrict__ xref_next, SimGate gt) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     double Xl[13], Ul[6], pa[3], pb[3];
@@ -132,13 +139,7 @@ sim_kernel(SimConst c, int B, double* __restrict__ X, const double* __restrict__
         mat3T_vec(R, xr + 6, Xl + 7);
         Xl[10] = Xl[11] = Xl[12] = 0.0;
     } else {
-        for (int k = 0; k < nsteps; ++k) {
-            rk4_step(c, Xl, Ul, (k < s) ? pa : pb);
-            if (Xsteps) {
-#pragma unroll
-                for (int i = 0; i < 13; ++i) Xsteps[((size_t)k * 13 + i) * B + b] = Xl[i];
-            }
-        }
+        sim_tick(c, gt.mode, gate_bits_of(gt, b), gt.leg_max2, Xl, Ul, pa, pb, s, nsteps, Xsteps, (size_t)B, b);
     }
 #pragma unroll
     for (int i = 0; i < 13; ++i) X[(size_t)i * B + b] = Xl[i];
@@ -416,16 +417,32 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
     const size_t mat_bytes = hmpc::mat_doubles((int)N, fsize) * 8;
     const size_t smem_cap = (size_t)prop.sharedMemPerBlockOptin;
     h->mats_in_smem = (vec_bytes + mat_bytes + 1024 <= smem_cap);
+    // N > 10: the matrices go to the L2 workspace even when they would fit in shared memory -- two 128-register CTAs per
+    // SM beat one 223-register CTA with shared-memory matrices (N = 20, 65536 hoppers: 1.91 M vs 1.51 M steps/s,
+    // profiles/README.md); HMPC_WIDE_SMEM=1 selects the shared-memory kernel
+    if (n > 64) { const char* ev = getenv("HMPC_WIDE_SMEM"); if (!(ev && atoi(ev))) h->mats_in_smem = false; }
     h->mpc_smem = vec_bytes + (h->mats_in_smem ? mat_bytes : 0);
     // occupancy experiments (profiles/README.md): HMPC_SMEM_PAD=<bytes> pads the dynamic shared memory request
     if (const char* pad = getenv("HMPC_SMEM_PAD")) h->mpc_smem += (size_t)atol(pad);
     if (h->mpc_smem > smem_cap) { hmpc_destroy(h); return fail(HMPC_ERR_UNSUPPORTED, "horizon too large for shared memory"); }
     h->mpc_threads = (n <= 64) ? 128 : 256;   // one CTA per SM beyond N = 10: use the wider CTA
     // the 128-thread instantiations are compiled for shared-memory matrices only
-    if (h->mpc_threads == 128 && !h->mats_in_smem) { hmpc_destroy(h); return fail(HMPC_ERR_UNSUPPORTED, "shared memory too small for the N <= 10 solver kernel"); }
+    if (n <= 64 && !h->mats_in_smem) { hmpc_destroy(h); return fail(HMPC_ERR_UNSUPPORTED, "shared memory too small for the N <= 10 solver kernel"); }
     int per_sm = 1;
     if (h->mats_in_smem) per_sm = std::max<int>(1, (int)((size_t)prop.sharedMemPerMultiprocessor / (h->mpc_smem + 1024)));
-    else per_sm = std::max<int>(1, std::min<int>(8, (int)((size_t)prop.sharedMemPerMultiprocessor / (h->mpc_smem + 1024))));
+    else {
+        // N > 10, matrices in the L2 workspace.  Three builds of the same kernel, chosen by how many CTAs the vectors
+        // in shared memory let an SM hold (HMPC_WIDE_CTAS=1|2|4 overrides; measured at 65536 hoppers, 3f,
+        // profiles/README.md): four 128-thread CTAs (128 registers; N = 20: 2.10 M steps/s), two 256-thread CTAs
+        // (128 registers; N = 20: 1.93 M, N = 40: 0.56 M), one 256-thread CTA (235 registers; N = 40: 0.42 M).
+        // More independent hoppers per SM win because each hopper's pivot chain leaves most of its warps waiting.
+        h->wide_ctas = 4;
+        if (const char* ev = getenv("HMPC_WIDE_CTAS")) { const int v = atoi(ev); h->wide_ctas = (v == 1 || v == 2) ? v : 4; }
+        per_sm = std::max<int>(1, std::min<int>(h->wide_ctas, (int)((size_t)prop.sharedMemPerMultiprocessor / (h->mpc_smem + 1024))));
+        if (per_sm < h->wide_ctas) h->wide_ctas = per_sm >= 2 ? 2 : 1;
+        if (h->wide_ctas == 4) h->mpc_threads = 128;
+        per_sm = std::min(per_sm, h->wide_ctas);
+    }
     h->mpc_grid = (int)std::min<size_t>(B, (size_t)h->sm_count * per_sm);
     if (!h->mats_in_smem) {
         if ((e = cudaMalloc((void**)&h->ws, (size_t)h->mpc_grid * mat_bytes)) != cudaSuccess) {
@@ -436,11 +453,11 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
     // the attribute is process-global per kernel: always the device maximum (minus room for static shared memory),
     // so that a second handle never lowers it for the first
     const int smem_i = (int)smem_cap - 512;
-    if (h->mpc_threads == 128) {
+    if (6 * h->cfg.N <= 64) {
         if (cfg->precision == HMPC_FP32) e = hmpc::mpc_set_smem_n10_f32(smem_i);
         else e = (cfg->solver == HMPC_SOLVER_ADMM) ? hmpc::mpc_set_smem_n10_f64_admm(smem_i) : hmpc::mpc_set_smem_n10_f64(smem_i);
     }
-    else e = h->mats_in_smem ? hmpc::mpc_set_smem_wide_smem(smem_i) : hmpc::mpc_set_smem_wide_gmem(smem_i);
+    else e = h->mats_in_smem ? hmpc::mpc_set_smem_wide_smem(smem_i) : (h->wide_ctas == 4 ? hmpc::mpc_set_smem_wide_gmem4(smem_i) : h->wide_ctas == 2 ? hmpc::mpc_set_smem_wide_gmem2(smem_i) : hmpc::mpc_set_smem_wide_gmem(smem_i));
     if (e != cudaSuccess ||
         (e = cudaFuncSetAttribute(hmpc::condense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_i)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(hmpc::linearize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_i)) != cudaSuccess) {
@@ -523,6 +540,7 @@ int hmpc_destroy(hmpc_handle* h) {
     cudaFree(h->code); cudaFree(h->valid); cudaFree(h->st_tick); cudaFree(h->nfac); cudaFree(h->path); cudaFree(h->ninf); cudaFree(h->flops); cudaFree(h->work_ctr);
     cudaFree(h->plan_sin); cudaFree(h->plan_pfidx); cudaFree(h->plan_cmask); cudaFree(h->plan_sw);
     cudaFree(h->win_xref); cudaFree(h->win_pf); cudaFree(h->win_C); cudaFree(h->win_sw);
+    cudaFree(h->gate_glob);
     cudaFree(h->prep); cudaFree(h->prep_flag); cudaFree(h->defer_list); cudaFree(h->n_defer);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     delete h;
@@ -564,7 +582,8 @@ int hmpc_rk4(hmpc_handle* h, double* X, const double* U, const double* pf, int n
     if (!X || !U || !pf || nsteps < 0) return fail(HMPC_ERR_BAD_ARG, "bad argument");
     const int B = h->cfg.batch;
     hmpc::sim_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(make_sim_const(h->cfg), B, X, U, pf, nullptr,
-                                                              nullptr, nsteps, nullptr, nullptr, nullptr, X_steps, nullptr, nullptr);
+                                                              nullptr, nsteps, nullptr, nullptr, nullptr, X_steps, nullptr, nullptr,
+                                                              hmpc::SimGate{HMPC_GATE_OFF, nullptr, nullptr, nullptr, 0, 0, 0.0});
     ++h->launches;
     HMPC_CUDA(cudaGetLastError());
     return HMPC_OK;
@@ -614,11 +633,13 @@ cudaError_t launch_mpc(hmpc_handle* h, const hmpc::QpConst& qc, const hmpc::MpcI
     }
     const hmpc::MpcLaunch l{h->mpc_grid, h->mpc_threads, h->mpc_smem, h->stream, h->cfg.batch, h->sm_count, h->ws,
                             h->work_ctr + 2, warp ? h->defer_list : nullptr, warp ? h->work_ctr + 1 : nullptr};
-    if (h->mpc_threads == 128) {
+    if (6 * h->cfg.N <= 64) {
         if (h->cfg.precision == HMPC_FP32) hmpc::mpc_launch_n10_f32(l, qc, io);
         else if (h->cfg.solver == HMPC_SOLVER_ADMM) hmpc::mpc_launch_n10_f64_admm(l, qc, io);
         else hmpc::mpc_launch_n10_f64(l, qc, io);
     } else if (h->mats_in_smem) hmpc::mpc_launch_wide_smem(l, qc, io);
+    else if (h->wide_ctas == 4) hmpc::mpc_launch_wide_gmem4(l, qc, io);
+    else if (h->wide_ctas == 2) hmpc::mpc_launch_wide_gmem2(l, qc, io);
     else hmpc::mpc_launch_wide_gmem(l, qc, io);
     ++h->launches;
     return cudaGetLastError();
@@ -674,6 +695,9 @@ int rollout_impl(hmpc_handle* h, bool planned, double* X, const double* xref_tab
         }
     }
     h->ev_ticks = h->timing ? n_ticks : 0;
+    if (h->gate_mode == HMPC_GATE_SCHEDULE && (planned ? !h->gate_glob : !h->gate_tab))
+        return fail(HMPC_ERR_BAD_ARG, planned ? "HMPC_GATE_SCHEDULE: hmpc_set_contact_gate was given no gate_glob for hmpc_rollout_planned"
+                                              : "HMPC_GATE_SCHEDULE: hmpc_set_contact_gate was given no gate_tab for hmpc_rollout");
     const hmpc::QpConst qc = make_qp_const(h->cfg);
     const hmpc::SimConst sc = make_sim_const(h->cfg);
     const int sim_grid = (Bi + 127) / 128;
@@ -696,6 +720,11 @@ int rollout_impl(hmpc_handle* h, bool planned, double* X, const double* xref_tab
             xr = xref_tab + row * 12 * B; pf = pf_tab + row * 3 * B; Cm = C_tab + row * B;
             sw = pf_switch ? pf_switch + row * B : nullptr;
         }
+        hmpc::SimGate gate{h->gate_mode, nullptr, nullptr, nullptr, tick0 + t, h->gate_max_tick, h->leg_max * h->leg_max};
+        if (h->gate_mode == HMPC_GATE_SCHEDULE) {
+            if (planned) { gate.glob = h->gate_glob; gate.off = h->plan.off; }
+            else gate.bits = h->gate_tab + (size_t)(tick0 + t) * B;
+        }
         hmpc::MpcIo io = make_io(h, h->xin, xr, pf, Cm, (init && t == 0) ? 1 : 0, 1, nullptr, nullptr, h->U0, st, it);
         if (h->timing) HMPC_CUDA(cudaEventRecord(h->ev[3 * t], h->stream));
         HMPC_CUDA(launch_mpc(h, qc, io));
@@ -703,7 +732,7 @@ int rollout_impl(hmpc_handle* h, bool planned, double* X, const double* xref_tab
         hmpc::sim_kernel<<<sim_grid, 128, 0, h->stream>>>(
             sc, Bi, X, h->U0, pf, pf + 3 * B, sw, h->cfg.mpc_factor, h->xin,
             X_log ? X_log + (size_t)(t + 1) * 13 * B : nullptr, U_log ? U_log + (size_t)t * 6 * B : nullptr,
-            nullptr, respawn ? h->st_tick : nullptr, respawn ? xr + 12 * B : nullptr);
+            nullptr, respawn ? h->st_tick : nullptr, respawn ? xr + 12 * B : nullptr, gate);
         if (h->timing) HMPC_CUDA(cudaEventRecord(h->ev[3 * t + 2], h->stream));
         ++h->launches;
     }
@@ -781,6 +810,33 @@ int hmpc_rollout_planned(hmpc_handle* h, double* X, int tick0, int n_ticks, int 
     if (!h->plan_ok) return fail(HMPC_ERR_BAD_ARG, "hmpc_plan_set has not been called");
     if (!X || tick0 < 0 || n_ticks < 0) return fail(HMPC_ERR_BAD_ARG, "bad argument");
     return rollout_impl(h, true, X, nullptr, nullptr, nullptr, nullptr, tick0, n_ticks, init, X_log, U_log, status, iters);
+}
+
+int hmpc_set_contact_gate(hmpc_handle* h, int mode, const uint32_t* gate_tab, const uint32_t* gate_glob_host, int max_tick,
+                          double leg_max) {
+    if (int rc = check_handle(h)) return rc;
+    if (mode != HMPC_GATE_OFF && mode != HMPC_GATE_SCHEDULE && mode != HMPC_GATE_DETECT) return fail(HMPC_ERR_BAD_ARG, "unknown gate mode");
+    if (mode == HMPC_GATE_SCHEDULE) {
+        if (h->cfg.mpc_factor > 32) return fail(HMPC_ERR_UNSUPPORTED, "HMPC_GATE_SCHEDULE needs mpc_factor <= 32 (one mask bit per simulator step)");
+        if (!gate_tab && !gate_glob_host) return fail(HMPC_ERR_BAD_ARG, "HMPC_GATE_SCHEDULE needs gate_tab or gate_glob");
+        if (gate_glob_host && max_tick < 1) return fail(HMPC_ERR_BAD_ARG, "gate_glob needs max_tick >= 1");
+    }
+    if (mode == HMPC_GATE_DETECT && !(leg_max > 0.0)) return fail(HMPC_ERR_BAD_ARG, "HMPC_GATE_DETECT needs leg_max > 0");
+    HMPC_CUDA(cudaStreamSynchronize(h->stream));          // the previous tables may still be in use
+    cudaFree(h->gate_glob);
+    h->gate_glob = nullptr; h->gate_tab = nullptr; h->gate_max_tick = 0; h->gate_mode = HMPC_GATE_OFF; h->leg_max = 0.0;
+    if (mode == HMPC_GATE_SCHEDULE) {
+        if (gate_glob_host) {
+            cudaError_t e = cudaMalloc((void**)&h->gate_glob, (size_t)max_tick * 4);
+            if (e != cudaSuccess) return fail(HMPC_ERR_ALLOC, std::string("cudaMalloc gate table: ") + cudaGetErrorString(e));
+            HMPC_CUDA(cudaMemcpy(h->gate_glob, gate_glob_host, (size_t)max_tick * 4, cudaMemcpyHostToDevice));
+            h->gate_max_tick = max_tick;
+        }
+        h->gate_tab = gate_tab;
+    }
+    if (mode == HMPC_GATE_DETECT) h->leg_max = leg_max;
+    h->gate_mode = mode;
+    return HMPC_OK;
 }
 
 int hmpc_set_timing(hmpc_handle* h, int enable) {

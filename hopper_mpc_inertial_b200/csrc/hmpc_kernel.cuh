@@ -28,7 +28,7 @@ mpc_kernel(QpConst c, int B, int sm_count, double* __restrict__ ws, int* __restr
     // CTAs are dealt to the SMs round-robin, so the CTAs sharing an SM differ in blockIdx.x / #SMs
     sys.solver_warp = blockIdx.x / sm_count;
     // horizons beyond N = 10 (256-thread CTAs): tensor-core tiles, all warps of the CTA (LinSys::factor_tiled)
-    sys.tiled = (THREADS == 256 && sizeof(F) == 8 && tiled_factor_applies(c.N)) ? 1 : 0;
+    sys.tiled = (sizeof(F) == 8 && tiled_factor_applies(c.N)) ? 1 : 0;
     // dynamic distribution of hoppers over the persistent CTAs (solve times differ: warm active-set path
     // vs interior-point path); results do not depend on the order
     // list mode: only the hoppers the warp kernel deferred (hmpc_warp.cuh), in any order
@@ -76,6 +76,10 @@ cudaError_t mpc_set_smem_wide_smem(int bytes);    // 256 threads, 1 CTA/SM, shar
 void mpc_launch_wide_smem(const MpcLaunch&, const QpConst&, const MpcIo&);
 cudaError_t mpc_set_smem_wide_gmem(int bytes);    // 256 threads, matrices in the L2-resident workspace, FP64 factor
 void mpc_launch_wide_gmem(const MpcLaunch&, const QpConst&, const MpcIo&);
+cudaError_t mpc_set_smem_wide_gmem2(int bytes);   // the same compiled for 2 CTAs/SM (<= 128 registers)
+void mpc_launch_wide_gmem2(const MpcLaunch&, const QpConst&, const MpcIo&);
+cudaError_t mpc_set_smem_wide_gmem4(int bytes);   // 128 threads, 4 CTAs/SM, matrices in the L2 workspace
+void mpc_launch_wide_gmem4(const MpcLaunch&, const QpConst&, const MpcIo&);
 
 
 // the warp-per-hopper warm-path kernel (hmpc_warp.cuh, instantiated in inst_warp.cu)

@@ -10,6 +10,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdint.h>
 
 namespace hmpc {
 
@@ -131,6 +132,55 @@ __device__ __forceinline__ void rk4_step(const SimConst& c, double X[13], const 
     for (int i = 0; i < 13; ++i) X[i] = X[i] + (h / 6.0) * (f1[i] + 2.0 * f2[i] + 2.0 * f3[i] + f4[i]);
     const double nq = sqrt(X[3] * X[3] + X[4] * X[4] + X[5] * X[5] + X[6] * X[6]);
     X[3] /= nq; X[4] /= nq; X[5] /= nq; X[6] /= nq;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Contact gate of the applied control (include/hmpc.h: hmpc_set_contact_gate).  The reference computes the scheduled
+// contact s = gait_scheduler(t, t0) at every simulator step and logs it, but applies U[0] ungated --
+// `f_hist[k, :] = U[0, :]  # * s` (robotrunner.py:99,111-112).  mode 0 is that behaviour; mode 1 switches the
+// commented-out factor on (bit k of `bits` = s at simulator step k of the tick); mode 2 detects contact from the state:
+// the leg vector of dynamics_ct (robotrunner.py:143), r = rh + R(q)'(pf - p), is no longer than leg_max.
+// ------------------------------------------------------------------------------------------------
+struct SimGate {
+    int mode;                    // HMPC_GATE_*
+    const uint32_t* bits;        // [B] masks of this tick (table flavour), or null
+    const uint32_t* glob;        // [max_tick] masks on the common clock (planned flavour), or null
+    const int32_t* off;          // [B] tick offsets of the hoppers (planned flavour)
+    int tick, max_tick;
+    double leg_max2;             // leg_max squared
+};
+__device__ __forceinline__ uint32_t gate_bits_of(const SimGate& gt, int b) {
+    if (gt.mode != 1) return 0xffffffffu;
+    if (gt.bits) return gt.bits[b];
+    const int j = gt.off[b] + gt.tick;
+    return gt.glob[j < gt.max_tick ? j : gt.max_tick - 1];
+}
+__device__ __forceinline__ bool leg_reaches(const SimConst& c, const double X[13], const double pf[3], double leg_max2) {
+    double R[9], r[3];
+    const double d[3] = {pf[0] - X[0], pf[1] - X[1], pf[2] - X[2]};
+    quat_rotm(&X[3], R);
+    mat3T_vec(R, d, r);
+    r[0] += c.rh[0]; r[1] += c.rh[1]; r[2] += c.rh[2];
+    return r[0] * r[0] + r[1] * r[1] + r[2] * r[2] <= leg_max2;
+}
+// One MPC tick of the simulator for one hopper (robotrunner.py:110-113): nsteps x rk4_normalized with the tick's
+// control held (times the contact gate), footstep pa before simulator step sw and pb from it on.  Xsteps (may be
+// null): state after every step, [nsteps][13][B].
+__device__ __forceinline__ void sim_tick(const SimConst& c, int gate_mode, uint32_t bits, double leg_max2, double X[13],
+                                         const double U[6], const double pa[3], const double pb[3], int sw, int nsteps,
+                                         double* Xsteps, size_t B, int b) {
+    const double Z[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int k = 0; k < nsteps; ++k) {
+        const double* pf = (k < sw) ? pa : pb;
+        bool on = true;
+        if (gate_mode == 1) on = (bits >> k) & 1u;
+        else if (gate_mode == 2) on = leg_reaches(c, X, pf, leg_max2);
+        rk4_step(c, X, on ? U : Z, pf);
+        if (Xsteps) {
+#pragma unroll
+            for (int i = 0; i < 13; ++i) Xsteps[((size_t)k * 13 + i) * B + b] = X[i];
+        }
+    }
 }
 
 }  // namespace hmpc

@@ -81,6 +81,18 @@ def run_clock(n_steps, dt, t_start):
     return t
 
 
+def gate_masks(n_ticks, mpc_factor, dt, t_start, t_p=T_P, phi_switch=PHI_SWITCH, t0=0.0):
+    """Scheduled contact at every simulator step, packed per MPC tick: bit i of entry j = gait_scheduler(t_k, t0) at
+    k = mpc_factor j + i on the run clock (robotrunner.py:97-99: `t = t + self.dt`, `s = self.gait_scheduler(t, t0)`).
+    This is the factor of the reference's commented-out gate `f_hist[k, :] = U[0, :]  # * s` (robotrunner.py:111).
+    Returns (n_ticks,) uint32 (needs mpc_factor <= 32)."""
+    if mpc_factor > 32:
+        raise ValueError("gate masks hold one bit per simulator step: mpc_factor <= 32")
+    s = gait_scheduler(run_clock(n_ticks * mpc_factor, dt, t_start), t0, t_p, phi_switch).reshape(n_ticks, mpc_factor)
+    w = (np.uint64(1) << np.arange(mpc_factor, dtype=np.uint64))
+    return ((s != 0).astype(np.uint64) * w).sum(axis=-1).astype(np.uint32)
+
+
 def mpc_tables(x_ref, pf_ref, n_ticks, N, mpc_factor, dt, mpc_dt, t_start, t_p=T_P, phi_switch=PHI_SWITCH):
     """MPC-rate tables of one hopper for ``hmpc_rollout``.
 
@@ -122,6 +134,7 @@ def global_tables(N_run, N, max_tick, mpc_factor=20, dt=1e-3, mpc_dt=0.02, t_sta
       pf_idx (n_sim,)    simulator index whose reference xy is the footstep in force at step k  (:214-224)
       Cglob (max_tick,N) contact flags of the MPC window of global tick j, cmask the same as bit masks (:97-102,172-180)
       sw_glob (max_tick,) simulator step inside tick j at which the footstep index changes (mpc_factor = never)
+      gate_glob (max_tick,) uint32 scheduled contact at the simulator steps of tick j, one bit per step (gate_masks)
     with the reference's running float sums."""
     t_ref = N_run + N * mpc_factor
     if n_sim is None:
@@ -150,7 +163,8 @@ def global_tables(N_run, N, max_tick, mpc_factor=20, dt=1e-3, mpc_dt=0.02, t_sta
     w = (np.uint64(1) << np.arange(N, dtype=np.uint64))
     cmask = ((Cglob != 0).astype(np.uint64) * w).sum(axis=-1).astype(np.uint64)
     s45 = np.sin(45 * np.pi / 180)
-    return dict(sin_tab=sin_tab, pf_idx=pf_idx.astype(np.int32), sw_glob=sw_glob, Cglob=Cglob, cmask=cmask,
+    gate_glob = gate_masks(max_tick, mpc_factor, dt, t_start, t_p, phi_switch) if mpc_factor <= 32 else None
+    return dict(sin_tab=sin_tab, pf_idx=pf_idx.astype(np.int32), sw_glob=sw_glob, Cglob=Cglob, cmask=cmask, gate_glob=gate_glob,
                 curve_psi1=-0.4 * s45, curve_psi2=-s45, n_sim=n_sim, max_tick=max_tick, N_run=N_run, t_p=t_p)
 
 
@@ -165,7 +179,7 @@ def batch_tables(x0, xf, curve, tick_offset, N_run, n_ticks, N, mpc_factor=20, d
     t_start, running sums) is the reference's.
     Returns dict of numpy arrays in the SoA layout of include/hmpc.h:
       xref_tab (n_ticks+N, 12, B), pf_tab (n_ticks+N+1, 3, B), C_tab (n_ticks, B) uint64,
-      pf_switch (n_ticks, B) uint8, C (n_ticks, B, N) float."""
+      pf_switch (n_ticks, B) uint8, C (n_ticks, B, N) float, gate_tab (n_ticks, B) uint32 (gate_masks per hopper)."""
     x0 = np.asarray(x0, float); xf = np.asarray(xf, float)
     B = x0.shape[0]
     curve = np.asarray(curve, bool)
@@ -214,6 +228,7 @@ def batch_tables(x0, xf, curve, tick_offset, N_run, n_ticks, N, mpc_factor=20, d
     sw[np.all(pf_tab[:n_ticks] == pf_tab[1:n_ticks + 1], axis=-1)] = mpc_factor
     C = gt["Cglob"][jj]                                                       # (n_ticks,B,N)
     C_tab = gt["cmask"][jj]
+    gate_tab = gt["gate_glob"][jj] if gt["gate_glob"] is not None else None      # (n_ticks,B) uint32 step masks
     return dict(xref_tab=np.ascontiguousarray(xref_tab.transpose(0, 2, 1)),
                 pf_tab=np.ascontiguousarray(pf_tab.transpose(0, 2, 1)),
-                C_tab=C_tab, pf_switch=sw, C=C)
+                C_tab=C_tab, pf_switch=sw, C=C, gate_tab=gate_tab)

@@ -41,8 +41,15 @@ def convert(X_in):
 
 class Runner:
     def __init__(self, dt=1e-3, dyn='2f', curve=False, N_run=5000, N=60, device=0, progress=True,
-                 **mpc_kwargs):
+                 contact_gate="off", leg_max=None, **mpc_kwargs):
         self.dt, self.N_run, self.curve, self.dyn = dt, N_run, curve, dyn
+        # contact gate of the applied control (robotrunner.py:111 `f_hist[k, :] = U[0, :]  # * s`): "off" = the
+        # reference as shipped, "schedule" = the commented-out factor switched on, "detect" = leg reach <= leg_max
+        if contact_gate not in ("off", "schedule", "detect"):
+            raise ValueError("contact_gate must be 'off', 'schedule' or 'detect'")
+        if contact_gate == "detect" and not (leg_max and leg_max > 0):
+            raise ValueError("contact_gate='detect' needs leg_max > 0")
+        self.contact_gate, self.leg_max = contact_gate, leg_max
         self.m = 7.5
         self.J = np.array([[76148072.89, 70089.52, 2067970.36],
                            [70089.52, 45477183.53, -87045.58],
@@ -101,6 +108,8 @@ class Runner:
 
     def run(self, plot=False):
         """The reference's closed loop (robotrunner.py:81-124), MPC + RK4 on the GPU."""
+        if self.contact_gate == "detect":
+            raise ValueError("contact_gate='detect' reads the state at every simulator step: use run_fused()")
         N_run = self.N_run + 1
         t = self.t_start
         t0 = 0
@@ -127,19 +136,21 @@ class Runner:
             U = self.mpc.mpcontrol(x_in=x_in, x_ref_in=x_refk, pf=pf_refk, C=C, init=init)
             init = False
             Ud = torch.as_tensor(U[0].reshape(6, 1).copy(), device=dev)
-            # integrate the tick; split where the footstep reference changes
-            i = 0
             nst = len(ts)
+            s_k = np.array([self.gait_scheduler(tt, t0) for tt in ts], float)
+            gate = s_k if self.contact_gate == "schedule" else np.ones(nst)
+            # integrate the tick; split where the footstep reference (or the contact gate) changes
+            i = 0
             while i < nst:
                 j = i + 1
-                while j < nst and np.all(pf_ref[k0 + j] == pf_ref[k0 + i]):
+                while j < nst and np.all(pf_ref[k0 + j] == pf_ref[k0 + i]) and gate[j] == gate[i]:
                     j += 1
                 pfd = torch.as_tensor(pf_ref[k0 + i].reshape(3, 1).copy(), device=dev)
-                Xs = bm.rk4(Xd, Ud, pfd, j - i, log_steps=True)
+                Xs = bm.rk4(Xd, Ud * float(gate[i]), pfd, j - i, log_steps=True)
                 X_traj[k0 + i + 1:k0 + j + 1] = Xs[:, :, 0].cpu().numpy()
                 i = j
-            f_hist[k0:k0 + nst] = U[0]
-            s_hist[k0:k0 + nst] = [self.gait_scheduler(tt, t0) for tt in ts]
+            f_hist[k0:k0 + nst] = U[0][None, :] * gate[:, None]
+            s_hist[k0:k0 + nst] = s_k
         self.X_traj, self.f_hist, self.s_hist, self.x_ref, self.pf_ref = X_traj, f_hist, s_hist, x_ref, pf_ref
         if plot:
             self.plot()
@@ -156,6 +167,13 @@ class Runner:
         self.mpc._push_gains(bm)
         dev = bm.device
         X = torch.as_tensor(self.X_0.reshape(13, 1).copy(), device=dev)
+        if self.contact_gate == "schedule":
+            gm = planner.gate_masks(n_ticks, self.mpc_factor, self.dt, self.t_start, self.t_p, self.phi_switch)
+            bm.set_contact_gate("schedule", gate_tab=torch.as_tensor(gm.view(np.int32).reshape(n_ticks, 1).copy(), device=dev))
+        elif self.contact_gate == "detect":
+            bm.set_contact_gate("detect", leg_max=float(self.leg_max))
+        else:
+            bm.set_contact_gate("off")
         out = bm.rollout(X, torch.as_tensor(xt[:, :, None].copy(), device=dev),
                          torch.as_tensor(pt[:, :, None].copy(), device=dev),
                          torch.as_tensor(cbits_from_C(C).view(np.int64).reshape(n_ticks, 1).copy(), device=dev),

@@ -16,12 +16,15 @@ def main(argv=None):
     parser.add_argument("--device", type=int, default=0)
     parser.add_argument("--plot", action="store_true", help="save plots (needs matplotlib)")
     parser.add_argument("--fused", action="store_true", help="use the fused rollout path")
+    parser.add_argument("--gate", choices=["off", "schedule", "detect"], default="off",
+                        help="contact gate of the applied control (reference robotrunner.py:111 has `* s` commented out = off)")
+    parser.add_argument("--leg_max", type=float, default=None, help="leg reach for --gate detect [m]")
     args = parser.parse_args(argv)
 
     from .robotrunner import Runner
     dt = 1e-3
     runner = Runner(dt=dt, dyn=args.dyn, curve=bool(args.curve), N_run=args.N_run, N=args.horizon,
-                    device=args.device)
+                    device=args.device, contact_gate=args.gate, leg_max=args.leg_max)
     if args.fused:
         X_log, U_log = runner.run_fused()
         print("final state:", X_log[-1])

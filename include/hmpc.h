@@ -223,6 +223,24 @@ int hmpc_plan_tables(hmpc_handle* h, int tick0, int n_ticks, double* xref_tab, d
 int hmpc_rollout_planned(hmpc_handle* h, double* X, int tick0, int n_ticks, int init, double* X_log, double* U_log,
                          int32_t* status, int32_t* iters);
 
+/* ---- contact gate of the applied control (second half) --------------------------------------------
+ * The reference computes the scheduled contact s = gait_scheduler(t, t0) at every simulator step and logs it
+ * (robotrunner.py:99,112) but applies the control ungated: `f_hist[k, :] = U[0, :]  # * s` (robotrunner.py:111).
+ *   HMPC_GATE_OFF       (default) the reference as shipped: U[0] is held over the whole tick
+ *   HMPC_GATE_SCHEDULE  the commented-out factor switched on: simulator step i of a tick applies U[0] * s_i with s_i
+ *                       the scheduled contact at that step's time (1 kHz gait clock, robotrunner.py:97-99,166-171)
+ *   HMPC_GATE_DETECT    contact detected from the state instead of the clock: s_i = 1 while the leg vector of
+ *                       dynamics_ct, r = rh + R(q)'(pf - p) (robotrunner.py:143), is no longer than leg_max, else 0
+ * gate_tab  [T][B] uint32 (device, referenced not copied; used by hmpc_rollout): bit i of entry (tick, b) = s at
+ *           simulator step i of that tick, indexed like C_tab;
+ * gate_glob [max_tick] uint32 (HOST, copied; used by hmpc_rollout_planned): the same masks on the common clock,
+ *           hopper b reads entry tick_offset[b] + tick (planner.global_tables: gate_glob).
+ * Either may be NULL when the corresponding rollout flavour is not used (that flavour then returns HMPC_ERR_BAD_ARG).
+ * HMPC_GATE_SCHEDULE requires mpc_factor <= 32.  The MPC itself is unchanged: it keeps planning on the schedule. */
+enum { HMPC_GATE_OFF = 0, HMPC_GATE_SCHEDULE = 1, HMPC_GATE_DETECT = 2 };
+int hmpc_set_contact_gate(hmpc_handle* h, int mode, const uint32_t* gate_tab, const uint32_t* gate_glob_host, int max_tick,
+                          double leg_max);
+
 /* Per-hopper statistics of the most recent hmpc_solve (or accumulated over the most recent
  * hmpc_rollout): nfac [B] = matrix factorisations, path [B] = HMPC_PATH_* of the last solve,
  * n_infeasible [B] = ticks flagged HMPC_PRIMAL_INFEASIBLE (device int32 arrays), flops [B] = algorithmic

@@ -68,11 +68,21 @@ class OracleMpc:
         return self._solve(x_in, x_ref_in, pf, C, x_guess)
 
 
+def leg_reaches(X, pf, prm, leg_max):
+    """HMPC_GATE_DETECT: the leg vector of dynamics_ct, r = rh + R(q)'(pf - p) (robotrunner.py:143), is no longer than
+    leg_max."""
+    Rm = ho.quat_rotm(X[3:7])
+    r = prm.rh + Rm.T @ (np.asarray(pf, float) - X[0:3])
+    return float(r @ r) <= leg_max * leg_max
+
+
 def closed_loop(prm: ho.Params, X0, xref_tab, pf_tab, C, pf_switch, n_ticks, solver="exact", osqp_opts=None,
-                u_perturb=None, sqp_sweeps=1):
+                u_perturb=None, sqp_sweeps=1, gate=None, leg_max=None):
     """X0 (13,), xref_tab (T+N,12), pf_tab (T+N+1,3), C (T,N), pf_switch (T,).  Returns X_log
     (n_ticks+1,13), U_log (n_ticks,6).  ``u_perturb(t)`` optionally adds a perturbation to U[0] (used by
-    the sensitivity study that justifies the closed-loop tolerance)."""
+    the sensitivity study that justifies the closed-loop tolerance).  ``gate`` (T, mpc_factor) 0/1: the
+    scheduled contact s at every simulator step, applied as the reference's commented-out factor; ``leg_max``:
+    contact detected from the leg reach instead (product extension, include/hmpc.h HMPC_GATE_*)."""
     mpc = OracleMpc(prm, solver, osqp_opts, sqp_sweeps)
     X = np.array(X0, float)
     N = prm.N
@@ -86,7 +96,12 @@ def closed_loop(prm: ho.Params, X0, xref_tab, pf_tab, C, pf_switch, n_ticks, sol
             u0 = u0 + u_perturb(t)
         for i in range(prm.mpc_factor):
             pf = pf_tab[t] if i < pf_switch[t] else pf_tab[t + 1]
-            X = ho.rk4_normalized(X, u0, pf, prm)
+            s = 1.0
+            if gate is not None:                    # `f_hist[k, :] = U[0, :] * s` (robotrunner.py:111, commented out there)
+                s = float(gate[t, i] != 0)
+            elif leg_max is not None:
+                s = 1.0 if leg_reaches(X, pf, prm, leg_max) else 0.0
+            X = ho.rk4_normalized(X, u0 * s, pf, prm)
         X_log[t + 1] = X
         U_log[t] = u0
     return X_log, U_log

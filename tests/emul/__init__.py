@@ -127,6 +127,19 @@ class EmulMpc:
         return (X, x) if convert else X
 
 
+    def sim_tick(self, X, U, pfa, pfb, sw=None, gate_mode=0, bits=None, leg_max=0.0):
+        """One MPC tick of the simulator (hmpc_sim.cuh: sim_tick) with the contact gate; returns the new X (13,B)."""
+        X = np.ascontiguousarray(X, float).copy()
+        sw = None if sw is None else np.ascontiguousarray(sw, np.uint8)
+        bits = None if bits is None else np.ascontiguousarray(bits, np.uint32)
+        lib = load()
+        lib.emul_sim_tick.argtypes = [C.c_void_p] * 6 + [C.c_int, C.c_void_p, C.c_double]
+        rc = lib.emul_sim_tick(C.byref(self.cfg), _p(X), _p(np.ascontiguousarray(U, float)), _p(np.ascontiguousarray(pfa, float)),
+                               _p(np.ascontiguousarray(pfb, float)), _p(sw), int(gate_mode), _p(bits), float(leg_max))
+        assert rc == 0
+        return X
+
+
 def plan_tables(x0, xf, curve, off, gt, N, n_ticks, tick0=0, mpc_factor=20, dt=1e-3):
     """The device planner (csrc/hmpc_plan.cuh) run on the host: same outputs as BatchMpc.plan_tables (numpy)."""
     x0 = np.ascontiguousarray(x0, float); xf = np.ascontiguousarray(xf, float)

@@ -264,4 +264,25 @@ int emul_rk4(const hmpc_config* cfg, double* X, const double* U, const double* p
     return 0;
 }
 
+// One MPC tick of the simulator with the contact gate (hmpc_sim.cuh: sim_tick), all pointers HOST memory:
+// X [13][B] in/out, U [6][B], pfa / pfb [3][B], sw [B] uint8 (may be null), bits [B] uint32 (may be null).
+int emul_sim_tick(const hmpc_config* cfg, double* X, const double* U, const double* pfa, const double* pfb, const uint8_t* sw,
+                  int gate_mode, const uint32_t* bits, double leg_max) {
+    SimConst s;
+    s.m = cfg->m; s.g = cfg->g; s.h = cfg->sim_dt;
+    for (int i = 0; i < 9; ++i) { s.J[i] = cfg->J[i]; s.Jinv[i] = cfg->Jinv[i]; }
+    for (int i = 0; i < 3; ++i) s.rh[i] = cfg->rh[i];
+    const int B = cfg->batch;
+    for (int b = 0; b < B; ++b) {
+        double Xl[13], Ul[6], pa[3], pb[3];
+        for (int i = 0; i < 13; ++i) Xl[i] = X[(size_t)i * B + b];
+        for (int i = 0; i < 6; ++i) Ul[i] = U[(size_t)i * B + b];
+        for (int i = 0; i < 3; ++i) { pa[i] = pfa[(size_t)i * B + b]; pb[i] = pfb[(size_t)i * B + b]; }
+        sim_tick(s, gate_mode, bits ? bits[b] : 0xffffffffu, leg_max * leg_max, Xl, Ul, pa, pb, sw ? (int)sw[b] : cfg->mpc_factor,
+                 cfg->mpc_factor, nullptr, (size_t)B, b);
+        for (int i = 0; i < 13; ++i) X[(size_t)i * B + b] = Xl[i];
+    }
+    return 0;
+}
+
 }  // extern "C"

@@ -158,3 +158,62 @@ def test_admm_mode_matches_numpy_port(dyn):
             else:
                 assert st[b] == info["status"]
                 np.testing.assert_allclose(U[:, :, b].reshape(-1), x, rtol=1e-7, atol=1e-7)
+
+
+def test_contact_gate_sim_tick_matches_oracle():
+    """hmpc_sim.cuh sim_tick with the contact gate (include/hmpc.h HMPC_GATE_*): the scheduled gate is the reference's
+    commented-out `U[0, :] * s` (robotrunner.py:111) step by step; the detected gate tests the leg vector of
+    dynamics_ct (robotrunner.py:143) against leg_max before every step."""
+    from oracle.closed_loop import leg_reaches
+    B, N = 5, 10
+    sc = scenarios.make_batch(B, N=N, n_ticks=4, seed=3)
+    em = EmulMpc(B, N=N)
+    rng = np.random.default_rng(0)
+    U = rng.normal(size=(6, B)) * 10
+    U[2] += 70
+    bits = np.array([0xfffff, 0x003ff, 0xffc00, 0x0, 0x5a5a5], np.uint32)
+    sw = np.array([20, 5, 20, 12, 0], np.uint8)
+    pfa, pfb = sc["pf_tab"][0], sc["pf_tab"][1]
+    prm = ho.Params(N=N)
+    X = sc["X0"].copy()
+    X[2] = np.array([0.30, 0.36, 0.395, 0.41, 0.45])
+    toggled = 0
+    for mode, lm in ((0, 0.0), (1, 0.0), (2, 0.40)):
+        Xn = em.sim_tick(X, U, pfa, pfb, sw, mode, bits, lm)
+        for b in range(B):
+            Xo, ons = X[:, b].copy(), []
+            for i in range(20):
+                pf = pfa[:, b] if i < sw[b] else pfb[:, b]
+                s = 1.0 if mode == 0 else (float((int(bits[b]) >> i) & 1) if mode == 1 else float(leg_reaches(Xo, pf, prm, lm)))
+                ons.append(s)
+                Xo = ho.rk4_normalized(Xo, U[:, b] * s, pf, prm)
+            np.testing.assert_allclose(Xn[:, b], Xo, rtol=1e-13, atol=1e-13)
+            toggled += mode == 2 and 0 < sum(ons) < 20
+    assert toggled >= 1            # the detected gate switched inside a tick for at least one hopper
+
+
+def test_closed_loop_with_scheduled_gate_matches_oracle():
+    """Closed loop with HMPC_GATE_SCHEDULE: emulated solver + gated simulator tick vs the oracle loop with the same gate."""
+    from oracle.closed_loop import closed_loop
+    B, N, n_ticks = 3, 10, 14
+    sc = scenarios.make_batch(B, N=N, n_ticks=n_ticks, seed=12)
+    em = EmulMpc(B, N=N)
+    em.set_gains(sc["Qdiag"], sc["Rdiag"])
+    X = sc["X0"].copy()
+    Xl = [X.copy()]
+    for t in range(n_ticks):
+        _, x_in = em.rk4(X, np.zeros((6, B)), np.zeros((3, B)), 0, convert=True)
+        U, Xs, st, it, nf, pa = em.solve(x_in, sc["xref_tab"][t:t + N], sc["pf_tab"][t:t + N], sc["C_tab"][t], t == 0)
+        assert np.all(st == 0)
+        X = em.sim_tick(X, U[0], sc["pf_tab"][t], sc["pf_tab"][t + 1], sc["pf_switch"][t], 1, sc["gate_tab"][t])
+        Xl.append(X.copy())
+    Xl = np.stack(Xl)
+    gated = 0
+    for b in range(B):
+        prm = ho.Params(N=N, Qdiag=sc["Qdiag"][:, b].copy(), Rdiag=sc["Rdiag"][:, b].copy())
+        gate = (sc["gate_tab"][:n_ticks, b, None].astype(np.int64) >> np.arange(20)) & 1
+        gated += int((gate == 0).sum())
+        Xo, Uo = closed_loop(prm, sc["X0"][:, b], sc["xref_tab"][:, :, b], sc["pf_tab"][:, :, b], sc["C"][:, b],
+                             sc["pf_switch"][:, b], n_ticks, gate=gate)
+        np.testing.assert_allclose(Xl[:, :, b], Xo, rtol=0, atol=2e-9)
+    assert gated > 0

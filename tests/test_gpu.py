@@ -9,7 +9,7 @@ from hopper_mpc_inertial_b200 import _lib, scenarios
 from oracle import device_port as dp
 from oracle import hopper_oracle as ho
 from oracle import qp_solvers as qs
-from oracle.closed_loop import OracleMpc, closed_loop
+from oracle.closed_loop import OracleMpc, QPFailed, closed_loop
 from tests.conftest import golden, normalised_oracle_qp, u_tol
 
 pytestmark = pytest.mark.gpu
@@ -609,3 +609,60 @@ def test_sharded_run_equals_unsharded():
         parts.append(run(sc, r if ndev >= 2 else 0))
     assert np.array_equal(np.concatenate([p[0] for p in parts], axis=-1), X_full)
     assert np.array_equal(np.concatenate([p[1] for p in parts], axis=-1), U_full)
+
+
+def test_contact_gate_matches_oracle_and_both_rollout_flavours_agree():
+    """SURVEY 8 row f4 (second half): the contact gate of the applied control.  HMPC_GATE_SCHEDULE is the reference's
+    commented-out `f_hist[k, :] = U[0, :] * s` (robotrunner.py:99,111) at 1 kHz; HMPC_GATE_DETECT gates on the leg reach.
+    Both against the oracle loop with the same gate; the planned flavour (common-clock masks + tick offsets) is
+    bit-identical to the table flavour; the default stays ungated."""
+    from hopper_mpc_inertial_b200 import planner
+    B, N, n_ticks = 6, 10, 16
+    sc = scenarios.make_batch(B, N=N, n_ticks=n_ticks, seed=12)
+    tabs = (T(sc["xref_tab"]), T(sc["pf_tab"]), cb64(sc["C_tab"]), T(sc["pf_switch"]))
+    gate_bits = (sc["gate_tab"][:n_ticks, :, None].astype(np.int64) >> np.arange(20)) & 1        # (T,B,20)
+    assert (gate_bits == 0).any() and (gate_bits == 1).any()
+
+    def run(mode, planned=False, **kw):
+        bm = mk(B, "3f", N)
+        bm.set_gains(T(sc["Qdiag"]), T(sc["Rdiag"]))
+        X = T(sc["X0"]).clone()
+        if planned:
+            _plan_set(bm, sc)
+            bm.set_contact_gate(mode, gate_glob=planner.global_tables(**sc["plan"]["global_args"])["gate_glob"], **kw)
+            out = bm.rollout_planned(X, 0, n_ticks, True, log=True)
+        else:
+            bm.set_contact_gate(mode, gate_tab=T(sc["gate_tab"].view(np.int32)) if mode == "schedule" else None, **kw)
+            out = bm.rollout(X, *tabs, 0, n_ticks, True, log=True)
+        torch.cuda.synchronize()
+        return out["X_log"].cpu().numpy(), out["U_log"].cpu().numpy(), out["status"].cpu().numpy(), bm
+
+    Xoff, Uoff, Soff, _ = run("off")
+    Xs, Us, Ss, bm = run("schedule")
+    Xp, Up, Sp, _ = run("schedule", planned=True)
+    Xd, Ud, Sd, _ = run("detect", leg_max=0.45)
+    assert np.array_equal(Xs, Xp) and np.array_equal(Us, Up) and np.array_equal(Ss, Sp)
+    assert np.abs(Xs - Xoff).max() > 1e-3 and np.abs(Xd - Xoff).max() > 1e-3          # the gates do change the run
+    checked = 0
+    for b in range(B):
+        p = ho.Params(N=N, Qdiag=sc["Qdiag"][:, b].copy(), Rdiag=sc["Rdiag"][:, b].copy())
+        args = (p, sc["X0"][:, b], sc["xref_tab"][:, :, b], sc["pf_tab"][:, :, b], sc["C"][:, b], sc["pf_switch"][:, b], n_ticks)
+        for Xg, Ug, Sg, kw in ((Xoff, Uoff, Soff, {}), (Xs, Us, Ss, dict(gate=gate_bits[:, b])), (Xd, Ud, Sd, dict(leg_max=0.45))):
+            try:
+                Xo, Uo = closed_loop(*args, **kw)
+            except QPFailed:                       # a gated hopper may fall: the reference would raise, the device flags it
+                assert Sg[b] == _lib.STATUS_INFEASIBLE
+                continue
+            assert Sg[b] == 0
+            assert np.all(np.abs(Ug[:, :, b] - Uo) <= 10 * u_tol(Uo)), (b, kw.keys())
+            np.testing.assert_allclose(Xg[:, :, b], Xo, rtol=0, atol=1e-6)
+            checked += 1
+    assert checked >= 3 * B - 2
+    # error behaviour: a scheduled gate needs the masks of the rollout flavour that is used
+    with pytest.raises(_lib.HmpcError):
+        bm.set_contact_gate("schedule")
+    bm.set_contact_gate("schedule", gate_glob=np.ones(4, np.uint32))
+    with pytest.raises(_lib.HmpcError):
+        bm.rollout(T(sc["X0"]).clone(), *tabs, 0, 2, True)
+    with pytest.raises(_lib.HmpcError):
+        bm.set_contact_gate("detect", leg_max=0.0)

@@ -115,3 +115,24 @@ def test_device_planner_source_is_bit_identical_to_the_numpy_planner(dyn, N, n_t
     # tables=False builds the same initial states without the tables
     sc2 = scenarios.make_batch(96, N=N, n_ticks=n_ticks, seed=5, dyn=dyn, tables=False)
     assert np.array_equal(sc2["X0"], sc["X0"]) and "pf_tab" not in sc2
+
+
+def test_gate_masks_follow_the_run_clock():
+    """planner.gate_masks: bit i of tick j = gait_scheduler at the reference's run-loop time of simulator step
+    20 j + i (robotrunner.py:97-99: t = t + dt, s = gait_scheduler(t, t0)); per-hopper tables index the common clock."""
+    n_ticks, mf, dt, t_start = 90, 20, 1e-3, 0.2
+    gm = planner.gate_masks(n_ticks, mf, dt, t_start)
+    assert gm.dtype == np.uint32
+    t = t_start
+    prm = ho.Params()
+    for j in range(n_ticks):
+        for i in range(mf):
+            t = t + dt
+            assert ((int(gm[j]) >> i) & 1) == int(ho.gait_scheduler(t, 0, prm)), (j, i)
+    assert 0 < np.count_nonzero(gm == 0) and np.count_nonzero(gm == (1 << mf) - 1) > 0      # whole swing / stance ticks
+    assert np.any((gm != 0) & (gm != (1 << mf) - 1))                                        # ticks with a contact switch inside
+    sc = scenarios.make_batch(6, N=10, n_ticks=12, seed=4)
+    gt = planner.global_tables(**sc["plan"]["global_args"])
+    for b in range(6):
+        off = int(sc["tick_offset"][b])
+        assert np.array_equal(sc["gate_tab"][:, b], gt["gate_glob"][off:off + 12])
