@@ -495,6 +495,14 @@ def run_b200(args):
     roofline_hbm = {"bound": "hbm", "kernel": kname, "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                     "peak_source": hbm_src, "algorithmic_bytes_per_launch": bytes_tick * B,
                     "note": "reported for completeness: arithmetic intensity >> machine balance, HBM does not bind"}
+    # sim_kernel (K3): one thread per hopper, 20 RK4 steps in registers -- the one kernel whose bound is FP64 arithmetic.
+    # Algorithmic FLOPs: SURVEY 8(d) F_rk4 = mpc_factor x 1300 per hopper-tick.
+    sim_s = sim_ms * 1e-3 / max(nt, 1)
+    sim_flops = 20 * 1300.0 * B
+    roofline_sim = {"bound": "fp64", "kernel": "sim_kernel", "achieved": sim_flops / sim_s / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                    "frac": (sim_flops / sim_s / 1e12 / fp64_peak) if fp64_peak else None, "avg_launch_ms": sim_s * 1e3,
+                    "algorithmic_flops_per_hopper_tick": 20 * 1300.0, "share_of_step": sim_ms / ms,
+                    "ncu": "profiles/r2ab_sim_kernel_ncu.txt (FP64 pipe active cycles and DFMA issue rate of the same kernel)"}
     working_set_mb = B * (bytes_tick + 13 * 16 + 15 * 8 * 2) / 1e6
     cache_note = ("inputs larger than L2 (per-tick working set %.0f MB per GPU > 126 MB L2)" % working_set_mb) if working_set_mb > 126 \
         else ("per-tick working set %.0f MB per GPU fits the 126 MB L2; every tick reads new reference rows and rewrites the "
@@ -522,7 +530,7 @@ def run_b200(args):
                                            "uploads host-built windows every tick"},
             "gpu_launches": int(launches_all),
             "clocks": clocks, "log_gather": gather_info,
-            "roofline": roofline, "roofline_hbm": roofline_hbm, "p50_qp_solve_us": p50,
+            "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_sim_kernel": roofline_sim, "p50_qp_solve_us": p50,
             "solver_stats": {"solved_exact_frac": solved, "infeasible_ticks": int(inf_ticks),
                              "ipm_iters_per_tick": float(it.mean() / K), "factorisations_per_tick": float(nf.mean() / K),
                              "warm_path_frac_last_tick": float(np.mean(pa == 1)),

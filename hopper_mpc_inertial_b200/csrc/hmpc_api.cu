@@ -421,7 +421,8 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
     // SM beat one 223-register CTA with shared-memory matrices (N = 20, 65536 hoppers: 1.91 M vs 1.51 M steps/s,
     // profiles/README.md); HMPC_WIDE_SMEM=1 selects the shared-memory kernel
     if (n > 64) { const char* ev = getenv("HMPC_WIDE_SMEM"); if (!(ev && atoi(ev))) h->mats_in_smem = false; }
-    h->mpc_smem = vec_bytes + (h->mats_in_smem ? mat_bytes : 0);
+    const size_t vec_bytes_ws = ((hmpc::work_vec_doubles((int)N, hmpc::mv_in_workspace((int)N)) + 1) & ~(size_t)1) * 8;
+    h->mpc_smem = h->mats_in_smem ? vec_bytes + mat_bytes : vec_bytes_ws;
     // occupancy experiments (profiles/README.md): HMPC_SMEM_PAD=<bytes> pads the dynamic shared memory request
     if (const char* pad = getenv("HMPC_SMEM_PAD")) h->mpc_smem += (size_t)atol(pad);
     if (h->mpc_smem > smem_cap) { hmpc_destroy(h); return fail(HMPC_ERR_UNSUPPORTED, "horizon too large for shared memory"); }
@@ -436,8 +437,11 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
         // profiles/README.md): four 128-thread CTAs (128 registers; N = 20: 2.10 M steps/s), two 256-thread CTAs
         // (128 registers; N = 20: 1.93 M, N = 40: 0.56 M), one 256-thread CTA (235 registers; N = 40: 0.42 M).
         // More independent hoppers per SM win because each hopper's pivot chain leaves most of its warps waiting.
-        h->wide_ctas = 4;
-        if (const char* ev = getenv("HMPC_WIDE_CTAS")) { const int v = atoi(ev); h->wide_ctas = (v == 1 || v == 2) ? v : 4; }
+        // Four CTAs per SM only while their workspaces stay L2-resident (N <= 22 on a 126 MB L2; N = 40 with four
+        // 128-thread CTAs streams its factors from HBM: 0.43 M instead of 0.56 M steps/s).
+        const size_t ws_cta = mat_bytes + hmpc::ws_mv_doubles((int)N) * 8;
+        h->wide_ctas = ((size_t)h->sm_count * 4 * ws_cta <= (size_t)prop.l2CacheSize) ? 4 : 2;
+        if (const char* ev = getenv("HMPC_WIDE_CTAS")) { const int v = atoi(ev); if (v == 1 || v == 2 || v == 4) h->wide_ctas = v; }
         per_sm = std::max<int>(1, std::min<int>(h->wide_ctas, (int)((size_t)prop.sharedMemPerMultiprocessor / (h->mpc_smem + 1024))));
         if (per_sm < h->wide_ctas) h->wide_ctas = per_sm >= 2 ? 2 : 1;
         if (h->wide_ctas == 4) h->mpc_threads = 128;
@@ -445,7 +449,7 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
     }
     h->mpc_grid = (int)std::min<size_t>(B, (size_t)h->sm_count * per_sm);
     if (!h->mats_in_smem) {
-        if ((e = cudaMalloc((void**)&h->ws, (size_t)h->mpc_grid * mat_bytes)) != cudaSuccess) {
+        if ((e = cudaMalloc((void**)&h->ws, (size_t)h->mpc_grid * (mat_bytes + hmpc::ws_mv_doubles((int)N) * 8))) != cudaSuccess) {
             hmpc_destroy(h);
             return fail(HMPC_ERR_ALLOC, std::string("cudaMalloc workspace: ") + cudaGetErrorString(e));
         }

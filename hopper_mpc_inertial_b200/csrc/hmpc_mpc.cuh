@@ -14,11 +14,17 @@ namespace hmpc {
 // the factor is provably a shared-memory access (LDS/STS instead of generic loads).
 template <bool SMEM_MATS>
 __device__ inline void setup_work(Work& w, const QpConst& c, double* smem, double* ws, int fsize = 8) {
-    carve(w, smem, c.N);
     const size_t n = 6 * (size_t)c.N;
     double* mat;
-    if (SMEM_MATS) mat = smem + ((work_vec_doubles(c.N) + 1) & ~(size_t)1);
-    else mat = ws + (size_t)blockIdx.x * mat_doubles(c.N, fsize);
+    if (SMEM_MATS) {
+        carve(w, smem, c.N);
+        mat = smem + ((work_vec_doubles(c.N) + 1) & ~(size_t)1);
+    } else {
+        // per-CTA workspace slice: matrices, then (long horizons) the interior point's m-vectors
+        const size_t md = mat_doubles(c.N, fsize);
+        mat = ws + (size_t)blockIdx.x * (md + ws_mv_doubles(c.N));
+        carve(w, smem, c.N, mv_in_workspace(c.N) ? mat + md : nullptr);
+    }
     w.H = mat; w.Lm = mat + n * (n + 1) / 2;
 }
 

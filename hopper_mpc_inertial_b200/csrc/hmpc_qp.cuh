@@ -128,21 +128,30 @@ __host__ __device__ inline size_t mat_doubles(int N, int fsize = 8) {
 }
 // compact-system vectors: padded to whole tiles for the tiled path
 __host__ __device__ inline int kkt_vec(int N) { return kkt_max(N) + (6 * N > 64 ? 8 : 0); }
-__host__ __device__ inline size_t work_vec_doubles(int N) {
+// Longest horizons (N >= 58, the reference's N = 60 among them): with every vector in shared memory a CTA needs more
+// than half of the SM's 228 KB, so the nine m-vectors only the interior point (and, aliased, the condensing) uses move
+// to the L2 workspace next to the matrices -- 47 KB at N = 60, which buys the second resident CTA (65536 hoppers:
+// 103 k -> 139 k steps/s; at N = 40, where two CTAs fit anyway, the same move costs 5 %).  The two m-vectors of the
+// active-set refinement stay in shared memory.
+constexpr int kNumMVecShared = 2;
+__host__ __device__ inline bool mv_in_workspace(int N) { return N > 57; }
+__host__ __device__ inline size_t ws_mv_doubles(int N) { return mv_in_workspace(N) ? (size_t)(kNumMVec - kNumMVecShared) * 11 * N : 0; }
+__host__ __device__ inline size_t work_vec_doubles(int N, bool mv_ws = false) {
     const int n = 6 * N, m = 11 * N;
     size_t d = 0;
     // linearisation (cfree, gp, pfw, Qd, Rd, PC, PS alias the last three m-vectors: dead once condense() returns)
     d += 2 * N + 9 * N + 18 * N + 12 + 12 * (N + 1) + N;
     d += n + 2 * m;           // g lo hi
     d += 3 * n + (N > 14 ? N - 14 : 0) + 4 * kkt_vec(N);   // x xp tmp(+pad) | xt rhs sc dinv
-    d += kNumMVec * m;
+    d += (mv_ws ? kNumMVecShared : kNumMVec) * m;
     d += 48;                  // red
     d += (n + kkt_max(N) + 4 + 1) / 2;          // int32: idx grow cnt
     d += (2 * n + 2 * m + N + 7) / 8;           // int8: fixed pin code side stance
     return d;
 }
 
-__device__ inline void carve(Work& w, double* base, int N) {
+// mvext: null, or where the m-vectors beyond the first kNumMVecShared live (workspace, ws_mv_doubles(N))
+__device__ inline void carve(Work& w, double* base, int N, double* mvext = nullptr) {
     const int n = 6 * N, m = 11 * N, kk = kkt_max(N);
     double* p = base;
     auto take = [&](size_t k) { double* r = p; p += k; return r; };
@@ -154,7 +163,10 @@ __device__ inline void carve(Work& w, double* base, int N) {
     // tmp | xt | rhs | sc are contiguous: together they are the 4-column panel scratch of LinSys::factor
     w.x = take(n); w.xp = take(n); w.tmp = take(n + (N > 14 ? N - 14 : 0));   // pad: 4 (kkt_max - 4) panel entries
     { const int kv = kkt_vec(N); w.xt = take(kv); w.rhs = take(kv); w.sc = take(kv); w.dinv = take(kv); }
-    for (int i = 0; i < kNumMVec; ++i) w.mv[i] = take(m);
+    for (int i = 0; i < kNumMVec; ++i) {
+        if (mvext && i >= kNumMVecShared) { w.mv[i] = mvext; mvext += m; }
+        else w.mv[i] = take(m);
+    }
     // condense-only scratch on top of the solvers' last three m-vectors: 12(N+1) + 4N + 3N + 18 + 2(N+1) <= 33N
     w.cfree = w.mv[kNumMVec - 3]; w.gp = w.cfree + 12 * (N + 1); w.pfw = w.gp + 4 * N;
     w.Qd = w.pfw + 3 * N; w.Rd = w.Qd + 12; w.PC = w.Rd + 6; w.PS = w.PC + (N + 1);
@@ -1418,7 +1430,22 @@ __device__ inline SolveInfo admm_solve(const QpConst& c, Work& w, Sys& sys, cons
     for (int r = tid; r < m; r += T) z[r] = A.row(r, w.x);     // OSQP: z = A x at a (warm or cold) start, no projection
     __syncthreads();
     info.nfac = 1;
-    if (sys.factor(A, rv, sigma, 0.0, w.tmp)) { info.status = ST_NON_FINITE; return info; }
+    // N <= 10 kernels: the ADMM system (free variables only, order nF <= 6N, positive definite) fits the packed factor
+    // storage as 8x8 tiles, so the factorisation and -- every iteration -- the substitutions run on the FP64 tensor
+    // core with all warps of the CTA (factor_tiled / solve_tiled) instead of the one-warp substitution chain
+    // (profiles/README.md: 18 k cycles per solve).  The polish that follows uses the packed layout again.
+    const int tiled_keep = sys.tiled;
+    double* fscr = w.tmp;
+#ifndef HMPC_HOST_EMUL
+    {
+        const int nt = (nF + 7) >> 3, kk = kkt_max(N);
+        if (sizeof(typename Sys::real) == 8 && !sys.tiled && T >= 64 && kkt_vec(N) >= 64 && nt * (nt + 1) / 2 * 64 <= kk * (kk + 1) / 2) {
+            sys.tiled = 1;
+            fscr = w.xt;            // one 64-double tile of scratch; xt is dead while a factorisation runs
+        }
+    }
+#endif
+    if (sys.factor(A, rv, sigma, 0.0, fscr)) { sys.tiled = tiled_keep; info.status = ST_NON_FINITE; return info; }
     const int last_it = c.max_iter;
     int next_check = (c.mode == 1) ? last_it : min(c.first_check, last_it);
     for (int it = 1; it <= last_it; ++it) {
@@ -1472,10 +1499,11 @@ __device__ inline SolveInfo admm_solve(const QpConst& c, Work& w, Sys& sys, cons
                 rho = rn;
                 set_rho(rho);
                 ++info.nfac;
-                if (sys.factor(A, rv, sigma, 0.0, w.tmp)) { info.status = ST_NON_FINITE; break; }
+                if (sys.factor(A, rv, sigma, 0.0, fscr)) { info.status = ST_NON_FINITE; break; }
             }
         }
     }
+    sys.tiled = tiled_keep;
     for (int r = tid; r < m; r += T) {
         const double zz = z[r], yy = y[r];
         w.code[r] = ((zz - w.lo[r]) < -yy) ? -1 : (((w.hi[r] - zz) < yy) ? 1 : 0);

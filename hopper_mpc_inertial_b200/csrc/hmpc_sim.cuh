@@ -114,6 +114,19 @@ __device__ __forceinline__ void dynamics_ct(const SimConst& c, const double X[13
     mat3_vec(c.Jinv, t, &dX[10]);
 }
 
+__device__ __forceinline__ double sim_rsqrt(double a) {
+#ifdef HMPC_HOST_EMUL
+    return 1.0 / sqrt(a);
+#else
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    const double h = 0.5 * a;
+    r = fma(r, fma(-h * r, r, 0.5), r);
+    r = fma(r, fma(-h * r, r, 0.5), r);
+    return r;
+#endif
+}
+
 __device__ __forceinline__ void rk4_step(const SimConst& c, double X[13], const double U[6],
                                          const double pf[3]) {
     double f1[13], f2[13], f3[13], f4[13], Xt[13];
@@ -130,8 +143,10 @@ __device__ __forceinline__ void rk4_step(const SimConst& c, double X[13], const 
     dynamics_ct(c, Xt, U, pf, f4);
 #pragma unroll
     for (int i = 0; i < 13; ++i) X[i] = X[i] + (h / 6.0) * (f1[i] + 2.0 * f2[i] + 2.0 * f3[i] + f4[i]);
-    const double nq = sqrt(X[3] * X[3] + X[4] * X[4] + X[5] * X[5] + X[6] * X[6]);
-    X[3] /= nq; X[4] /= nq; X[5] /= nq; X[6] /= nq;
+    // q / |q| (robotrunner.py:163) as q * rsqrt(q.q): one MUFU seed + two Newton steps instead of a square root and
+    // four divisions (ncu: that line held 23 % of the kernel's stall samples); within 1-2 ulp of the divided form
+    const double iq = sim_rsqrt(X[3] * X[3] + X[4] * X[4] + X[5] * X[5] + X[6] * X[6]);
+    X[3] *= iq; X[4] *= iq; X[5] *= iq; X[6] *= iq;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1,5 +1,5 @@
 """Summarise an ncu report (run HERE, no GPU needed):  python tools/ncu_summary.py gpurun_out/prof.ncu-rep TAG BATCH
-Writes profiles/<TAG>_mpc_kernel_ncu.txt (key metrics + stall samples per CUDA source line) and updates
+Writes profiles/<TAG>_<KERNEL>_ncu.txt (KERNEL = optional 4th argument, default mpc_kernel) (key metrics + stall samples per CUDA source line) and updates
 profiles/ncu_summary.json (DRAM bytes per hopper of mpc_kernel, read by bench.py for roofline.traffic)."""
 import csv
 import json
@@ -9,6 +9,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep, tag, batch = sys.argv[1], sys.argv[2], int(sys.argv[3])
+kname = sys.argv[4] if len(sys.argv) > 4 else "mpc_kernel"      # output file suffix; only "mpc_kernel" updates ncu_summary.json
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, data = rows[0], rows[1], rows[2:]
@@ -20,7 +21,7 @@ keys = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed",
         "sm__sass_thread_inst_executed_op_dfma_pred_on.sum.peak_sustained", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__cycles_elapsed.avg", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]
-lines = [f"# ncu --set full --clock-control none --import-source on -k regex:mpc_kernel  ({rep}); batch {batch} hoppers per launch"]
+lines = [f"# ncu --set full --clock-control none --import-source on -k regex:{kname}  ({rep}); batch {batch} hoppers per launch"]
 vals = {}
 for k in keys:
     if k in hdr:
@@ -69,9 +70,9 @@ lines.append("# warp stall reasons (share of samples): " + ", ".join(f"{k[6:]} {
 lines.append("# stall samples per CUDA source line (top 25)")
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:25]:
     lines.append(f"{k[0]}:{k[1]:4d} samples {100 * a[0] / tot:5.1f}% inst {100 * a[1] / toti:5.1f}%  {a[2]}")
-out = os.path.join(ROOT, "profiles", f"{tag}_mpc_kernel_ncu.txt")
+out = os.path.join(ROOT, "profiles", f"{tag}_{kname}_ncu.txt")
 open(out, "w").write("\n".join(lines) + "\n")
-js = os.path.join(ROOT, "profiles", "ncu_summary.json")
+js = os.path.join(ROOT, "profiles", "ncu_summary.json") if kname == "mpc_kernel" else os.devnull
 json.dump({"source": os.path.basename(out), "capture_batch": batch, "mpc_kernel_dram_bytes_per_hopper": dram_per_hopper,
            "mpc_kernel_dram_bytes_per_launch_at_capture": sum(per_launch) / len(per_launch)}, open(js, "w"), indent=1)
 print(open(out).read())
