@@ -79,6 +79,7 @@ struct hmpc_handle {
     int64_t launches = 0;
     // warp-per-hopper warm path (hmpc_warp.cuh): geometry, per-warp Hessian workspace, deferral list
     bool warp_ok = false;
+    bool warp_admm = false;      // solver = ADMM: the warp kernel is mpc_warp_admm_kernel
     int warp_rounds = 0, warp_group = 0;
     int warp_grid = 0, warp_wpc = 1, warp_kcap = 0, warp_wdoubles = 0, warp_per_sm = 0, warp_regs = 0;
     size_t warp_smem = 0, pstride = 0;
@@ -469,7 +470,32 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
         return fail(HMPC_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     }
     // ---- warp-per-hopper warm path: cut the SM's shared memory into per-warp slices ----
-    if (hmpc::warp_path_applies(*cfg, 0)) {
+    if (hmpc::warp_path_applies(*cfg, 0) && cfg->solver == HMPC_SOLVER_ADMM) {
+        // ADMM mode: free-running warps, one CTA per SM, as many warps as the larger slices (z, y, rho behind the
+        // exact path's slice) allow among the instantiated CTA sizes
+        h->warp_kcap = hmpc::warp_kcap(*cfg);
+        h->warp_wdoubles = (int)(hmpc::warp_work_doubles((int)N, h->warp_kcap) + hmpc::warp_admm_doubles((int)N));
+        const size_t wbytes = (size_t)h->warp_wdoubles * 8;
+        int wpc = 0;
+        for (int cand : {10, 6}) if (!wpc && hmpc::warp_admm_wpc_supported(cand) && wbytes * cand + 1024 <= smem_cap) wpc = cand;
+        if (wpc) {
+            h->warp_wpc = wpc; h->warp_per_sm = wpc; h->warp_smem = wbytes * wpc; h->warp_rounds = 0; h->warp_group = wpc;
+            h->warp_grid = (int)std::min<size_t>(((size_t)B + wpc - 1) / wpc, (size_t)h->sm_count);
+            h->pstride = hmpc::prep_stride((int)N);
+            if ((e = cudaMalloc((void**)&h->prep, B * h->pstride * 8)) != cudaSuccess ||
+                (e = cudaMalloc((void**)&h->prep_flag, B * 4)) != cudaSuccess) {
+                hmpc_destroy(h);
+                return fail(HMPC_ERR_ALLOC, std::string("cudaMalloc QP records: ") + cudaGetErrorString(e));
+            }
+            if ((e = hmpc::warp_admm_set_smem(wpc, smem_i)) != cudaSuccess || (e = hmpc::prep_set_smem(smem_i)) != cudaSuccess ||
+                (e = hmpc::warp_admm_regs(wpc, &h->warp_regs)) != cudaSuccess) {
+                hmpc_destroy(h);
+                return fail(HMPC_ERR_CUDA, std::string("cudaFuncSetAttribute (ADMM warp kernel): ") + cudaGetErrorString(e));
+            }
+            h->warp_ok = true;
+            h->warp_admm = true;
+        }
+    } else if (hmpc::warp_path_applies(*cfg, 0)) {
         h->warp_kcap = hmpc::warp_kcap(*cfg);
         h->warp_wdoubles = (int)hmpc::warp_work_doubles((int)N, h->warp_kcap);
         const size_t wbytes = (size_t)h->warp_wdoubles * 8;
@@ -629,7 +655,8 @@ cudaError_t launch_mpc(hmpc_handle* h, const hmpc::QpConst& qc, const hmpc::MpcI
     const bool warp = h->warp_ok && hmpc::warp_path_applies(h->cfg, io.init);
     if (warp) {
         const hmpc::WarpLaunch wl{h->warp_grid, h->warp_wpc, h->warp_rounds, h->warp_group, h->warp_smem, h->stream, h->cfg.batch, h->warp_kcap,
-                                  h->warp_wdoubles, h->prep, h->pstride, h->prep_flag, h->work_ctr, h->defer_list, h->work_ctr + 1};
+                                  h->warp_wdoubles, h->prep, h->pstride, h->prep_flag, h->work_ctr, h->defer_list, h->work_ctr + 1,
+                                  h->warp_admm ? 1 : 0};
         hmpc::prep_launch(wl, qc, io);
         hmpc::warp_launch(wl, qc, io);
         defer_stats_kernel<<<1, 1, 0, h->stream>>>(h->work_ctr, h->n_defer);

@@ -93,6 +93,7 @@ struct WarpLaunch {
     size_t pstride;
     int32_t* flags;         // per-hopper PREP_* flag
     int *work_ctr, *defer_list, *defer_cnt;
+    int admm = 0;           // 1: the ADMM warp kernel (free-running warps, wdoubles includes warp_admm_doubles)
 };
 int prep_wdoubles(int N);
 cudaError_t prep_set_smem(int bytes);
@@ -101,5 +102,8 @@ bool warp_wpc_supported(int rounds, int wpc);
 cudaError_t warp_set_smem(int rounds, int wpc, int bytes);
 cudaError_t warp_regs(int rounds, int wpc, int* regs);
 void warp_launch(const WarpLaunch&, const QpConst&, const MpcIo&);
+bool warp_admm_wpc_supported(int wpc);
+cudaError_t warp_admm_set_smem(int wpc, int bytes);
+cudaError_t warp_admm_regs(int wpc, int* regs);
 
 }  // namespace hmpc

@@ -163,9 +163,10 @@ __device__ inline void carve(Work& w, double* base, int N, double* mvext = nullp
     // tmp | xt | rhs | sc are contiguous: together they are the 4-column panel scratch of LinSys::factor
     w.x = take(n); w.xp = take(n); w.tmp = take(n + (N > 14 ? N - 14 : 0));   // pad: 4 (kkt_max - 4) panel entries
     { const int kv = kkt_vec(N); w.xt = take(kv); w.rhs = take(kv); w.sc = take(kv); w.dinv = take(kv); }
-    for (int i = 0; i < kNumMVec; ++i) {
-        if (mvext && i >= kNumMVecShared) { w.mv[i] = mvext; mvext += m; }
-        else w.mv[i] = take(m);
+    for (int i = 0; i < kNumMVecShared; ++i) w.mv[i] = take(m);
+    {   // the remaining m-vectors hang off ONE base pointer (shared memory or workspace): constant offsets, no pointer table
+        double* mvb = mvext ? mvext : take((size_t)(kNumMVec - kNumMVecShared) * m);
+        for (int i = kNumMVecShared; i < kNumMVec; ++i) w.mv[i] = mvb + (size_t)(i - kNumMVecShared) * m;
     }
     // condense-only scratch on top of the solvers' last three m-vectors: 12(N+1) + 4N + 3N + 18 + 2(N+1) <= 33N
     w.cfree = w.mv[kNumMVec - 3]; w.gp = w.cfree + 12 * (N + 1); w.pfw = w.gp + 4 * N;

@@ -60,6 +60,10 @@ struct WWork {
     int8_t *code, *pin, *fixed, *side, *stance;   // [m] [n] [n] [m] [N]
     int nf, ld;
     int nt_max;                  // tiles per side of the factor storage (kcap / 8)
+    // ADMM mode only: K = H + dadd I + A' diag(wts) A over the system variables (null: K = the KKT system of the
+    // active-set refinement)
+    const double* wts;
+    double dadd;
 };
 
 constexpr int kWarpKcap = 56;                       // 7 tiles of 8: largest order of the compact KKT system
@@ -94,6 +98,8 @@ __host__ __device__ inline size_t prep_hstride(int N) { const size_t l = (6 * (s
 __host__ __device__ inline size_t prep_stride(int N) {
     return prep_hstride(N) + ((6 * (size_t)N + 7) & ~(size_t)7) + (((size_t)N + 7) & ~(size_t)7) + 16;
 }
+// ADMM mode: three more m-vectors per warp (z, y, rho) behind the slice of warp_work_doubles
+__host__ __device__ inline size_t warp_admm_doubles(int N) { return (3 * 11 * (size_t)N + 1) & ~(size_t)1; }
 constexpr int kPrepKcap = 8;      // the prep kernel's per-warp slice: same carve, smallest factor (unused there)
 
 __device__ inline void wcarve(WWork& w, double* base, int N, int kcap) {
@@ -121,6 +127,7 @@ __device__ inline void wcarve(WWork& w, double* base, int N, int kcap) {
     w.pin = reinterpret_cast<int8_t*>(q); q += n;
     w.stance = reinterpret_cast<int8_t*>(q); q += N;
     w.nf = 0; w.ld = 0; w.nt_max = (kcap + 7) / 8;
+    w.wts = nullptr; w.dadd = 0.0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -490,10 +497,20 @@ __device__ inline void wmatvec(WWork& w, int lane) {
 }
 
 // entry (i, j), i >= j, of the compact KKT system in the ordering [nF variables | ng rows]
+// ADMM operator: what A' diag(wts) A + dadd I adds to entry (ci, cj) of the compact Hessian (hmpc_qp.cuh: LinSys::entry)
+__device__ __forceinline__ double wweights(const WWork& w, const AOp& A, int ci, int cj) {
+    const int vi = (int)w.fr[ci], vj = (int)w.fr[cj];
+    double s = A.gram(vi, vj, w.wts);
+    if (ci == cj) s += w.wts[vi] + w.dadd;
+    return s;
+}
 static __device__ __noinline__ double wentry(const QpConst& c, const WWork& w, const AOp& A, int nF, int nk, int i, int j) {
     const int n = 6 * c.N;
     if (i < j || i >= nk) return 0.0;
-    if (i < nF) return w.Hc[(int)w.idx[j] * w.ld + (int)w.idx[i]];
+    if (i < nF) {
+        const double h = w.Hc[(int)w.idx[j] * w.ld + (int)w.idx[i]];
+        return w.wts ? h + wweights(w, A, (int)w.idx[i], (int)w.idx[j]) : h;
+    }
     if (j < nF) return A.coef(n + (int)w.grow[i - nF], (int)w.fr[w.idx[j]]);
     if (i == j) return wrow_coupled(c, w, (int)w.grow[i - nF]) ? 0.0 : -1.0;
     return 0.0;
@@ -543,6 +560,10 @@ __device__ inline int wfactor(const QpConst& c, WWork& w, const AOp& A, int nF, 
             if (8 * I + 8 <= nF) {                                   // variables x variables (H is stored symmetric)
                 const int ri = (int)w.idx[i];
                 k0 = hc0[ri]; k1 = hc1[ri];
+                if (w.wts) {                                         // ADMM operator (i >= j0, j0 + 1 may exceed i: unused)
+                    k0 += wweights(w, A, ri, (int)w.idx[j0]);
+                    k1 += wweights(w, A, ri, (int)w.idx[j0 + 1]);
+                }
             } else {
                 k0 = wentry(c, w, A, nF, nk, i, j0); k1 = wentry(c, w, A, nF, nk, i, j0 + 1);
             }
@@ -864,7 +885,8 @@ __device__ inline int wfetch(const QpConst& c, WWork& w, double* rec, const int3
     return 1;
 }
 // wfinish: roll the verified solution out, store outputs and the handle state of hopper b.
-__device__ inline void wfinish(const QpConst& c, WWork& w, int b, int B, const MpcIo& io, const WInfo& info, int lane) {
+__device__ inline void wfinish(const QpConst& c, WWork& w, int b, int B, const MpcIo& io, const WInfo& info, int lane,
+                            int st = ST_SOLVED, int path = PATH_WARM, int iters = 0) {
     const int N = c.N, n = 6 * N, m = 11 * N;
     const size_t Bs = (size_t)B;
     // ---- roll the solution out (mpc_cvx_euler_3f.py:133,140 dynamics rows) and store ----
@@ -925,15 +947,17 @@ __device__ inline void wfinish(const QpConst& c, WWork& w, int b, int B, const M
     for (int r = lane; r < m; r += 32) io.code[(size_t)r * Bs + b] = w.code[r];
     if (io.U0_out && lane < 6) io.U0_out[(size_t)lane * Bs + b] = u[lane];
     if (lane == 0) {
-        io.valid[b] = 1;
+        io.valid[b] = (st == ST_SOLVED || st == ST_INEXACT) ? 1 : 0;
         if (io.flops) io.flops[b] = (io.accumulate ? io.flops[b] : 0.0) + info.flops;
-        io.st_tick[b] = ST_SOLVED;
-        io.path[b] = PATH_WARM;
+        io.st_tick[b] = st;
+        io.path[b] = path;
         if (io.accumulate) {
+            if (st != ST_SOLVED && io.status[b] == 0) io.status[b] = st;
+            io.iters[b] += iters;
             io.nfac[b] += info.nfac;
         } else {
-            io.status[b] = ST_SOLVED;
-            io.iters[b] = 0;
+            io.status[b] = st;
+            io.iters[b] = iters;
             io.nfac[b] = info.nfac;
             io.ninf[b] = 0;
         }
@@ -958,6 +982,162 @@ __device__ inline int mpc_hopper_warp(const QpConst& c, WWork& w, double* rec, c
 }
 
 // ------------------------------------------------------------------------------------------------
+// OSQP-style ADMM for one warp (north_star K2; the CTA statement is admm_solve in hmpc_qp.cuh, the numpy statement
+// oracle/device_port.py admm_solve -- same iteration, same check cadence, same rho rule):
+//     x~ = K^-1 (sigma x - g + A'(rho z - y)),  K = H + sigma I + A' diag(rho) A   over the non-fixed variables
+//     x+ = alpha x~ + (1-alpha) x ;  z+ = clip(alpha A x~ + (1-alpha) z + y/rho) ;  y+ = y + rho (.. - z+)
+// K is factorised once (and again when rho moves by more than 5x) as tensor-core tiles in the warp's shared-memory
+// slice (wfactor with the weights of the ADMM operator), every iteration is one tiled substitution (wsolve) plus
+// vector work over the m rows; the residuals of OSQP's termination test and the rho update are warp-shuffle
+// reductions.  On entry w.xp = warm start (or zeros); on exit w.xp = x, y = multipliers, w.code = OSQP's polish guess
+// of the active set.  Returns ST_INEXACT (residual test met), ST_MAX_ITER, ST_NON_FINITE, or -2 when the system
+// does not fit the factor storage.  wv and xt live on w.mul and w.hx (both dead while the iteration runs).
+// ------------------------------------------------------------------------------------------------
+__device__ inline int wadmm(const QpConst& c, WWork& w, const AOp& A, int kcap, WInfo& info, int& iters, double* z, double* y,
+                            double* rv, int lane) {
+    const int N = c.N, n = 6 * N, m = 11 * N;
+    const int nF = w.nf;
+    iters = 0;
+    if (nF > kcap) return -2;
+    double *x = w.xp, *xt = w.hx, *wv = w.mul;
+    double rho = c.rho0;
+    const double sigma = c.sigma, alpha = c.alpha;
+    auto set_rho = [&](double r) {
+        for (int i = lane; i < m; i += 32) {
+            const double lo = wrow_lo(c, w, i), hi = wrow_hi(c, w, i);
+            double v = r;
+            if (lo < -kInfThresh && hi > kInfThresh) v = kRhoMin;
+            else if (hi - lo < 1e-4) v = fmin(1e3 * r, kRhoMax);
+            rv[i] = v;
+        }
+        __syncwarp();
+    };
+    set_rho(rho);
+    for (int i = lane; i < nF; i += 32) w.idx[i] = (uint8_t)i;       // the system holds every non-fixed variable
+    for (int i = lane; i < n; i += 32) {
+        const double v = w.fixed[i] ? 0.0 : x[i];
+        x[i] = fmin(fmax(v, wbox_lo(w, i)), wbox_hi(w, i));
+        xt[i] = 0.0;
+    }
+    __syncwarp();
+    for (int r = lane; r < m; r += 32) { z[r] = A.row(r, x); y[r] = 0.0; }   // OSQP: z = A x at the start, y = 0
+    __syncwarp();
+    w.wts = rv; w.dadd = sigma;
+    ++info.nfac;
+    info.flops += flops_factor(nF);
+    int st = ST_MAX_ITER;
+    if (wfactor(c, w, A, nF, 0, 0.0, lane)) { w.wts = nullptr; return ST_NON_FINITE; }
+    const int last_it = c.max_iter;
+    int next_check = (c.mode == 1) ? last_it : min(c.first_check, last_it);
+    for (int it = 1; it <= last_it; ++it) {
+        for (int r = lane; r < m; r += 32) wv[r] = rv[r] * z[r] - y[r];
+        __syncwarp();
+        for (int i = lane; i < nF; i += 32) { const int vi = w.fr[i]; w.rhs[i] = sigma * x[vi] - w.g[vi] + A.colT(vi, wv); }
+        __syncwarp();
+        wsolve(w, nF, 0, lane);
+        info.flops += flops_solve(nF);
+        for (int i = lane; i < nF; i += 32) xt[w.fr[i]] = w.rhs[i];        // fixed entries of xt stay 0
+        __syncwarp();
+        for (int r = lane; r < m; r += 32) {
+            const double zt = A.row(r, xt);
+            const double zr = alpha * zt + (1.0 - alpha) * z[r];
+            const double rr = rv[r];
+            const double zn = fmin(fmax(zr + y[r] / rr, wrow_lo(c, w, r)), wrow_hi(c, w, r));
+            y[r] += rr * (zr - zn);
+            z[r] = zn;
+        }
+        for (int i = lane; i < n; i += 32) x[i] = alpha * xt[i] + (1.0 - alpha) * x[i];
+        __syncwarp();
+        iters = it;
+        if (it != next_check && it != last_it) continue;
+        next_check = it + c.check;
+        // ---- residuals of the unscaled problem (OSQP termination test) ----
+        wmatvec(w, lane);                                  // hx = H x (overwrites xt, recomputed next iteration)
+        info.flops += flops_matvec(n);
+        double v0 = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0, v5 = 0;   // pri, npri, dua, |Hx|, |A'y|, |g|
+        for (int r = lane; r < m; r += 32) {
+            const double ax = A.row(r, x);
+            v0 = fmax(v0, fabs(ax - z[r]));
+            v1 = fmax(v1, fmax(fabs(ax), fabs(z[r])));
+        }
+        int notfinite = 0;
+        for (int i = lane; i < n; i += 32) {
+            if (w.fixed[i]) continue;                      // eliminated variables carry an implicit multiplier
+            const double aty = A.colT(i, y);
+            const double G = w.hx[i] + w.g[i] + aty;
+            if (!(fabs(G) < 1e300)) notfinite = 1;
+            v2 = fmax(v2, fabs(G));
+            v3 = fmax(v3, fabs(w.hx[i]));
+            v4 = fmax(v4, fabs(aty));
+            v5 = fmax(v5, fabs(w.g[i]));
+        }
+        v0 = wmax(v0); v1 = wmax(v1); v2 = wmax(v2); v3 = wmax(v3); v4 = wmax(v4); v5 = wmax(v5);
+        notfinite = __any_sync(kFullMask, notfinite);
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) xt[i] = 0.0;    // hx held H x: fixed entries of xt must read 0 again
+        __syncwarp();
+        const double pri = v0, npri = v1, dua = v2, ndua = fmax(v3, fmax(v4, v5));
+        if (notfinite || !(pri == pri) || !(dua == dua)) { st = ST_NON_FINITE; break; }
+        if (c.mode == 1) break;
+        if (pri <= c.eps_abs + c.eps_rel * npri && dua <= c.eps_abs + c.eps_rel * ndua) { st = ST_INEXACT; break; }
+        if (it == last_it) break;
+        if (c.adaptive_rho) {
+            double rn = rho * sqrt((pri / fmax(npri, 1e-10)) / fmax(dua / fmax(ndua, 1e-10), 1e-10));
+            rn = fmin(fmax(rn, kRhoMin), kRhoMax);
+            if (rn > 5.0 * rho || rn < 0.2 * rho) {
+                rho = rn;
+                set_rho(rho);
+                ++info.nfac;
+                info.flops += flops_factor(nF);
+                if (wfactor(c, w, A, nF, 0, 0.0, lane)) { st = ST_NON_FINITE; break; }
+            }
+        }
+    }
+    w.wts = nullptr; w.dadd = 0.0;
+    for (int r = lane; r < m; r += 32) {
+        const double zz = z[r], yy = y[r];
+        w.code[r] = (int8_t)(((zz - wrow_lo(c, w, r)) < -yy) ? -1 : (((wrow_hi(c, w, r) - zz) < yy) ? 1 : 0));
+    }
+    __syncwarp();
+    return st;
+}
+
+// One warm ADMM tick of hopper b by one warp: record -> ADMM -> (polish) -> roll-out.  Returns 1 when the hopper is
+// done, 0 when it has to take the CTA kernel (no valid previous tick, infeasible height row, system too large,
+// non-finite iterate).  extra: the warp's z / y / rho vectors (warp_admm_doubles).
+template <int SLOTS>
+__device__ inline int mpc_hopper_warp_admm(const QpConst& c, WWork& w, double* extra, double* rec, const int32_t* flag, int kcap,
+                                           int b, int B, const MpcIo& io, int lane) {
+    const int N = c.N, n = 6 * N, m = 11 * N;
+    if (!wfetch(c, w, rec, flag, b, B, io, lane)) return 0;
+    AOp A{N, n, c.dyn == 3 ? 1 : 0, c.mu, w.stance, w.hinv};
+    WInfo info{0, c.condense_flops};
+    double *z = extra, *y = extra + m, *rv = extra + 2 * m;
+    int iters = 0;
+    int st = wadmm(c, w, A, kcap, info, iters, z, y, rv, lane);
+    if (st < 0 || st == ST_NON_FINITE) return 0;
+    if (c.polish) {
+        // OSQP's polish=True: the verified active-set refinement from ADMM's guess; the iterate is kept in z (dead now)
+        for (int i = lane; i < n; i += 32) z[i] = w.xp[i];
+        __syncwarp();
+        wpolish_init(c, w, lane);
+        int ok = 0;
+        for (int trial = 0; trial <= c.retries; ++trial) {
+            const int r = wtrial<SLOTS>(c, w, A, kcap, info, lane);
+            if (r > 0) ok = 1;
+            if (r != 0) break;
+        }
+        if (ok) st = ST_SOLVED;
+        else {
+            for (int i = lane; i < n; i += 32) w.xp[i] = z[i];
+            __syncwarp();
+        }
+    }
+    wfinish(c, w, b, B, io, info, lane, st, PATH_ADMM, iters);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Host-side dispatch rules, shared by the library (hmpc_api.cu) and the test emulation (tests/emul).
 // ------------------------------------------------------------------------------------------------
 constexpr int kWarpMaxN = 10;     // horizons the warp kernel is instantiated for (n = 6N <= 64: two rows per lane)
@@ -970,7 +1150,8 @@ inline int warp_kcap(const hmpc_config& cfg) {
     return k;
 }
 inline bool warp_path_applies(const hmpc_config& cfg, int init) {
-    return cfg.hot_path == HMPC_HOT_AUTO && !init && cfg.warm_start && cfg.solver == HMPC_SOLVER_EXACT &&
+    return cfg.hot_path == HMPC_HOT_AUTO && !init && cfg.warm_start &&
+           (cfg.solver == HMPC_SOLVER_EXACT || cfg.solver == HMPC_SOLVER_ADMM) &&
            cfg.precision == HMPC_FP64 && cfg.sqp_sweeps <= 1 && cfg.N >= 3 && cfg.N <= kWarpMaxN;
 }
 
@@ -1017,6 +1198,32 @@ mpc_warp_kernel(QpConst c, int B, int kcap, int wdoubles, double* __restrict__ p
         const int done = mpc_hopper_warp<SLOTS>(c, w, prep + (size_t)b * pstride, flags + b, kcap, b, B, io, lane);
         __syncwarp();
         if (done <= 0 && lane == 0) defer_list[atomicAdd(defer_cnt, 1)] = b | (done < 0 ? kDeferWarmFailed : 0);
+    }
+}
+
+// ADMM mode (hmpc_config.solver = HMPC_SOLVER_ADMM): WPC free-running warps per CTA, one hopper each, the same ticket
+// counter and deferral list as above.  The iteration count differs from hopper to hopper by design (early exit), so
+// there is nothing to run in lock-step.
+template <int WPC>
+__global__ void __launch_bounds__(32 * WPC, 1)
+mpc_warp_admm_kernel(QpConst c, int B, int kcap, int wdoubles, double* __restrict__ prep, size_t pstride,
+                     const int32_t* __restrict__ flags, int* __restrict__ work_ctr, int* __restrict__ defer_list,
+                     int* __restrict__ defer_cnt, MpcIo io) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    WWork w;
+    double* slice = smem + (size_t)wid * wdoubles;
+    wcarve(w, slice, c.N, kcap);
+    double* extra = slice + warp_work_doubles(c.N, kcap);
+    for (;;) {
+        int b = 0;
+        if (lane == 0) b = atomicAdd(work_ctr, 1);
+        b = __shfl_sync(kFullMask, b, 0);
+        if (b >= B) break;
+        b = work_item(c, b, B);
+        const int done = mpc_hopper_warp_admm<2>(c, w, extra, prep + (size_t)b * pstride, flags + b, kcap, b, B, io, lane);
+        __syncwarp();
+        if (!done && lane == 0) defer_list[atomicAdd(defer_cnt, 1)] = b;
     }
 }
 

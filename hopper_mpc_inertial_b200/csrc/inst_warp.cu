@@ -63,7 +63,31 @@ void prep_launch(const WarpLaunch& l, const QpConst& qc, const MpcIo& io) {
         qc, l.B, wd, l.prep, l.pstride, l.flags, io);
 }
 
+// ADMM mode: free-running warps, one CTA per SM
+constexpr int kAdmmWpcA = 10, kAdmmWpcB = 6;
+bool warp_admm_wpc_supported(int wpc) { return wpc == kAdmmWpcA || wpc == kAdmmWpcB; }
+cudaError_t warp_admm_set_smem(int wpc, int bytes) {
+    return wpc == kAdmmWpcA ? cudaFuncSetAttribute(mpc_warp_admm_kernel<kAdmmWpcA>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
+                            : cudaFuncSetAttribute(mpc_warp_admm_kernel<kAdmmWpcB>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+cudaError_t warp_admm_regs(int wpc, int* regs) {
+    cudaFuncAttributes a;
+    const cudaError_t e = wpc == kAdmmWpcA ? cudaFuncGetAttributes(&a, mpc_warp_admm_kernel<kAdmmWpcA>)
+                                           : cudaFuncGetAttributes(&a, mpc_warp_admm_kernel<kAdmmWpcB>);
+    if (e == cudaSuccess) *regs = a.numRegs;
+    return e;
+}
+
 void warp_launch(const WarpLaunch& l, const QpConst& qc, const MpcIo& io) {
+    if (l.admm) {
+        if (l.wpc == kAdmmWpcA)
+            mpc_warp_admm_kernel<kAdmmWpcA><<<l.grid, 32 * kAdmmWpcA, l.smem, l.stream>>>(qc, l.B, l.kcap, l.wdoubles, l.prep, l.pstride, l.flags,
+                                                                                         l.work_ctr, l.defer_list, l.defer_cnt, io);
+        else
+            mpc_warp_admm_kernel<kAdmmWpcB><<<l.grid, 32 * kAdmmWpcB, l.smem, l.stream>>>(qc, l.B, l.kcap, l.wdoubles, l.prep, l.pstride, l.flags,
+                                                                                         l.work_ctr, l.defer_list, l.defer_cnt, io);
+        return;
+    }
 #define CALL(K, W, M)                                                                                     \
     K<2, W, M><<<l.grid, 32 * W, l.smem, l.stream>>>(qc, l.B, l.kcap, l.wdoubles, l.prep, l.pstride,      \
                                                      l.flags, l.work_ctr, l.defer_list, l.defer_cnt, l.group, io)

@@ -146,7 +146,8 @@ int emul_solve(const hmpc_config* cfg, const double* Qd, const double* Rd, const
     g_emul_warp_done = 0;
     if (warp_path_applies(*cfg, init)) {
         const int kcap = warp_kcap(*cfg);
-        std::vector<double> wsm(warp_work_doubles(N, kcap) + 8), psm(warp_work_doubles(N, kPrepKcap) + 8), rec(prep_stride(N) + 8);
+        std::vector<double> wsm(warp_work_doubles(N, kcap) + warp_admm_doubles(N) + 8), psm(warp_work_doubles(N, kPrepKcap) + 8), rec(prep_stride(N) + 8);
+        const bool admm = cfg->solver == HMPC_SOLVER_ADMM;
         for (int b = 0; b < B; ++b) {
             int done = 0;
             int32_t flag = -1;
@@ -159,7 +160,8 @@ int emul_solve(const hmpc_config* cfg, const double* Qd, const double* Rd, const
             run_warp([&](int lane) {
                 WWork ww;
                 wcarve(ww, wsm.data(), N, kcap);
-                const int d = mpc_hopper_warp<2>(c, ww, rec.data(), &flag, kcap, b, B, io, lane);
+                const int d = admm ? mpc_hopper_warp_admm<2>(c, ww, wsm.data() + warp_work_doubles(N, kcap), rec.data(), &flag, kcap, b, B, io, lane)
+                                   : mpc_hopper_warp<2>(c, ww, rec.data(), &flag, kcap, b, B, io, lane);
                 if (lane == 0) done = d;
             });
             deferred[b] = done > 0 ? 0 : 1;

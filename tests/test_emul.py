@@ -217,3 +217,32 @@ def test_closed_loop_with_scheduled_gate_matches_oracle():
                              sc["pf_switch"][:, b], n_ticks, gate=gate)
         np.testing.assert_allclose(Xl[:, :, b], Xo, rtol=0, atol=2e-9)
     assert gated > 0
+
+
+@pytest.mark.parametrize("polish", [1, 0])
+def test_warp_admm_equals_cta_admm(polish):
+    """solver = ADMM on warm ticks runs one warp per hopper (hmpc_warp.cuh: wadmm, tensor-core tiled factor and
+    substitutions, shuffle reductions for OSQP's residual test and the rho update).  Same iteration as the CTA statement
+    (hmpc_qp.cuh: admm_solve): equal iteration counts, factorisations and status, iterates equal to rounding; with
+    polish the verified optimum."""
+    B, N, n_ticks = 3, 10, 4
+    sc = scenarios.make_batch(B, N=N, n_ticks=n_ticks, seed=21)
+    ems = [EmulMpc(B, N=N, solver=1, polish=polish, hot_path=hp, max_iter=4000) for hp in (0, 1)]
+    for em in ems:
+        em.set_gains(sc["Qdiag"], sc["Rdiag"])
+    X = sc["X0"].copy()
+    warp_ticks = 0
+    for t in range(n_ticks):
+        _, x_in = ems[0].rk4(X, np.zeros((6, B)), np.zeros((3, B)), 0, convert=True)
+        outs = [em.solve(x_in, sc["xref_tab"][t:t + N], sc["pf_tab"][t:t + N], sc["C_tab"][t], t == 0) for em in ems]
+        (U0, X0s, st0, it0, nf0, pa0), (U1, X1s, st1, it1, nf1, pa1) = outs
+        warp_ticks += ems[0].warp_done
+        assert ems[1].warp_done == 0
+        assert np.array_equal(st0, st1) and np.array_equal(it0, it1) and np.array_equal(nf0, nf1)
+        assert np.all(st0 == (0 if polish else 4)) and np.all(pa0 == 4)
+        np.testing.assert_allclose(U0, U1, rtol=1e-7, atol=1e-7)
+        np.testing.assert_allclose(X0s, X1s, rtol=1e-7, atol=1e-8)
+        for em in ems:                              # keep both on the same closed loop: the CTA statement's control
+            em.Usol[:] = ems[1].Usol; em.Xsol[:] = ems[1].Xsol; em.code[:] = ems[1].code
+        X = ems[1].sim_tick(X, U1[0], sc["pf_tab"][t], sc["pf_tab"][t + 1], sc["pf_switch"][t])
+    assert warp_ticks == B * (n_ticks - 1)          # every warm tick went through the warp kernel

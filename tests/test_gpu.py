@@ -666,3 +666,56 @@ def test_contact_gate_matches_oracle_and_both_rollout_flavours_agree():
         bm.rollout(T(sc["X0"]).clone(), *tabs, 0, 2, True)
     with pytest.raises(_lib.HmpcError):
         bm.set_contact_gate("detect", leg_max=0.0)
+
+
+@pytest.mark.parametrize("dyn", ["3f", "2f"])
+def test_warp_admm_closed_loop(dyn):
+    """north_star K2 on warm ticks = one warp per hopper (mpc_warp_admm_kernel).  Against the CTA statement of the same
+    iteration (hot_path = cta): equal iteration counts, factorisations, status; with polish (OSQP's polish=True) every
+    tick lands on the certified oracle optimum, so the closed loop follows the oracle loop."""
+    B, N, n_ticks = 8, 10, 12
+    sc = scenarios.make_batch(B, N=N, n_ticks=n_ticks, seed=7, dyn=dyn)
+    tabs = (T(sc["xref_tab"]), T(sc["pf_tab"]), cb64(sc["C_tab"]), T(sc["pf_switch"]))
+    res = {}
+    for hp in ("auto", "cta"):
+        bm = mk(B, dyn, N, solver="admm", polish=1, hot_path=hp, max_iter=4000)
+        bm.set_gains(T(sc["Qdiag"]), T(sc["Rdiag"]))
+        X = T(sc["X0"]).clone()
+        out = bm.rollout(X, *tabs, 0, n_ticks, True, log=True)
+        torch.cuda.synchronize()
+        nf, pa, ni = [a.cpu().numpy() for a in bm.solve_stats()]
+        res[hp] = (out["X_log"].cpu().numpy(), out["U_log"].cpu().numpy(), out["status"].cpu().numpy(), out["iters"].cpu().numpy(), nf, pa,
+                   bm.hot_path_info())
+    Xa, Ua, sa, ia, nfa, paa, ha = res["auto"]
+    Xc, Uc, sc_, ic, nfc, pac, hc = res["cta"]
+    assert ha["warps_per_sm"] >= 6 and hc["warps_per_sm"] == 0
+    assert ha["deferred"] <= B                         # warm ticks stayed in the warp kernel
+    assert np.all(sa == 0) and np.all(sc_ == 0) and np.all(paa == _lib.PATH_ADMM)
+    assert np.array_equal(ia, ic) and np.array_equal(nfa, nfc)
+    np.testing.assert_allclose(Ua, Uc, rtol=1e-6, atol=1e-6)
+    for b in range(B):
+        p = ho.Params(dyn=dyn, N=N, Qdiag=sc["Qdiag"][:, b].copy(), Rdiag=sc["Rdiag"][:, b].copy())
+        Xo, Uo = closed_loop(p, sc["X0"][:, b], sc["xref_tab"][:, :, b], sc["pf_tab"][:, :, b], sc["C"][:, b], sc["pf_switch"][:, b], n_ticks)
+        assert np.all(np.abs(Ua[:, :, b] - Uo) <= 10 * u_tol(Uo)), np.abs(Ua[:, :, b] - Uo).max()
+        np.testing.assert_allclose(Xa[:, :, b], Xo, rtol=0, atol=1e-6)
+
+
+def test_warp_admm_early_exit_iterate_without_polish():
+    """polish = 0: the warp kernel returns OSQP's eps-terminated iterate (status INEXACT) -- equal to the CTA statement
+    at the same iteration count."""
+    B, N = 16, 10
+    sc = scenarios.make_batch(B, N=N, n_ticks=3, seed=5)
+    outs = []
+    for hp in ("auto", "cta"):
+        bm = mk(B, "3f", N, solver="admm", polish=0, hot_path=hp, max_iter=4000)
+        bm.set_gains(T(sc["Qdiag"]), T(sc["Rdiag"]))
+        X = T(sc["X0"]).clone()
+        tabs = (T(sc["xref_tab"]), T(sc["pf_tab"]), cb64(sc["C_tab"]), T(sc["pf_switch"]))
+        bm.rollout(X, *tabs, 0, 1, True)
+        out = bm.rollout(X, *tabs, 1, 1, False, log=True)           # one warm tick from identical state
+        torch.cuda.synchronize()
+        outs.append((out["U_log"].cpu().numpy(), out["status"].cpu().numpy(), out["iters"].cpu().numpy(), bm.hot_path_info()["deferred"]))
+    (Ua, sa, ia, da), (Uc, sc_, ic, dc) = outs
+    assert da == 0
+    assert np.all(sa == _lib.STATUS_INEXACT) and np.array_equal(sa, sc_) and np.array_equal(ia, ic)
+    np.testing.assert_allclose(Ua, Uc, rtol=1e-7, atol=1e-7)
