@@ -504,12 +504,13 @@ __device__ __forceinline__ double wweights(const WWork& w, const AOp& A, int ci,
     if (ci == cj) s += w.wts[vi] + w.dadd;
     return s;
 }
+template <bool ADMM = false>
 static __device__ __noinline__ double wentry(const QpConst& c, const WWork& w, const AOp& A, int nF, int nk, int i, int j) {
     const int n = 6 * c.N;
     if (i < j || i >= nk) return 0.0;
     if (i < nF) {
         const double h = w.Hc[(int)w.idx[j] * w.ld + (int)w.idx[i]];
-        return w.wts ? h + wweights(w, A, (int)w.idx[i], (int)w.idx[j]) : h;
+        return ADMM ? h + wweights(w, A, (int)w.idx[i], (int)w.idx[j]) : h;
     }
     if (j < nF) return A.coef(n + (int)w.grow[i - nF], (int)w.fr[w.idx[j]]);
     if (i == j) return wrow_coupled(c, w, (int)w.grow[i - nF]) ? 0.0 : -1.0;
@@ -528,6 +529,9 @@ static __device__ __noinline__ double wentry(const QpConst& c, const WWork& w, c
 // the diagonal in between.  Storage w.L: lower block triangle of row-major 8x8 tiles, the diagonal tiles hold W_J.
 // Returns nonzero (all lanes) when a pivot has the wrong sign or is not finite.
 // ------------------------------------------------------------------------------------------------
+// ADMM = true: K's variable block carries the weights of the ADMM operator (w.wts, w.dadd); a template parameter so
+// that the exact path's kernel is not touched by it (154 registers; 168 with a run-time switch, -1.4 % throughput).
+template <bool ADMM = false>
 __device__ inline int wfactor(const QpConst& c, WWork& w, const AOp& A, int nF, int ng, double eps, int lane) {
     HMPC_EMUL_COUNT(2);
     const int nk = nF + ng, nt = (nk + 7) >> 3;
@@ -560,12 +564,12 @@ __device__ inline int wfactor(const QpConst& c, WWork& w, const AOp& A, int nF, 
             if (8 * I + 8 <= nF) {                                   // variables x variables (H is stored symmetric)
                 const int ri = (int)w.idx[i];
                 k0 = hc0[ri]; k1 = hc1[ri];
-                if (w.wts) {                                         // ADMM operator (i >= j0, j0 + 1 may exceed i: unused)
+                if (ADMM) {                                          // ADMM operator (i >= j0, j0 + 1 may exceed i: unused)
                     k0 += wweights(w, A, ri, (int)w.idx[j0]);
                     k1 += wweights(w, A, ri, (int)w.idx[j0 + 1]);
                 }
             } else {
-                k0 = wentry(c, w, A, nF, nk, i, j0); k1 = wentry(c, w, A, nF, nk, i, j0 + 1);
+                k0 = wentry<ADMM>(c, w, A, nF, nk, i, j0); k1 = wentry<ADMM>(c, w, A, nF, nk, i, j0 + 1);
             }
             double a0 = 0.0, a1 = 0.0;
             const int kplain = J < Jb ? J : Jb;
@@ -1026,7 +1030,7 @@ __device__ inline int wadmm(const QpConst& c, WWork& w, const AOp& A, int kcap, 
     ++info.nfac;
     info.flops += flops_factor(nF);
     int st = ST_MAX_ITER;
-    if (wfactor(c, w, A, nF, 0, 0.0, lane)) { w.wts = nullptr; return ST_NON_FINITE; }
+    if (wfactor<true>(c, w, A, nF, 0, 0.0, lane)) { w.wts = nullptr; return ST_NON_FINITE; }
     const int last_it = c.max_iter;
     int next_check = (c.mode == 1) ? last_it : min(c.first_check, last_it);
     for (int it = 1; it <= last_it; ++it) {
@@ -1089,7 +1093,7 @@ __device__ inline int wadmm(const QpConst& c, WWork& w, const AOp& A, int kcap, 
                 set_rho(rho);
                 ++info.nfac;
                 info.flops += flops_factor(nF);
-                if (wfactor(c, w, A, nF, 0, 0.0, lane)) { st = ST_NON_FINITE; break; }
+                if (wfactor<true>(c, w, A, nF, 0, 0.0, lane)) { st = ST_NON_FINITE; break; }
             }
         }
     }
