@@ -281,12 +281,9 @@ __device__ inline void wlinearize_all(const QpConst& c, WWork& w, int b, int B, 
 
 // stance flags, box bounds, height-row scaling, fixed variables and the compact ordering of the non-fixed ones: all
 // functions of the contact schedule only.  Ends with a __syncwarp().
-__device__ inline void wload_sets(const QpConst& c, WWork& w, int b, const MpcIo& io, int lane) {
+__device__ inline void wload_sets(const QpConst& c, WWork& w, uint64_t bits, int lane) {
     const int N = c.N, n = 6 * N;
-    {
-        const uint64_t bits = io.Cbits[b];
-        for (int k = lane; k < N; k += 32) w.stance[k] = (int8_t)((bits >> k) & 1ull);
-    }
+    for (int k = lane; k < N; k += 32) w.stance[k] = (int8_t)((bits >> k) & 1ull);
     if (lane < 12) {   // box bounds by (stance, component)
         const int st = lane / 6, cc = lane - 6 * st;
         double lo = -kInf, hi = kInf;
@@ -317,7 +314,7 @@ __device__ inline int wcondense(const QpConst& c, WWork& w, int b, int B, const 
     const size_t Bs = (size_t)B;
     for (int i = lane; i < 12; i += 32) { w.xin[i] = io.x_in[i * Bs + b]; w.Qd[i] = io.Qd[i * Bs + b]; }
     if (lane < 6) w.Rd[lane] = io.Rd[lane * Bs + b];
-    wload_sets(c, w, b, io, lane);
+    wload_sets(c, w, io.Cbits[b], lane);
     wlinearize_all(c, w, b, B, io, lane);
     __syncwarp();
     // prefix sums of cos / sin (same summation order as condense())
@@ -478,20 +475,35 @@ __device__ inline void wmatvec(WWork& w, int lane) {
     __syncwarp();
     const double* hp = w.Hc + g * ld + 2 * t;
 #pragma unroll 1
-    for (int I = 0; I < ntf; ++I) {
-        // all tiles of the block row are requested from L2 before the first product (ntf <= 8)
-        d2 h[8];
+    for (int I = 0; I < ntf; I += 2) {
+        // all tiles of TWO block rows are requested from L2 before the first product (ntf <= 8): one L2 round trip per
+        // pair of block rows (ncu: the products of this loop held 10 % of the kernel's long-scoreboard stalls)
+        const bool two = I + 1 < ntf;
+        const double* hq = hp + (two ? 8 * ld : 0);
+        d2 h[8], q[8];
 #pragma unroll
         for (int K = 0; K < 8; ++K) h[K] = (K < ntf) ? ld2(hp + 8 * K) : d2{0.0, 0.0};
-        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;            // two chains: even / odd column tiles
+#pragma unroll
+        for (int K = 0; K < 8; ++K) q[K] = (K < ntf) ? ld2(hq + 8 * K) : d2{0.0, 0.0};
+        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;            // two chains per block row: even / odd column tiles
+        double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
 #pragma unroll
         for (int K = 0; K < 8; K += 2) {
-            if (K < ntf) tile_mac(a0, a1, h[K], vec_b(w.xc + 8 * K, lane));
-            if (K + 1 < ntf) tile_mac(b0, b1, h[K + 1], vec_b(w.xc + 8 * K + 8, lane));
+            if (K < ntf) {
+                const d2 v = vec_b(w.xc + 8 * K, lane);
+                tile_mac(a0, a1, h[K], v);
+                tile_mac(c0, c1, q[K], v);
+            }
+            if (K + 1 < ntf) {
+                const d2 v = vec_b(w.xc + 8 * K + 8, lane);
+                tile_mac(b0, b1, h[K + 1], v);
+                tile_mac(e0, e1, q[K + 1], v);
+            }
         }
         const int i = 8 * I + g;
         if (t == 0 && i < nf) w.hx[w.fr[i]] = a0 + b0;
-        hp += 8 * ld;
+        if (two && t == 0 && i + 8 < nf) w.hx[w.fr[i + 8]] = c0 + e0;
+        hp += 16 * ld;
     }
     __syncwarp();
 }
@@ -567,6 +579,20 @@ __device__ inline int wfactor(const QpConst& c, WWork& w, const AOp& A, int nF, 
                 if (ADMM) {                                          // ADMM operator (i >= j0, j0 + 1 may exceed i: unused)
                     k0 += wweights(w, A, ri, (int)w.idx[j0]);
                     k1 += wweights(w, A, ri, (int)w.idx[j0 + 1]);
+                }
+            } else if (i < nF) {
+                // a variable row inside the tile row that also holds active rows: its two Hessian entries are gathered
+                // like above -- both loads in flight together and ahead of the tile products -- instead of through two
+                // dependent wentry() calls (ncu: 20 % of the kernel's long-scoreboard stalls sat in wentry).  A column
+                // >= nF lies above the diagonal for this row: never used.
+                const int ri = (int)w.idx[i];
+                const bool v0 = j0 < nF, v1 = j0 + 1 < nF;
+                const int cj0 = v0 ? (int)w.idx[j0] : 0, cj1 = v1 ? (int)w.idx[j0 + 1] : 0;
+                const double h0 = w.Hc[cj0 * w.ld + ri], h1 = w.Hc[cj1 * w.ld + ri];
+                k0 = v0 ? h0 : 0.0; k1 = v1 ? h1 : 0.0;
+                if (ADMM) {
+                    if (v0) k0 += wweights(w, A, ri, cj0);
+                    if (v1) k1 += wweights(w, A, ri, cj1);
                 }
             } else {
                 k0 = wentry<ADMM>(c, w, A, nF, nk, i, j0); k1 = wentry<ADMM>(c, w, A, nF, nk, i, j0 + 1);
@@ -856,34 +882,60 @@ __device__ inline void wprep(const QpConst& c, WWork& w, double* rec, int32_t* f
 __device__ inline int wfetch(const QpConst& c, WWork& w, double* rec, const int32_t* flag, int b, int B, const MpcIo& io, int lane) {
     const int N = c.N, n = 6 * N, m = 11 * N;
     const size_t Bs = (size_t)B;
+    // Every global load of the fetch is issued here, back to back, into registers (n <= 64: two entries per lane,
+    // m <= 128: four): ONE HBM round trip instead of five dependent ones.  In the lock-step kernel the fetch of one
+    // warp is on the critical path of its whole group's round.
+    const double* rg = rec + prep_hstride(N);
+    const double* rh = rg + ((n + 7) & ~7);
+    const double* rx = rh + ((N + 7) & ~7);
     const int f = *flag;
+    const uint64_t bits = io.Cbits[b];
+    double gq[2] = {0.0, 0.0}, uq[2] = {0.0, 0.0};
+    int8_t cq[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int i = lane + 32 * q;
+        if (i < n) {
+            // warm start: stage k starts from the previous tick's stage k+1, the last two stages keep their own
+            // previous pattern (mpc_hopper in hmpc_mpc.cuh)
+            const int src = (i / 6 < N - 2) ? i + 6 : i;
+            gq[q] = rg[i];
+            uq[q] = io.Usol[(size_t)src * Bs + b];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int r = lane + 32 * q;
+        if (r < m) {
+            int src;
+            if (r < n) src = (r / 6 < N - 2) ? r + 6 : r;
+            else if (r < n + 4 * N) src = ((r - n) / 4 < N - 2) ? r + 4 : r;
+            else src = (r - n - 4 * N < N - 2) ? r + 1 : r;
+            cq[q] = io.code[(size_t)src * Bs + b];
+        }
+    }
+    const double hl = lane < N ? rh[lane] : 0.0;            // N <= kWarpMaxN < 32
+    const double xi = lane < 12 ? rx[lane] : 0.0;
     if (f == PREP_INVALID) { HMPC_EMUL_COUNT(4); return 0; }
     if (f == PREP_INFEASIBLE) { HMPC_EMUL_COUNT(5); return 0; }
     w.Hc = rec;
-    wload_sets(c, w, b, io, lane);
+    wload_sets(c, w, bits, lane);
 #ifndef HMPC_HOST_EMUL
     // the record was written by another kernel long ago: pull the Hessian into L2 while the rest is set up
     for (int o = 16 * lane; o < w.nf * w.ld; o += 16 * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + o));
 #endif
-    const double* rg = rec + prep_hstride(N);
-    const double* rh = rg + ((n + 7) & ~7);
-    const double* rx = rh + ((N + 7) & ~7);
-    for (int i = lane; i < n; i += 32) w.g[i] = rg[i];
-    for (int k = lane; k < N; k += 32) w.hlo[k] = rh[k];
-    if (lane < 12) w.xin[lane] = rx[lane];
-    // warm start: stage k starts from the previous tick's stage k+1, the last two stages keep their own previous
-    // pattern (mpc_hopper in hmpc_mpc.cuh)
-    for (int i = lane; i < n; i += 32) {
-        const int src = (i / 6 < N - 2) ? i + 6 : i;
-        w.xp[i] = io.Usol[(size_t)src * Bs + b];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int i = lane + 32 * q;
+        if (i < n) { w.g[i] = gq[q]; w.xp[i] = uq[q]; }
     }
-    for (int r = lane; r < m; r += 32) {
-        int src;
-        if (r < n) src = (r / 6 < N - 2) ? r + 6 : r;
-        else if (r < n + 4 * N) src = ((r - n) / 4 < N - 2) ? r + 4 : r;
-        else src = (r - n - 4 * N < N - 2) ? r + 1 : r;
-        w.code[r] = io.code[(size_t)src * Bs + b];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int r = lane + 32 * q;
+        if (r < m) w.code[r] = cq[q];
     }
+    if (lane < N) w.hlo[lane] = hl;
+    if (lane < 12) w.xin[lane] = xi;
     __syncwarp();
     wpolish_init(c, w, lane);
     return 1;
