@@ -544,8 +544,13 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
                 return fail(HMPC_ERR_ALLOC, std::string("cudaMalloc QP records: ") + cudaGetErrorString(e));
             }
             h->warp_rounds = rounds;
-            h->warp_group = best_wpc;
-            if (const char* ev = getenv("HMPC_WARP_GROUP")) { const int v = atoi(ev); if (abs(v) >= 1 && abs(v) <= best_wpc) h->warp_group = v; }
+            // lock-step group = all warps of the CTA, one re-alignment barrier after the factorisation (measured, 131072
+            // hoppers: groups of 12 / 6 / 4 / 3 / 2 warps 8.38 / 7.83 / 7.48 / 7.30 / 7.12 M steps/s; with the barrier
+            // 8.48 M); HMPC_WARP_GROUP / HMPC_WARP_SYNCS override.  Encoded as group + 256 * barriers.
+            int grp = best_wpc, nsync = 1;
+            if (const char* ev = getenv("HMPC_WARP_GROUP")) { const int v = atoi(ev); if (v >= 1 && v <= best_wpc) grp = v; }
+            if (const char* ev = getenv("HMPC_WARP_SYNCS")) { const int v = atoi(ev); if (v >= 0 && v <= 2) nsync = v; }
+            h->warp_group = grp + 256 * nsync;
             if ((e = hmpc::warp_set_smem(rounds, best_wpc, smem_i)) != cudaSuccess ||
                 (e = hmpc::prep_set_smem(smem_i)) != cudaSuccess) {
                 hmpc_destroy(h);

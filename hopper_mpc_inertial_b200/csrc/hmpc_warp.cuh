@@ -312,10 +312,31 @@ __device__ inline void wload_sets(const QpConst& c, WWork& w, uint64_t bits, int
 __device__ inline int wcondense(const QpConst& c, WWork& w, int b, int B, const MpcIo& io, int lane) {
     const int N = c.N, n = 6 * N;
     const size_t Bs = (size_t)B;
-    for (int i = lane; i < 12; i += 32) { w.xin[i] = io.x_in[i * Bs + b]; w.Qd[i] = io.Qd[i * Bs + b]; }
-    if (lane < 6) w.Rd[lane] = io.Rd[lane * Bs + b];
-    wload_sets(c, w, io.Cbits[b], lane);
-    wlinearize_all(c, w, b, B, io, lane);
+    // Every global load of the condensing is issued here, back to back, into registers -- state, gains, contact mask,
+    // the linearisation point and footstep of this lane's stage, this lane's reference row: ONE HBM round trip instead
+    // of four dependent ones (N <= kWarpMaxN < 32: one stage / one row per lane).
+    const int k = lane;                                   // stage of wlinearize_all, row i = lane of the error loop
+    double xq = 0.0, qq = 0.0, rq = 0.0, gp[4] = {0.0, 0.0, 0.0, 0.0}, pfq[3] = {0.0, 0.0, 0.0}, xr[12];
+    if (lane < 12) { xq = io.x_in[lane * Bs + b]; qq = io.Qd[lane * Bs + b]; }
+    if (lane < 6) rq = io.Rd[lane * Bs + b];
+    const uint64_t bits = io.Cbits[b];
+    if (k < N) {
+        if (k == 0) {
+            gp[0] = io.x_in[0 * Bs + b]; gp[1] = io.x_in[1 * Bs + b]; gp[2] = io.x_in[2 * Bs + b]; gp[3] = io.x_in[5 * Bs + b];
+        } else {
+            const size_t o = (size_t)(k + 1) * 12;
+            gp[0] = io.Xsol[(o + 0) * Bs + b]; gp[1] = io.Xsol[(o + 1) * Bs + b];
+            gp[2] = io.Xsol[(o + 2) * Bs + b]; gp[3] = io.Xsol[(o + 5) * Bs + b];
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) pfq[i] = io.pf[(size_t)(3 * k + i) * Bs + b];
+    }
+#pragma unroll
+    for (int q = 0; q < 12; ++q) xr[q] = (lane >= 1 && lane <= N) ? io.x_ref[((size_t)(lane - 1) * 12 + q) * Bs + b] : 0.0;
+    if (lane < 12) { w.xin[lane] = xq; w.Qd[lane] = qq; }
+    if (lane < 6) w.Rd[lane] = rq;
+    wload_sets(c, w, bits, lane);
+    if (k < N) wlinearize_stage(c, gp, pfq, w.cz + k, w.sz + k, w.Bw + 18 * k);      // wlinearize_all on the loaded point
     __syncwarp();
     // prefix sums of cos / sin (same summation order as condense())
     for (int i = lane; i <= N; i += 32) {
@@ -342,7 +363,7 @@ __device__ inline int wcondense(const QpConst& c, WWork& w, int b, int B, const 
         cf[4] = x0[4] + dt * (-ps * x0[9] + pc * x0[10]);
         cf[5] = x0[5] + dt * (di * x0[11]);
         if (i >= 1)
-            for (int q = 0; q < 12; ++q) w.err[12 * i + q] = cf[q] - io.x_ref[((size_t)(i - 1) * 12 + q) * Bs + b];
+            for (int q = 0; q < 12; ++q) w.err[12 * i + q] = cf[q] - xr[q];           // i == lane (N < 32)
         if (i < N) {
             double up = 0.0;
             for (int j = 0; j + 2 <= i; ++j) if (w.stance[j]) up += (double)(i - j - 1);
@@ -720,9 +741,10 @@ __device__ inline void wpolish_init(const QpConst& c, WWork& w, int lane) {
 }
 // One trial: 1 = verified optimum (w.xp, w.mul, w.code), 0 = active set updated, try again, -1 = give up,
 // -2 = the system does not fit this kernel's factor storage.
-struct NoSync { __device__ __forceinline__ void operator()() const {} };
-// mid: called exactly once per trial by every lane, after the factorisation (lock-step kernel: a group barrier that
-// re-aligns the warps of the SM before the refinement / verification code; NoSync elsewhere)
+struct NoSync { __device__ __forceinline__ void operator()(int) const {} };
+// mid(p): re-alignment points of the lock-step kernel (a group barrier that brings the warps of the SM back in step so
+// that they share instruction fetches; NoSync elsewhere).  Every lane calls mid(0) -- after the factorisation -- and
+// mid(1) -- after the refinement loop -- exactly once per trial, whatever path it takes.
 template <int SLOTS, class Sync = NoSync>
 __device__ inline int wtrial(const QpConst& c, WWork& w, const AOp& A, int kcap, WInfo& info, int lane, Sync mid = Sync()) {
     const int N = c.N, n = 6 * N, m = 11 * N;
@@ -744,12 +766,12 @@ __device__ inline int wtrial(const QpConst& c, WWork& w, const AOp& A, int kcap,
         const int ng = wcompact(n, m - n, kcap, w.grow, n, lane, [&](int r) { return w.code[r] != 0; });
         __syncwarp();
         const int nk = nF + ng;
-        if (nk > kcap) { HMPC_EMUL_COUNT(6); mid(); return -2; }     // too large for this kernel, not a failed attempt
+        if (nk > kcap) { HMPC_EMUL_COUNT(6); mid(0); mid(1); return -2; }     // too large for this kernel, not a failed attempt
         ++info.nfac;
         info.flops += flops_factor(nk);
         const int fbad = wfactor(c, w, A, nF, ng, c.kkt_eps, lane);
-        mid();
-        if (fbad) return -1;
+        mid(0);
+        if (fbad) { mid(1); return -1; }
         double prev = 1e300;
         bool hx_current = false;
         for (int k = 0; k < c.max_refine; ++k) {
@@ -776,7 +798,7 @@ __device__ inline int wtrial(const QpConst& c, WWork& w, const AOp& A, int kcap,
             }
             v0 = wmax(v0); v1 = wmax(v1);
             __syncwarp();
-            if (!(v0 == v0)) return -1;
+            if (!(v0 == v0)) { mid(1); return -1; }
             if (k == 1 && ng == 0 && v0 <= 1e-7 * prev) { hx_current = true; break; }
             if (k >= 1 && (v1 <= 1e-12 || (k >= 2 && v0 > c.stagnation * prev))) { hx_current = true; break; }
             prev = v0;
@@ -788,6 +810,7 @@ __device__ inline int wtrial(const QpConst& c, WWork& w, const AOp& A, int kcap,
             }
             __syncwarp();
         }
+        mid(1);
         // ---- pass 1: multipliers of pinned variables, scales ----
         if (!hx_current) { wmatvec(w, lane); info.flops += flops_matvec(n); }
         double s_stat = 0.0, s_scale = 0.0, s_mult = 0.0;
@@ -1302,8 +1325,8 @@ mpc_warp_rounds_kernel(QpConst c, int B, int kcap, int wdoubles, double* __restr
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     // lock-step groups of gw warps, each on its own named barrier (the last group takes what is left of the CTA)
-    const int midsync = gw < 0;        // experiment switch: negative group size = one more barrier after the factorisation
-    if (gw < 0) gw = -gw;
+    const int nsync = gw >> 8;         // re-alignment barriers inside a trial (0, 1: after the factorisation, 2: + after the refinement)
+    gw &= 255;
     const int grp = wid / gw, bar_id = 1 + grp;
     const int bar_threads = 32 * ((grp + 1) * gw <= WPC ? gw : WPC - grp * gw);
     WWork w;
@@ -1322,8 +1345,8 @@ mpc_warp_rounds_kernel(QpConst c, int B, int kcap, int wdoubles, double* __restr
             else if (lane == 0) defer_list[atomicAdd(defer_cnt, 1)] = b;
         }
         if (group_all(bar_id, bar_threads, !have)) break;
-        auto mid = [&]() { if (midsync) group_all(bar_id, bar_threads, true); };
-        if (!have) mid();
+        auto mid = [&](int p) { if (p < nsync) group_all(bar_id, bar_threads, true); };
+        if (!have) { mid(0); mid(1); }
         if (have) {
             const int r = wtrial<SLOTS>(c, w, A, kcap, info, lane, mid);
             if (r > 0) { wfinish(c, w, b, B, io, info, lane); have = false; }
