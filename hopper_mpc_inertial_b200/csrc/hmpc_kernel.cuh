@@ -33,6 +33,8 @@ mpc_kernel(QpConst c, int B, int sm_count, double* __restrict__ ws, int* __restr
     // vs interior-point path); results do not depend on the order
     // list mode: only the hoppers the warp kernel deferred (hmpc_warp.cuh), in any order
     const int count = list ? *list_cnt : B;
+    // a short deferral list is latency-bound (at most one hopper per CTA): its interior points take the tiled factor
+    sys.ipm_tiled = (list && count <= (int)gridDim.x) ? 1 : 0;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_next = atomicAdd(work_ctr, 1);

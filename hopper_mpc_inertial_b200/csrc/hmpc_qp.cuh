@@ -600,6 +600,7 @@ struct LinSys {
     double flops = 0.0;   // algorithmic FLOPs of factor/solve since the last reset (same value in all threads)
     int solver_warp = 0;  // which warp of the CTA runs the substitutions
     int tiled = 0;        // 1: FP64 tensor-core tiles, all warps of the CTA (factor_tiled / solve_tiled; wide kernels)
+    int ipm_tiled = 0;    // 1: the interior point of an N <= 10 kernel may switch to the tiled factor (latency-bound launches only)
 
     __device__ inline double entry(const AOp& A, const double* wts, double dadd, double eps, int i, int j) const {
         if (i < nF) {   // i >= j
@@ -1165,7 +1166,7 @@ __device__ inline int polish_verified(const QpConst& c, Work& w, Sys& sys, const
 // On exit w.x = iterate, w.code = active-set estimate (lambda > slack).  Returns 1 when converged.
 // ------------------------------------------------------------------------------------------------
 template <class Sys>
-__device__ inline int ipm_solve(const QpConst& c, Work& w, Sys& sys, const AOp& A, SolveInfo& info) {
+__device__ inline int ipm_solve_body(const QpConst& c, Work& w, Sys& sys, const AOp& A, SolveInfo& info) {
     const int N = c.N, n = 6 * N, m = 11 * N, tid = threadIdx.x, T = blockDim.x;
     double *su = w.mv[0], *sl = w.mv[1], *lu = w.mv[2], *ll = w.mv[3], *rpu = w.mv[4], *rpl = w.mv[5];
     double *pu = w.mv[6], *pl = w.mv[7], *tv = w.mv[8], *adx = w.mv[9], *wts = w.mv[10];
@@ -1207,7 +1208,9 @@ __device__ inline int ipm_solve(const QpConst& c, Work& w, Sys& sys, const AOp& 
     }
     __syncthreads();
     ++info.nfac;
-    if (sys.factor(A, ni > 0.0 ? wts : nullptr, 0.0, 0.0, w.tmp)) return 0;
+    // N <= 10 kernels with the tiled factor switched on by ipm_solve(): one 64-double tile of scratch (w.sc is free here)
+    double* fscr = (sys.tiled && n <= 64) ? w.sc : w.tmp;
+    if (sys.factor(A, ni > 0.0 ? wts : nullptr, 0.0, 0.0, fscr)) return 0;
     for (int i = tid; i < nF; i += T) { const int vi = w.idx[i]; w.rhs[i] = -w.g[vi] - (ni > 0.0 ? A.colT(vi, tv) : 0.0); }
     sys.solve(w.rhs, w.rhs, w.sc);
     for (int i = tid; i < nF; i += T) w.x[w.idx[i]] = w.rhs[i];
@@ -1271,7 +1274,7 @@ __device__ inline int ipm_solve(const QpConst& c, Work& w, Sys& sys, const AOp& 
         }
         __syncthreads();
         ++info.nfac;
-        if (sys.factor(A, wts, 0.0, 0.0, w.tmp)) break;
+        if (sys.factor(A, wts, 0.0, 0.0, fscr)) break;
         double alpha = 1.0, sigmu = 0.0;
         for (int phase = 0; phase < 2; ++phase) {
             // complementarity targets: predictor rc = s*lam ; corrector rc = s*lam + ds*dlam - sigma*mu
@@ -1363,6 +1366,30 @@ __device__ inline int ipm_solve(const QpConst& c, Work& w, Sys& sys, const AOp& 
 // On entry (warm != 0): w.xp = time-shifted previous solution, w.code = time-shifted previous active set.
 // On exit: w.x = solution, w.code = active set (for the next tick's warm start).
 // ------------------------------------------------------------------------------------------------
+// Interior point with the factorisation switched to tensor-core tiles where the system allows it.  The Newton system
+// H + A'WA over the free variables is positive definite and of order <= 6N: at N <= 10 it fits the packed factor
+// storage as 8x8 tiles, so the factorisation and both substitutions of every iteration run through
+// LinSys::factor_tiled / solve_tiled with all warps of the CTA instead of the packed right-looking LDL' and its one-warp
+// substitution.  That halves the latency of an interior-point solve but costs throughput when every CTA of the SM is
+// in its interior point at once (measured: deferred list of <= one hopper per CTA 1.0 -> 0.5 ms, batch 4096 2.77 ->
+// 3.07 M steps/s; first tick of 131072 hoppers 184 -> 300 ms), so the kernel allows it (sys.ipm_tiled) only for a
+// deferral list no longer than its grid.  The polish that follows (order up to 7N + 2) uses the packed layout again.
+template <class Sys>
+__device__ inline int ipm_solve(const QpConst& c, Work& w, Sys& sys, const AOp& A, SolveInfo& info) {
+    const int keep = sys.tiled;
+#ifndef HMPC_HOST_EMUL
+    {
+        const int N = c.N, nt = (6 * N + 7) >> 3, kk = kkt_max(N);
+        if (sizeof(typename Sys::real) == 8 && sys.ipm_tiled && !sys.tiled && blockDim.x >= 64 && kkt_vec(N) >= 64 &&
+            nt * (nt + 1) / 2 * 64 <= kk * (kk + 1) / 2)
+            sys.tiled = 1;
+    }
+#endif
+    const int conv = ipm_solve_body(c, w, sys, A, info);
+    sys.tiled = keep;
+    return conv;
+}
+
 template <class Sys>
 __device__ inline SolveInfo solve_exact(const QpConst& c, Work& w, Sys& sys, const AOp& A, int warm) {
     const int n = 6 * c.N, tid = threadIdx.x, T = blockDim.x;
