@@ -65,9 +65,13 @@ struct QpConst {
     // order in which the persistent kernels take the hoppers: ticket i -> hopper (i * work_mul + work_add) mod B
     // (1, 0 = in order).  Results never depend on it; the stress test permutes it (HMPC_WORK_PERM, tests/test_gpu.py).
     int work_mul, work_add;
+    // optional second stage of that map (lock-step solve kernel only): a permutation of the hoppers that puts equal
+    // contact schedules next to each other (hmpc_api.cu: order_* kernels), or null
+    const int* work_order;
 };
 __device__ __forceinline__ int work_item(const QpConst& c, int i, int B) {
-    return (int)(((long long)i * c.work_mul + c.work_add) % B);
+    const int t = (int)(((long long)i * c.work_mul + c.work_add) % B);
+    return c.work_order ? c.work_order[t] : t;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -105,7 +105,7 @@ static QpConst qp_const(const hmpc_config& cfg) {
     c.eps_abs = cfg.eps_abs; c.eps_rel = cfg.eps_rel; c.rho0 = cfg.rho0; c.sigma = cfg.sigma;
     c.alpha = cfg.alpha; c.kkt_eps = cfg.kkt_eps; c.polish_tol = cfg.polish_tol; c.ipm_tol = cfg.ipm_tol;
     c.condense_flops = hmpc::flops_condense(cfg.N);
-    c.work_mul = 1; c.work_add = 0;
+    c.work_mul = 1; c.work_add = 0; c.work_order = nullptr;
     c.max_refine = 6;
     c.stagnation = 0.25;
     if (cfg.precision == HMPC_FP32) {

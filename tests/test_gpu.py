@@ -719,3 +719,27 @@ def test_warp_admm_early_exit_iterate_without_polish():
     assert da == 0
     assert np.all(sa == _lib.STATUS_INEXACT) and np.array_equal(sa, sc_) and np.array_equal(ia, ic)
     np.testing.assert_allclose(Ua, Uc, rtol=1e-7, atol=1e-7)
+
+
+def test_contact_mask_work_order_does_not_change_results(monkeypatch):
+    """The lock-step solve kernel takes the hoppers grouped by contact schedule (hmpc_api.cu: order_* kernels, a
+    counting sort on the contact masks every tick).  Scheduling only: with the grouping switched off
+    (HMPC_WORK_ORDER=0) the closed loop is bit-identical, respawns and deferrals included."""
+    B, N, n_ticks = 3000, 10, 14
+    sc = scenarios.make_batch(B, N=N, n_ticks=n_ticks, seed=8, gain_spread=2.0, perturb=1.0)
+    tabs = (T(sc["xref_tab"]), T(sc["pf_tab"]), cb64(sc["C_tab"]), T(sc["pf_switch"]))
+    res = []
+    for on in ("1", "0"):
+        monkeypatch.setenv("HMPC_WORK_ORDER", on)
+        bm = mk(B, "3f", N, on_infeasible="respawn")
+        bm.set_gains(T(sc["Qdiag"]), T(sc["Rdiag"]))
+        X = T(sc["X0"]).clone()
+        out = bm.rollout(X, *tabs, 0, n_ticks, True, log=True)
+        torch.cuda.synchronize()
+        nf, pa, ni = [a.cpu().numpy() for a in bm.solve_stats()]
+        res.append((X.cpu().numpy(), out["U_log"].cpu().numpy(), out["status"].cpu().numpy(), out["iters"].cpu().numpy(), nf, ni,
+                    bm.hot_path_info()["deferred"]))
+        bm.close()
+    for a, b in zip(res[0][:6], res[1][:6]):
+        assert np.array_equal(a, b)
+    assert res[0][6] == res[1][6] and res[0][6] > 0
