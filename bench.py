@@ -478,8 +478,9 @@ def run_b200(args):
     except Exception:
         pass
     # The solver kernels' arithmetic runs on the FP64 pipe (DMMA.8x8x4 tensor-core tiles + DFMA): that is the roofline
-    # the kernel is measured against.  It is far from it: the binding resource is instruction issue / fetch (ncu, see
-    # profiles/README.md: issue slots ~25 % busy, top stalls no_instruction / long_scoreboard / wait), not FP64 and not HBM.
+    # the kernel is measured against.  It is far from it: what binds is latency -- dependent DMMA / shuffle chains, L2 reads
+    # of the Hessian record and the lock-step barriers at 12 resident warps per SM (ncu, profiles/README.md) -- not FP64
+    # throughput and not HBM.
     kname = "mpc_prep_kernel + mpc_warp_rounds_kernel + mpc_kernel (deferred hoppers)" if hot["warps_per_sm"] else "mpc_kernel"
     roofline = {"bound": "tensor", "pipe": "FP64 (DMMA.8x8x4 tensor-core tiles and DFMA share the FP64 pipe)", "kernel": kname,
                 "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak if fp64_peak else None,
@@ -490,8 +491,10 @@ def run_b200(args):
                 "algorithmic_flops_per_launch": flops / max(nt, 1), "algorithmic_flops_per_hopper_tick": flops / max(nt, 1) / B,
                 "avg_launch_ms": mpc_s * 1e3, "share_of_step": mpc_ms / ms,
                 "launches_per_step": "prep + solve + deferred-list kernel (timed together with CUDA events around the three launches)",
-                "binding_resource": "instruction issue / fetch, not FP64 and not HBM: see profiles/README.md (ncu issue-slot "
-                                    "utilisation and stall breakdown of the same command)"}
+                "binding_resource": "dependent-issue latency at 12 resident warps per SM (shared memory: 18.9 KB of KKT factor and vectors per "
+                                    "hopper): ncu of the same command (profiles/r2ao_mpc_kernel_ncu.txt) shows issue slots 30 % busy, FP64 pipe "
+                                    "6.5 %, DRAM 6.5 %; stalls: fixed-latency wait 24 %, long scoreboard (L2) 24 %, lock-step barriers 19 %.  "
+                                    "Neither FP64 nor HBM binds"}
     roofline_hbm = {"bound": "hbm", "kernel": kname, "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                     "peak_source": hbm_src, "algorithmic_bytes_per_launch": bytes_tick * B,
                     "note": "reported for completeness: arithmetic intensity >> machine balance, HBM does not bind"}
