@@ -98,6 +98,8 @@ struct hmpc_handle {
     int* defer_list = nullptr;    // [B] hoppers the warp kernel handed to the CTA kernel this tick
     // work order of the lock-step solve kernel: hoppers grouped by contact schedule (order_* kernels)
     int* work_order = nullptr;    // [B] permutation, rebuilt every tick
+    double* warm = nullptr;       // [B][warm_stride] warm blocks of the warp kernels (MpcIo::warm)
+    int8_t* warm_ok = nullptr;    // [B]
     int* order_cnt = nullptr;     // [2][kOrderBuckets] bucket sizes / cursors
     int order_on = 1;             // HMPC_WORK_ORDER=0 switches the grouping off
     // contact gate of the simulator (hmpc_set_contact_gate)
@@ -490,6 +492,8 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
             h->warp_grid = (int)std::min<size_t>(((size_t)B + wpc - 1) / wpc, (size_t)h->sm_count);
             h->pstride = hmpc::prep_stride((int)N);
             if ((e = cudaMalloc((void**)&h->prep, B * h->pstride * 8)) != cudaSuccess ||
+                (e = cudaMalloc((void**)&h->warm, B * (size_t)hmpc::warm_stride_doubles((int)N) * 8)) != cudaSuccess ||
+                (e = cudaMalloc((void**)&h->warm_ok, B)) != cudaSuccess || (e = cudaMemset(h->warm_ok, 0, B)) != cudaSuccess ||
                 (e = cudaMalloc((void**)&h->prep_flag, B * 4)) != cudaSuccess) {
                 hmpc_destroy(h);
                 return fail(HMPC_ERR_ALLOC, std::string("cudaMalloc QP records: ") + cudaGetErrorString(e));
@@ -546,6 +550,8 @@ int hmpc_create(const hmpc_config* cfg, hmpc_handle** out) {
             h->warp_grid = (int)std::min<size_t>(want, (size_t)h->sm_count * (best_w / best_wpc));
             h->pstride = hmpc::prep_stride((int)N);
             if ((e = cudaMalloc((void**)&h->prep, B * h->pstride * 8)) != cudaSuccess ||
+                (e = cudaMalloc((void**)&h->warm, B * (size_t)hmpc::warm_stride_doubles((int)N) * 8)) != cudaSuccess ||
+                (e = cudaMalloc((void**)&h->warm_ok, B)) != cudaSuccess || (e = cudaMemset(h->warm_ok, 0, B)) != cudaSuccess ||
                 (e = cudaMalloc((void**)&h->prep_flag, B * 4)) != cudaSuccess) {
                 hmpc_destroy(h);
                 return fail(HMPC_ERR_ALLOC, std::string("cudaMalloc QP records: ") + cudaGetErrorString(e));
@@ -585,7 +591,7 @@ int hmpc_destroy(hmpc_handle* h) {
     cudaFree(h->win_xref); cudaFree(h->win_pf); cudaFree(h->win_C); cudaFree(h->win_sw);
     cudaFree(h->gate_glob);
     cudaFree(h->prep); cudaFree(h->prep_flag); cudaFree(h->defer_list); cudaFree(h->n_defer);
-    cudaFree(h->work_order); cudaFree(h->order_cnt);
+    cudaFree(h->work_order); cudaFree(h->order_cnt); cudaFree(h->warm); cudaFree(h->warm_ok);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     delete h;
     return HMPC_OK;
@@ -744,6 +750,9 @@ hmpc::MpcIo make_io(hmpc_handle* h, const double* x_in, const double* x_ref, con
     hmpc::MpcIo io;
     io.x_in = x_in; io.x_ref = x_ref; io.pf = pf; io.Cbits = Cbits; io.Qd = h->Qd; io.Rd = h->Rd;
     io.Xsol = h->Xsol; io.Usol = h->Usol; io.code = h->code; io.valid = h->valid;
+    if (h->warm && !getenv("HMPC_NO_WARM_BLOCK")) {       // experiment switch: the warp kernels gather the strided state only
+        io.warm = h->warm; io.warm_ok = h->warm_ok; io.warm_stride = hmpc::warm_stride_doubles(h->cfg.N);
+    }
     io.U_out = U; io.X_out = Xsol; io.U0_out = U0;
     io.status = status ? status : h->st_tmp; io.iters = iters ? iters : h->it_tmp;
     io.st_tick = h->st_tick; io.nfac = h->nfac; io.path = h->path; io.ninf = h->ninf; io.flops = h->flops;

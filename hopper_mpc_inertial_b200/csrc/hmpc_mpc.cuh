@@ -87,6 +87,12 @@ struct MpcIo {
     double *U_out, *X_out, *U0_out;
     int32_t *status, *iters, *st_tick, *nfac, *path, *ninf;
     double* flops;                // [B] algorithmic FLOPs (may be null)
+    // warp kernels only (may be null): the next tick's warm start of every hopper they finish, shifted already and
+    // contiguous per hopper -- [B][warm_stride] doubles: inputs [n -> 8] | active set [m bytes -> 8] -- and whether it
+    // is the hopper's newest state (1) or the CTA kernel has written Usol / code since (0)
+    double* warm = nullptr;
+    int8_t* warm_ok = nullptr;
+    int warm_stride = 0;
     int init, accumulate, respawn;
 };
 
@@ -204,6 +210,7 @@ __device__ inline void mpc_hopper(const QpConst& c, Work& w, Sys& sys, const AOp
     if (io.U0_out) for (int i = tid; i < 6; i += T) io.U0_out[(size_t)i * B + b] = w.x[i];
     if (tid == 0) {
         io.valid[b] = (st == ST_SOLVED || st == ST_INEXACT) ? 1 : 0;
+        if (io.warm_ok) io.warm_ok[b] = 0;        // Usol / code above are this hopper's newest state, not its warm block
         if (io.flops) io.flops[b] = (io.accumulate ? io.flops[b] : 0.0) + sys.flops;
         io.st_tick[b] = st;
         io.path[b] = path;

@@ -100,6 +100,8 @@ __host__ __device__ inline size_t prep_stride(int N) {
 }
 // ADMM mode: three more m-vectors per warp (z, y, rho) behind the slice of warp_work_doubles
 __host__ __device__ inline size_t warp_admm_doubles(int N) { return (3 * 11 * (size_t)N + 1) & ~(size_t)1; }
+// warm block of a hopper (MpcIo::warm): shifted inputs [n -> 8] | shifted active set [m bytes -> 8 doubles]
+__host__ __device__ inline int warm_stride_doubles(int N) { return ((6 * N + 7) & ~7) + ((((11 * N + 7) / 8) + 7) & ~7); }
 constexpr int kPrepKcap = 8;      // the prep kernel's per-warp slice: same carve, smallest factor (unused there)
 
 __device__ inline void wcarve(WWork& w, double* base, int N, int kcap) {
@@ -913,29 +915,51 @@ __device__ inline int wfetch(const QpConst& c, WWork& w, double* rec, const int3
     const double* rx = rh + ((N + 7) & ~7);
     const int f = *flag;
     const uint64_t bits = io.Cbits[b];
-    double gq[2] = {0.0, 0.0}, uq[2] = {0.0, 0.0};
-    int8_t cq[4] = {0, 0, 0, 0};
+    double gq[2] = {0.0, 0.0}, uq[2] = {0.0, 0.0}, uw[2] = {0.0, 0.0};
+    int8_t cq[4] = {0, 0, 0, 0}, cw[4] = {0, 0, 0, 0};
+    // Warm start: stage k starts from the previous tick's stage k+1, the last two stages keep their own previous
+    // pattern (mpc_hopper in hmpc_mpc.cuh).  A hopper this kernel finished last tick left exactly that, contiguous, in
+    // its warm block (wfinish); otherwise it is gathered from the strided state the CTA kernel wrote.  The hoppers come
+    // in contact-schedule order, so a strided read costs a 32-byte sector per element: the block is the common case.
+    const bool blk = io.warm_ok != nullptr;
+    const int fresh = blk ? (int)io.warm_ok[b] : 0;
+    const double* wb = blk ? io.warm + (size_t)b * io.warm_stride : nullptr;
+    const int8_t* wc = blk ? reinterpret_cast<const int8_t*>(wb + ((n + 7) & ~7)) : nullptr;
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         const int i = lane + 32 * q;
         if (i < n) {
-            // warm start: stage k starts from the previous tick's stage k+1, the last two stages keep their own
-            // previous pattern (mpc_hopper in hmpc_mpc.cuh)
-            const int src = (i / 6 < N - 2) ? i + 6 : i;
             gq[q] = rg[i];
-            uq[q] = io.Usol[(size_t)src * Bs + b];
+            if (blk) uw[q] = wb[i];
         }
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int r = lane + 32 * q;
-        if (r < m) {
-            int src;
-            if (r < n) src = (r / 6 < N - 2) ? r + 6 : r;
-            else if (r < n + 4 * N) src = ((r - n) / 4 < N - 2) ? r + 4 : r;
-            else src = (r - n - 4 * N < N - 2) ? r + 1 : r;
-            cq[q] = io.code[(size_t)src * Bs + b];
+        if (r < m && blk) cw[q] = wc[r];
+    }
+    if (!fresh) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int i = lane + 32 * q;
+            if (i < n) uq[q] = io.Usol[(size_t)((i / 6 < N - 2) ? i + 6 : i) * Bs + b];
         }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int r = lane + 32 * q;
+            if (r < m) {
+                int src;
+                if (r < n) src = (r / 6 < N - 2) ? r + 6 : r;
+                else if (r < n + 4 * N) src = ((r - n) / 4 < N - 2) ? r + 4 : r;
+                else src = (r - n - 4 * N < N - 2) ? r + 1 : r;
+                cq[q] = io.code[(size_t)src * Bs + b];
+            }
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) uq[q] = uw[q];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cq[q] = cw[q];
     }
     const double hl = lane < N ? rh[lane] : 0.0;            // N <= kWarpMaxN < 32
     const double xi = lane < 12 ? rx[lane] : 0.0;
@@ -1024,9 +1048,22 @@ __device__ inline void wfinish(const QpConst& c, WWork& w, int b, int B, const M
         if (io.U_out) io.U_out[(size_t)i * Bs + b] = u[i];
     }
     for (int r = lane; r < m; r += 32) io.code[(size_t)r * Bs + b] = w.code[r];
+    if (io.warm_ok) {        // the next tick's warm start, shifted (see wfetch), contiguous: full-sector writes and reads
+        double* wb = io.warm + (size_t)b * io.warm_stride;
+        int8_t* wc = reinterpret_cast<int8_t*>(wb + ((n + 7) & ~7));
+        for (int i = lane; i < n; i += 32) wb[i] = u[(i / 6 < N - 2) ? i + 6 : i];
+        for (int r = lane; r < m; r += 32) {
+            int src;
+            if (r < n) src = (r / 6 < N - 2) ? r + 6 : r;
+            else if (r < n + 4 * N) src = ((r - n) / 4 < N - 2) ? r + 4 : r;
+            else src = (r - n - 4 * N < N - 2) ? r + 1 : r;
+            wc[r] = w.code[src];
+        }
+    }
     if (io.U0_out && lane < 6) io.U0_out[(size_t)lane * Bs + b] = u[lane];
     if (lane == 0) {
         io.valid[b] = (st == ST_SOLVED || st == ST_INEXACT) ? 1 : 0;
+        if (io.warm_ok) io.warm_ok[b] = 1;
         if (io.flops) io.flops[b] = (io.accumulate ? io.flops[b] : 0.0) + info.flops;
         io.st_tick[b] = st;
         io.path[b] = path;

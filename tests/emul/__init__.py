@@ -79,6 +79,9 @@ class EmulMpc:
         self.Usol = np.zeros((N, 6, batch))
         self.code = np.zeros((m, batch), np.int8)
         self.valid = np.zeros(batch, np.int8)
+        # warm blocks of the warp kernels (MpcIo::warm), as the library keeps them per handle
+        self.warm = np.zeros((batch, load().emul_warm_stride(int(N))))
+        self.warm_ok = np.zeros(batch, np.int8)
 
     def set_gains(self, Qd, Rd):
         self.Qd = np.ascontiguousarray(Qd, float)
@@ -96,6 +99,8 @@ class EmulMpc:
         it = np.zeros(B, np.int32)
         nf = np.zeros(B, np.int32)
         pa = np.zeros(B, np.int32)
+        load().emul_set_warm.argtypes = [C.c_void_p, C.c_void_p]
+        load().emul_set_warm(_p(self.warm), _p(self.warm_ok))
         rc = load().emul_solve(C.byref(self.cfg), _p(self.Qd), _p(self.Rd), _p(x_in), _p(x_ref), _p(pf), _p(Cbits),
                                int(bool(init)), _p(self.Xsol), _p(self.Usol), _p(self.code), _p(self.valid),
                                _p(U), _p(Xs), _p(st), _p(it), _p(nf), _p(pa))

@@ -118,6 +118,9 @@ static QpConst qp_const(const hmpc_config& cfg) {
 }
 
 static int g_emul_warp_done = 0;
+// warm blocks of the warp kernels (MpcIo::warm): owned by the Python side, one set per EmulMpc, registered before a solve
+static double* g_warm = nullptr;
+static int8_t* g_warm_ok = nullptr;
 
 extern "C" {
 
@@ -140,6 +143,7 @@ int emul_solve(const hmpc_config* cfg, const double* Qd, const double* Rd, const
     io.U_out = U; io.X_out = Xsol; io.U0_out = nullptr;
     io.status = status; io.iters = iters; io.st_tick = st_tick.data(); io.nfac = nfac; io.path = path;
     io.ninf = ninf.data(); io.flops = nullptr; io.init = init; io.accumulate = 0; io.respawn = 0;
+    if (g_warm && g_warm_ok) { io.warm = g_warm; io.warm_ok = g_warm_ok; io.warm_stride = warm_stride_doubles(N); }
     // the library's dispatch (hmpc_api.cu: launch_mpc): warm ticks go through the warp-per-hopper kernel first,
     // hoppers it defers (and everything else) through the CTA kernel
     std::vector<char> deferred(B, 1), skipw(B, 0);
@@ -179,6 +183,9 @@ int emul_solve(const hmpc_config* cfg, const double* Qd, const double* Rd, const
     return 0;
 }
 
+// register (or, with nulls, drop) the warm-block state used by the following emul_solve calls: warm [B][warm_stride_doubles(N)]
+void emul_set_warm(double* warm, int8_t* warm_ok) { g_warm = warm; g_warm_ok = warm_ok; }
+int emul_warm_stride(int N) { return warm_stride_doubles(N); }
 // hoppers the warp path finished in the most recent emul_solve
 int emul_warp_done(void) { return g_emul_warp_done; }
 // event counters of the warp emulation since the last reset ([0] = DMMA lane-calls)

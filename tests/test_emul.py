@@ -244,5 +244,6 @@ def test_warp_admm_equals_cta_admm(polish):
         np.testing.assert_allclose(X0s, X1s, rtol=1e-7, atol=1e-8)
         for em in ems:                              # keep both on the same closed loop: the CTA statement's control
             em.Usol[:] = ems[1].Usol; em.Xsol[:] = ems[1].Xsol; em.code[:] = ems[1].code
+            em.warm_ok[:] = 0                       # ... which supersedes the warp kernel's own warm blocks
         X = ems[1].sim_tick(X, U1[0], sc["pf_tab"][t], sc["pf_tab"][t + 1], sc["pf_switch"][t])
     assert warp_ticks == B * (n_ticks - 1)          # every warm tick went through the warp kernel
