@@ -579,6 +579,37 @@ __device__ inline int wfactor(const QpConst& c, WWork& w, const AOp& A, int nF, 
     const double mv0 = (8 * Jb + 2 * t < nF) ? 1.0 : 0.0, mv1 = (8 * Jb + 2 * t + 1 < nF) ? 1.0 : 0.0;
     const bool ondiag0 = (2 * t == g), ondiag1 = (2 * t + 1 == g);
     int bad = 0;
+#ifdef HMPC_BULK_GATHER
+    // Hessian block of K, gathered up front: tile (I, J) of the variable rows is written where V(I, J) will live (each
+    // lane its own two entries), eight tiles -- sixteen L2 loads per lane -- in flight at a time, instead of one
+    // gather per tile inside the elimination (ncu: a third of the kernel's long-scoreboard stalls).  Entries outside the
+    // variable block (i or j >= nF) are written as 0 and produced by the elimination loop as before.
+    {
+        const int ntv = (nF + 7) >> 3, ntiles = ntv * (ntv + 1) / 2;
+        int I = 0, J = 0;
+#pragma unroll 1
+        for (int base = 0; base < ntiles; base += 8) {
+            d2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                v[u] = d2{0.0, 0.0};
+                if (base + u < ntiles) {
+                    const int i = 8 * I + g, j0 = 8 * J + 2 * t;
+                    if (i < nF) {
+                        const int ri = (int)w.idx[i];
+                        if (j0 < nF) v[u].x = w.Hc[(int)w.idx[j0] * w.ld + ri];
+                        if (j0 + 1 < nF) v[u].y = w.Hc[(int)w.idx[j0 + 1] * w.ld + ri];
+                    }
+                    if (++J > I) { ++I; J = 0; }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (base + u < ntiles) st2(L + 64 * (base + u) + fo, v[u].x, v[u].y);
+        }
+        __syncwarp();
+    }
+#endif
 #pragma unroll 1
     for (int J = 0; J < nt; ++J) {
         const int j0 = 8 * J + 2 * t;
@@ -598,7 +629,11 @@ __device__ inline int wfactor(const QpConst& c, WWork& w, const AOp& A, int nF, 
             double k0, k1;
             if (8 * I + 8 <= nF) {                                   // variables x variables (H is stored symmetric)
                 const int ri = (int)w.idx[i];
+#ifdef HMPC_BULK_GATHER
+                { const d2 kk = ld2(L + tile_off(I, J) + fo); k0 = kk.x; k1 = kk.y; }
+#else
                 k0 = hc0[ri]; k1 = hc1[ri];
+#endif
                 if (ADMM) {                                          // ADMM operator (i >= j0, j0 + 1 may exceed i: unused)
                     k0 += wweights(w, A, ri, (int)w.idx[j0]);
                     k1 += wweights(w, A, ri, (int)w.idx[j0 + 1]);
@@ -611,7 +646,12 @@ __device__ inline int wfactor(const QpConst& c, WWork& w, const AOp& A, int nF, 
                 const int ri = (int)w.idx[i];
                 const bool v0 = j0 < nF, v1 = j0 + 1 < nF;
                 const int cj0 = v0 ? (int)w.idx[j0] : 0, cj1 = v1 ? (int)w.idx[j0 + 1] : 0;
+#ifdef HMPC_BULK_GATHER
+                const d2 kk = ld2(L + tile_off(I, J) + fo);
+                const double h0 = kk.x, h1 = kk.y;
+#else
                 const double h0 = w.Hc[cj0 * w.ld + ri], h1 = w.Hc[cj1 * w.ld + ri];
+#endif
                 k0 = v0 ? h0 : 0.0; k1 = v1 ? h1 : 0.0;
                 if (ADMM) {
                     if (v0) k0 += wweights(w, A, ri, cj0);
