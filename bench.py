@@ -492,8 +492,8 @@ def run_b200(args):
                 "avg_launch_ms": mpc_s * 1e3, "share_of_step": mpc_ms / ms,
                 "launches_per_step": "prep + solve + deferred-list kernel (timed together with CUDA events around the three launches)",
                 "binding_resource": "dependent-issue latency at 12 resident warps per SM (shared memory: 18.9 KB of KKT factor and vectors per "
-                                    "hopper): ncu of the same command (profiles/r2ao_mpc_kernel_ncu.txt) shows issue slots 30 % busy, FP64 pipe "
-                                    "6.5 %, DRAM 6.5 %; stalls: fixed-latency wait 24 %, long scoreboard (L2) 24 %, lock-step barriers 19 %.  "
+                                    "hopper): ncu of the same command (profiles/r2ar_mpc_kernel_ncu.txt) shows issue slots 31 % busy, FP64 pipe "
+                                    "6.7 %, DRAM 6.1 %; stalls: fixed-latency wait 25 %, long scoreboard (L2) 23 %, lock-step barriers 18 %.  "
                                     "Neither FP64 nor HBM binds"}
     roofline_hbm = {"bound": "hbm", "kernel": kname, "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                     "peak_source": hbm_src, "algorithmic_bytes_per_launch": bytes_tick * B,
